@@ -1,0 +1,78 @@
+"""CPU: pin the oracle (oracle/neat_oracle.py) against golden vectors produced by the
+unmodified reference (oracle/make_golden.py).  No GPU, no /root/reference needed."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import neat_oracle as O
+import golden_io as G
+
+CASES = list(G.CASES)
+T = lambda a: torch.from_numpy(np.asarray(a))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_stage_outputs(name):
+    """get_sdf_vals / get_outputs (hand-derived normal) / both heads vs the reference modules."""
+    g, conf, sd = G.load(name)
+    P, _ = G.oracle_params(conf, sd)
+    x, d = T(g["stage_points"]), T(g["stage_dirs"])
+    assert G.rel_err(O.sdf_vals(P, x), g["stage_sdf_vals"]) < 2e-6
+    sdf, feat, grad, _ = O.sdf_outputs(P, x)
+    assert G.rel_err(sdf, g["stage_sdf"]) < 2e-6
+    assert G.rel_err(feat, g["stage_feat"]) < 2e-6
+    assert G.rel_err(grad, g["stage_grad"]) < 2e-5
+    # heads are checked on the reference's own (sdf, feat, grad) so errors do not compound
+    gr, ft = T(g["stage_grad"]), T(g["stage_feat"])
+    assert G.rel_err(O.rendering_forward(P, x, gr, d, ft), g["stage_rgb"]) < 2e-6
+    assert G.rel_err(O.attraction_forward(P, x, gr, d, ft), g["stage_lines3d"]) < 2e-6
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_eval_forward(name):
+    """Full eval-mode forward (bit-deterministic in the reference) incl. the error-bound sampler."""
+    g, conf, sd = G.load(name)
+    P, _ = G.oracle_params(conf, sd)
+    out = O.neat_forward(P, G.sampler_conf(conf), T(g["in_intrinsics"][0]), T(g["in_pose"][0]),
+                         T(g["in_uv"][0]), T(g["in_uv_proj"][0]), training=False)
+    assert out["z_vals"].shape == g["eval_z_vals"].shape
+    # the sampler takes discrete decisions (bisection on the error bound, searchsorted), so a few
+    # samples in zero-weight regions may land elsewhere under fp32 reassociation; the rendered
+    # outputs below are the parity statement, z_vals is checked as "almost all identical".
+    dz = np.abs(out["z_vals"].numpy() - g["eval_z_vals"])
+    assert (dz > 2e-4).mean() < 0.03
+    for k, tol in (("rgb_values", 1e-4), ("depth", 1e-4), ("points3d", 1e-4), ("lines3d", 1e-4),
+                   ("lines2d", 1e-4), ("lines2d_calib", 1e-4), ("l3d", 1e-3), ("sdf", 1e-4),
+                   ("normal_map", 1e-4)):
+        assert G.rel_err(out[k], g["eval_" + k]) < tol, k
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_train_forward_loss_backward(name):
+    """Training forward with replayed CPU-generator draws, the loss, and every parameter gradient
+    (autograd through the oracle's hand-derived normal pass == the reference's double backward)."""
+    g, conf, sd = G.load(name)
+    P, leaves = G.oracle_params(conf, sd, track=True)
+    out = O.neat_forward(P, G.sampler_conf(conf), T(g["in_intrinsics"][0]), T(g["in_pose"][0]),
+                         T(g["in_uv"][0]), T(g["in_uv_proj"][0]), gt_vertices=T(g["wf_vertices"]),
+                         training=True, rnd=G.train_randoms(g))
+    for k, tol in (("rgb_values", 1e-4), ("lines3d", 1e-4), ("lines2d_calib", 1e-4), ("grad_theta", 1e-4),
+                   ("j3d_local", 1e-4), ("j3d_global", 1e-5), ("j2d_local_calib", 1e-4)):
+        assert out[k].shape == g["train_" + k].shape, k
+        assert G.rel_err(out[k].detach(), g["train_" + k]) < tol, k
+    lo = O.neat_loss(out, T(g["in_rgb"][0]), T(g["in_lines2d"][0]), out["K"])
+    for k in ("loss", "rgb_loss", "eikonal_loss", "line_loss", "l2d_loss", "j3d_loss", "j2d_loss"):
+        assert abs(float(lo[k]) - float(g["loss_" + k])) <= 2e-5 * max(1.0, abs(float(g["loss_" + k]))), k
+    assert int(lo["count"]) == int(g["loss_count"])
+    lo["loss"].backward()
+    checked = 0
+    for n, t in leaves.items():
+        if "gstat_" + n not in g:
+            continue
+        gr = t.grad.numpy().astype(np.float64).ravel()
+        ref_norm = g["gstat_" + n][2]
+        got = gr[g["gidx_" + n]]
+        assert np.abs(got - g["gval_" + n]).max() <= 2e-4 * max(ref_norm, 1e-8) + 1e-7, n
+        assert abs(np.sqrt((gr * gr).sum()) - ref_norm) <= 1e-3 * max(ref_norm, 1e-8), n
+        checked += 1
+    assert checked >= 60
