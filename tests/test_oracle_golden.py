@@ -42,9 +42,10 @@ def test_eval_forward(name):
     dz = np.abs(out["z_vals"].numpy() - g["eval_z_vals"])
     assert (dz > 2e-4).mean() < 0.03
     for k, tol in (("rgb_values", 1e-4), ("depth", 1e-4), ("points3d", 1e-4), ("lines3d", 1e-4),
-                   ("lines2d", 1e-4), ("lines2d_calib", 1e-4), ("l3d", 1e-3), ("sdf", 1e-4),
-                   ("normal_map", 1e-4)):
+                   ("lines2d", 1e-4), ("lines2d_calib", 1e-4), ("l3d", 1e-3), ("normal_map", 1e-4)):
         assert G.rel_err(out[k], g["eval_" + k]) < tol, k
+    # `sdf` is the SDF at the composited surface point, i.e. ~0 (|s| ~ 1e-3): absolute tolerance
+    assert np.abs(out["sdf"].numpy() - g["eval_sdf"]).max() < 2e-6
 
 
 @pytest.mark.parametrize("name", CASES)
