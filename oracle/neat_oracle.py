@@ -129,13 +129,15 @@ def embed_jacobian_diag(x, n_freq):
 def softplus100(z):
     """nn.Softplus(beta=100, threshold=20)."""
     bz = z * SOFTPLUS_BETA
-    return torch.where(bz > SOFTPLUS_THRESHOLD, z, torch.log1p(torch.exp(bz)) / SOFTPLUS_BETA)
+    # the unselected branch is evaluated on a clamped argument so that autograd never sees inf/inf
+    soft = torch.log1p(torch.exp(bz.clamp(max=SOFTPLUS_THRESHOLD))) / SOFTPLUS_BETA
+    return torch.where(bz > SOFTPLUS_THRESHOLD, z, soft)
 
 
 def softplus100_d1(z):
     """sigma'(z) as autograd computes it for Softplus: sigmoid(beta z), 1 above the threshold."""
     bz = z * SOFTPLUS_BETA
-    e = torch.exp(bz)
+    e = torch.exp(bz.clamp(max=SOFTPLUS_THRESHOLD))
     return torch.where(bz > SOFTPLUS_THRESHOLD, torch.ones_like(z), e / (e + 1.0))
 
 
