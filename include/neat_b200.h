@@ -1,0 +1,159 @@
+/* neat_b200 -- C ABI of the B200-native NEAT attraction-field training step.
+ *
+ * The reference (cherubicXN/neat) has no native boundary: its hot path is Python calling ATen.
+ * Each entry point below replaces one reference function (cited as file:line relative to the
+ * reference tree) and is what a maintainer binds from the reference's Python side with ctypes
+ * (see INTEGRATION.md).  Conventions:
+ *   - all pointers are DEVICE pointers unless the name ends in _host; fp32 unless stated;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous, never synchronise and
+ *     never allocate (scratch comes from the caller, sizes from neat_workspace_bytes);
+ *   - return value 0 = success, otherwise a negative neat_status / positive cudaError_t.
+ */
+#ifndef NEAT_B200_H
+#define NEAT_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct neat_ctx neat_ctx;
+
+enum neat_status { NEAT_OK = 0, NEAT_EINVAL = -1, NEAT_ENOMEM = -2, NEAT_ENODEV = -3, NEAT_EUNSUPPORTED = -4 };
+
+/* Network shapes: code/confs/dtu.conf:28-70, code/model/networks/neat_wfr_rend_a.py:14-255 */
+typedef struct {
+  int sdf_layers;       /* number of Linear layers of ImplicitNetwork (len(dims)+1 = 9)            */
+  int sdf_hidden;       /* hidden width (256); multiple of 32, <= 256                               */
+  int sdf_skip;         /* skip_in[0] (4): input of this layer is [h, PE(x)] / sqrt(2); -1 = none  */
+  int multires;         /* positional-encoding octaves of ImplicitNetwork (6)                       */
+  int feat;             /* feature_vector_size (256)                                                */
+  int head_layers;      /* Linear layers of the rendering / attraction nets (5)                     */
+  int head_hidden;      /* their hidden width (256)                                                 */
+  int multires_view;    /* view-direction octaves of RenderingNetwork (4); attraction net uses 0   */
+  float sphere_radius;  /* scene_bounding_sphere (3.0)                                              */
+  float sphere_scale;   /* ImplicitNetwork.sphere_scale (20.0)                                      */
+} neat_net_config;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int neat_create(const neat_net_config* cfg, neat_ctx** out);
+void neat_destroy(neat_ctx* ctx);
+const char* neat_last_error(void);
+
+/* Flat fp32 parameter buffer shared with the host framework (effective weights, i.e. weight_norm
+ * already applied: neat_wfr_rend_a.py:71-72):
+ *   for net in (implicit, rendering, attraction): for layer l: W_l [out,in] row-major, then b_l [out].
+ * The gradient buffer produced by the backward entry points has the same layout.              */
+size_t neat_param_count(const neat_ctx* ctx);
+/* net: 0 implicit, 1 rendering, 2 attraction; kind: 0 weight, 1 bias.  Returns float offset or -1. */
+long neat_param_offset(const neat_ctx* ctx, int net, int layer, int kind);
+/* in/out features of a layer; returns 0 or NEAT_EINVAL */
+int neat_layer_dims(const neat_ctx* ctx, int net, int layer, int* in_features, int* out_features);
+
+/* Re-pack the flat parameters into tcgen05 operand slabs (bf16 hi/lo planes).  Call once per
+ * optimizer step, before any of the entry points below.                                        */
+int neat_pack_weights(neat_ctx* ctx, const float* flat_params, void* stream);
+
+/* ---- ImplicitNetwork.get_sdf_vals (neat_wfr_rend_a.py:131-137) ----------------------------- */
+/* points x[M,3] -> sdf[M] = min(net(x)[0], sphere_scale * (sphere_radius - |x|))               */
+int neat_sdf_points(neat_ctx* ctx, const float* x, int M, float* sdf, void* stream);
+/* the sampler's form (ray_sampler.py:146-151): x = o + z * d for z[R,n]; o is [R,3] (o_stride 3)
+ * or one camera centre [3] (o_stride 0); sdf[R,n]                                              */
+int neat_sdf_rays(neat_ctx* ctx, const float* rays_o, int o_stride, const float* rays_d, const float* z, int R,
+                  int n, float* sdf, void* stream);
+
+/* ---- ErrorBoundSampler.get_z_vals (code/model/ray_sampler.py:130-283) ------------------------ */
+typedef struct {
+  int n_eval;      /* N_samples_eval (128): samples added per iteration; <= 128                   */
+  int n_final;     /* N_samples (64)                                                              */
+  int n_extra;     /* N_samples_extra (32); n_final + 2 + n_extra <= 128                          */
+  int beta_iters;  /* bisection steps (10)                                                        */
+  int max_iters;   /* max_total_iters (5); n_eval * max_iters <= 640                              */
+  float near_;     /* ray_sampler.near (0)                                                        */
+  float far_;      /* 2 * scene_bounding_sphere                                                   */
+  float eps;       /* error bound target (0.1)                                                    */
+  float beta_min;  /* density.beta_min (1e-4): beta0 = |density.beta| + beta_min                  */
+} neat_sampler_config;
+
+size_t neat_sampler_workspace_bytes(int R);
+/* Phase 1: stratified depths, the iterative SDF queries (tensor-core kernel), error-bound bisection and
+ * inverse-CDF up-sampling until convergence; no host synchronisation (a device state word replaces
+ * `beta.max() > beta0`, ray_sampler.py:200).  t_rand [R,n_eval] and u_final [R,n_final] are the two
+ * torch.rand draws of a training call (ray_sampler.py:87,234) or NULL in eval mode (linspace).
+ * n_iters_dev (device int, may be NULL) receives k.                                              */
+int neat_sampler_run(neat_ctx* ctx, const neat_sampler_config* cfg, const float* rays_o, int o_stride,
+                     const float* rays_d, int R, const float* beta_param, const float* t_rand,
+                     const float* u_final, void* workspace, int* n_iters_dev, void* stream);
+/* Phase 2: near / far / extra columns, final sort, eikonal depth (ray_sampler.py:259-276).
+ * extra_idx: int64 table [max_iters][n_extra]; row k-1 holds the columns of z[R, n_eval*k] to add
+ * (training: randperm(L)[:n_extra], eval: linspace(0, L-1, n_extra).long()).  eik_idx [R] int64 or NULL
+ * (eval: column 0).  z_vals [R, n_final+2+n_extra], z_eik [R].                                   */
+int neat_sampler_finish(neat_ctx* ctx, const neat_sampler_config* cfg, int R, const int64_t* extra_idx,
+                        const int64_t* eik_idx, void* workspace, float* z_vals, float* z_eik, void* stream);
+
+/* ---- render points ------------------------------------------------------------------------- */
+/* A batch of M points, either explicit (x [M,3], optional per-point view dirs [M,3]) or generated on the
+ * fly as x = o + z d, M = R*S, point index = ray*S + sample (neat_wfr_rend_a.py:392-398).        */
+typedef struct {
+  const float* x;       /* explicit points or NULL                                                 */
+  const float* dirs;    /* explicit view directions or NULL (then rays_d[ray])                     */
+  const float* rays_o;  /* [3] (o_stride 0) or [R,3] (o_stride 3)                                  */
+  const float* rays_d;  /* [R,3]                                                                   */
+  const float* z;       /* [R,S]                                                                   */
+  int o_stride, R, S, M;
+} neat_points;
+
+/* ImplicitNetwork.get_outputs (clamp=1, neat_wfr_rend_a.py:111-129) / .gradient (clamp=0, :98-109):
+ * sdf [M] (may be NULL), grad [M,3] = d sdf / d x by the analytic reverse pass, act [M] (NULL ok) = 1
+ * where the network (not the bounding sphere) supplies the sdf, feat_tiles = the feature vectors as
+ * bf16 hi/lo operand tiles for neat_head_forward (NULL ok).  `save` is scratch: with training=1 it is
+ * the per-tile record the backward pass reads.                                                   */
+size_t neat_feat_tiles_bytes(int M);
+size_t neat_sdf_save_bytes(const neat_ctx* ctx, int M, int training);
+int neat_sdf_outputs(neat_ctx* ctx, const neat_points* pts, int clamp, int training, float* sdf, float* grad,
+                     float* act, void* feat_tiles, void* save, void* stream);
+
+/* RenderingNetwork.forward (head 0, :235-255) -> rgb [M,3];  AttractionFieldNetwork.forward (head 1,
+ * :175-197) -> lines3d [M,2,3].  normals [M,3] and feat_tiles come from neat_sdf_outputs.          */
+size_t neat_head_save_bytes(const neat_ctx* ctx, int M);
+int neat_head_forward(neat_ctx* ctx, int head, const neat_points* pts, const float* normals,
+                      const void* feat_tiles, int training, void* save, float* out, void* stream);
+
+/* rend_util.get_camera_params (code/utils/rend_util.py:55-81): uv [R,2], pose [4,4], K [4,4] ->
+ * dirs [R,3] (unit), cam [3]                                                                     */
+int neat_camera_rays(const float* uv, const float* pose, const float* K, int R, float* dirs, float* cam,
+                     void* stream);
+
+/* LaplaceDensity + VolSDFNetwork.volume_rendering + the weighted sums of VolSDFNetwork.forward
+ * (density.py:21-30, neat_wfr_rend_a.py:404-429, 540-554, 530-536)                               */
+typedef struct {
+  int R, S;
+  const float* z;          /* [R,S]   */
+  const float* sdf;        /* [R,S]   */
+  const float* rgb;        /* [R,S,3] */
+  const float* lines;      /* [R,S,6] */
+  const float* normals;    /* [R,S,3] or NULL (no normal map) */
+  const float* rays_o;     /* [3]     */
+  const float* rays_d;     /* [R,3]   */
+  const float* beta_param; /* density.beta */
+  float beta_min;
+  float* weights;          /* [R,S]   */
+  float* rgb_values;       /* [R,3]   */
+  float* lines3d;          /* [R,6]   */
+  float* depth;            /* [R]     */
+  float* points3d;         /* [R,3]   */
+  float* normal_map;       /* [R,3] or NULL */
+} neat_composite_args;
+int neat_composite_forward(const neat_composite_args* a, void* stream);
+
+/* project2D + the uv_proj ray / tangent-plane intersection (neat_wfr_rend_a.py:317-331, 433-456).
+ * pose_inv [16] receives pose^-1.  lines2d, lines2d_calib [R,2,2]; l3d [R,3].                    */
+int neat_line_geometry(int R, const float* pose, const float* K, const float* uv_proj, const float* points3d,
+                       const float* grad3d, const float* lines3d, float* pose_inv, float* lines2d,
+                       float* lines2d_calib, float* l3d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEAT_B200_H */

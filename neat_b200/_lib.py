@@ -1,0 +1,89 @@
+"""ctypes binding of libneat_b200.so (include/neat_b200.h).  No fallback: if the shared library is
+missing or a call fails, an exception is raised."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libneat_b200.so")
+
+
+class NeatError(RuntimeError):
+    pass
+
+
+class NetConfig(ctypes.Structure):
+    _fields_ = [("sdf_layers", ctypes.c_int), ("sdf_hidden", ctypes.c_int), ("sdf_skip", ctypes.c_int),
+                ("multires", ctypes.c_int), ("feat", ctypes.c_int), ("head_layers", ctypes.c_int),
+                ("head_hidden", ctypes.c_int), ("multires_view", ctypes.c_int),
+                ("sphere_radius", ctypes.c_float), ("sphere_scale", ctypes.c_float)]
+
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+# name -> (restype, argtypes); every symbol declared in include/neat_b200.h
+SIGNATURES = {
+    "neat_create": (_I, [ctypes.POINTER(NetConfig), ctypes.POINTER(_P)]),
+    "neat_destroy": (None, [_P]),
+    "neat_last_error": (ctypes.c_char_p, []),
+    "neat_param_count": (ctypes.c_size_t, [_P]),
+    "neat_param_offset": (ctypes.c_long, [_P, _I, _I, _I]),
+    "neat_layer_dims": (_I, [_P, _I, _I, ctypes.POINTER(_I), ctypes.POINTER(_I)]),
+    "neat_pack_weights": (_I, [_P, _P, _P]),
+    "neat_sdf_points": (_I, [_P, _P, _I, _P, _P]),
+    "neat_sdf_rays": (_I, [_P, _P, _I, _P, _P, _I, _I, _P, _P]),
+    "neat_sampler_workspace_bytes": (ctypes.c_size_t, [_I]),
+    "neat_sampler_run": (_I, [_P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P]),
+    "neat_sampler_finish": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P]),
+    "neat_feat_tiles_bytes": (ctypes.c_size_t, [_I]),
+    "neat_sdf_save_bytes": (ctypes.c_size_t, [_P, _I, _I]),
+    "neat_sdf_outputs": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "neat_head_save_bytes": (ctypes.c_size_t, [_P, _I]),
+    "neat_head_forward": (_I, [_P, _I, _P, _P, _P, _I, _P, _P, _P]),
+    "neat_camera_rays": (_I, [_P, _P, _P, _I, _P, _P, _P]),
+    "neat_composite_forward": (_I, [_P, _P]),
+    "neat_line_geometry": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+}
+
+
+class Points(ctypes.Structure):
+    _fields_ = [("x", _P), ("dirs", _P), ("rays_o", _P), ("rays_d", _P), ("z", _P),
+                ("o_stride", _I), ("R", _I), ("S", _I), ("M", _I)]
+
+
+class CompositeArgs(ctypes.Structure):
+    _fields_ = [("R", _I), ("S", _I), ("z", _P), ("sdf", _P), ("rgb", _P), ("lines", _P), ("normals", _P),
+                ("rays_o", _P), ("rays_d", _P), ("beta_param", _P), ("beta_min", ctypes.c_float),
+                ("weights", _P), ("rgb_values", _P), ("lines3d", _P), ("depth", _P), ("points3d", _P),
+                ("normal_map", _P)]
+
+
+class SamplerConfig(ctypes.Structure):
+    _fields_ = [("n_eval", ctypes.c_int), ("n_final", ctypes.c_int), ("n_extra", ctypes.c_int),
+                ("beta_iters", ctypes.c_int), ("max_iters", ctypes.c_int), ("near_", ctypes.c_float),
+                ("far_", ctypes.c_float), ("eps", ctypes.c_float), ("beta_min", ctypes.c_float)]
+
+_lib = None
+
+
+def load():
+    """Load the shared library (building it is __graft_entry__.build()'s / neat_b200.build's job)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NeatError("%s not found: run `python -m neat_b200.build` (nvcc, sm_100a). "
+                        "There is no CPU or PyTorch fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    lib.neat_debug_set_desc_swap.restype = _I
+    lib.neat_debug_set_desc_swap.argtypes = [_I]
+    _lib = lib
+    return lib
+
+
+def check(code):
+    if code != 0:
+        raise NeatError("neat_b200 call failed (%d): %s" % (code, load().neat_last_error().decode()))

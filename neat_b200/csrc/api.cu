@@ -1,0 +1,458 @@
+// C ABI of neat_b200 (include/neat_b200.h): context, weight packing, kernel launches.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "plan.h"
+#include "composite.cuh"
+#include "heads.cuh"
+#include "sampler.cuh"
+#include "sdf_query.cuh"
+#include "sdf_render.cuh"
+
+using namespace neat;
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return static_cast<int>(e);
+}
+#define CK(call)                                        \
+  do {                                                  \
+    cudaError_t e__ = (call);                           \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+template <class T>
+cudaError_t upload(const std::vector<T>& h, T** d) {
+  cudaError_t e = cudaMalloc(d, std::max<size_t>(h.size(), 1) * sizeof(T));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+constexpr int QUERY_STAGES = 4;
+constexpr int RENDER_STAGES = 4;
+inline size_t engine_smem_bytes(int stages) {
+  return (stages == 4 ? sizeof(EngineSmem<4>) : sizeof(EngineSmem<3>)) + 1024;
+}
+
+Step mk_step(const PLayer& w, int d_col, int wait_a, int commit_d) {
+  Step s{};
+  s.w = w;
+  s.d_col = static_cast<uint16_t>(d_col);
+  s.wait_a = static_cast<uint8_t>(wait_a);
+  s.commit_d = static_cast<uint8_t>(commit_d);
+  return s;
+}
+}  // namespace
+
+struct neat_ctx {
+  Plan plan;
+  int device = 0;
+  int num_sms = 0;
+  uint8_t* packed = nullptr;
+  int32_t* g_src = nullptr;
+  uint32_t *g_dst_hi = nullptr, *g_dst_lo = nullptr;
+  float* g_scale = nullptr;
+  int32_t* g_fsrc = nullptr;
+  uint32_t* g_fdst = nullptr;
+  Program prog_query, prog_render, prog_head[2];
+};
+
+// ---------------------------------------------------------------- packing kernels
+__global__ void pack_bf16_kernel(const float* __restrict__ flat, const int32_t* __restrict__ src,
+                                 const uint32_t* __restrict__ dst_hi, const uint32_t* __restrict__ dst_lo,
+                                 const float* __restrict__ scale, int n, __nv_bfloat16* __restrict__ packed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = src[i];
+  const float v = s >= 0 ? flat[s] * scale[i] : 0.f;
+  __nv_bfloat16 hi, lo;
+  split_bf16(v, hi, lo);
+  packed[dst_hi[i]] = hi;
+  packed[dst_lo[i]] = lo;
+}
+__global__ void pack_f32_kernel(const float* __restrict__ flat, const int32_t* __restrict__ src,
+                                const uint32_t* __restrict__ dst, int n, float* __restrict__ packed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = src[i];
+  packed[dst[i]] = s >= 0 ? flat[s] : 0.f;
+}
+
+extern "C" {
+
+const char* neat_last_error(void) { return g_err.c_str(); }
+
+int neat_create(const neat_net_config* cfg, neat_ctx** out) {
+  if (!cfg || !out) return fail(NEAT_EINVAL, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(NEAT_ENODEV, "no CUDA device");
+  neat_ctx* c = new neat_ctx();
+  try {
+    build_plan(*cfg, c->plan);
+  } catch (const std::exception& e) {
+    delete c;
+    return fail(NEAT_EUNSUPPORTED, e.what());
+  }
+  CK(cudaGetDevice(&c->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, c->device));
+  if (prop.major != 10) {
+    delete c;
+    return fail(NEAT_ENODEV, "neat_b200 needs an sm_100a device (tcgen05/TMEM)");
+  }
+  c->num_sms = prop.multiProcessorCount;
+  const GatherTables& g = c->plan.g;
+  CK(cudaMalloc(&c->packed, c->plan.packed_bytes));
+  CK(cudaMemset(c->packed, 0, c->plan.packed_bytes));
+  CK(upload(g.src, &c->g_src));
+  CK(upload(g.dst_hi, &c->g_dst_hi));
+  CK(upload(g.dst_lo, &c->g_dst_lo));
+  CK(upload(g.scale, &c->g_scale));
+  CK(upload(g.fsrc, &c->g_fsrc));
+  CK(upload(g.fdst, &c->g_fdst));
+
+  const Plan& P = c->plan;
+  Program& q = c->prog_query;
+  q.n = 0;
+  for (int l = 0; l < P.cfg.sdf_layers; ++l) q.s[q.n++] = mk_step(P.sdf_f[l], 0, 1, 1);
+
+  {
+    Program& r = c->prog_render;
+    const int L = P.cfg.sdf_layers;
+    r.n = 0;
+    for (int l = 0; l < L - 1; ++l) r.s[r.n++] = mk_step(P.sdf_f[l], 0, 1, 1);
+    r.s[r.n++] = mk_step(P.sdf_f_feat, 0, 1, 0);
+    r.s[r.n++] = mk_step(P.sdf_f[L - 1], 256, 0, 1);
+    for (int l = L - 2; l >= 0; --l) r.s[r.n++] = mk_step(P.sdf_t[l], 0, 1, 1);
+    for (int h = 0; h < 2; ++h) {
+      Program& g2 = c->prog_head[h];
+      const std::vector<PLayer>& fw = h == 0 ? P.rend_f : P.att_f;
+      g2.n = 0;
+      for (const PLayer& w : fw) g2.s[g2.n++] = mk_step(w, 0, 1, 1);
+    }
+  }
+  CK(cudaFuncSetAttribute(sdf_render_kernel<RENDER_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          static_cast<int>(engine_smem_bytes(RENDER_STAGES))));
+  CK(cudaFuncSetAttribute(head_fwd_kernel<RENDER_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          static_cast<int>(engine_smem_bytes(RENDER_STAGES))));
+  CK(cudaFuncSetAttribute(sdf_query_kernel<QUERY_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          static_cast<int>(engine_smem_bytes(QUERY_STAGES))));
+  *out = c;
+  return NEAT_OK;
+}
+
+void neat_destroy(neat_ctx* c) {
+  if (!c) return;
+  cudaFree(c->packed);
+  cudaFree(c->g_src);
+  cudaFree(c->g_dst_hi);
+  cudaFree(c->g_dst_lo);
+  cudaFree(c->g_scale);
+  cudaFree(c->g_fsrc);
+  cudaFree(c->g_fdst);
+  delete c;
+}
+
+size_t neat_param_count(const neat_ctx* c) { return c ? c->plan.n_params : 0; }
+
+static const std::vector<LinearDims>* net_of(const neat_ctx* c, int net) {
+  if (!c) return nullptr;
+  return net == 0 ? &c->plan.sdf : net == 1 ? &c->plan.rend : net == 2 ? &c->plan.att : nullptr;
+}
+long neat_param_offset(const neat_ctx* c, int net, int layer, int kind) {
+  const auto* v = net_of(c, net);
+  if (!v || layer < 0 || layer >= static_cast<int>(v->size())) return -1;
+  return static_cast<long>(kind == 0 ? (*v)[layer].w_off : (*v)[layer].b_off);
+}
+int neat_layer_dims(const neat_ctx* c, int net, int layer, int* in_f, int* out_f) {
+  const auto* v = net_of(c, net);
+  if (!v || layer < 0 || layer >= static_cast<int>(v->size())) return fail(NEAT_EINVAL, "bad net/layer");
+  if (in_f) *in_f = (*v)[layer].in;
+  if (out_f) *out_f = (*v)[layer].out;
+  return NEAT_OK;
+}
+
+int neat_pack_weights(neat_ctx* c, const float* flat, void* stream) {
+  if (!c || !flat) return fail(NEAT_EINVAL, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = static_cast<int>(c->plan.g.src.size());
+  const int nf = static_cast<int>(c->plan.g.fsrc.size());
+  pack_bf16_kernel<<<(n + 255) / 256, 256, 0, st>>>(flat, c->g_src, c->g_dst_hi, c->g_dst_lo, c->g_scale, n,
+                                                   reinterpret_cast<__nv_bfloat16*>(c->packed));
+  pack_f32_kernel<<<(nf + 255) / 256, 256, 0, st>>>(flat, c->g_fsrc, c->g_fdst, nf, reinterpret_cast<float*>(c->packed));
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+static int launch_query(neat_ctx* c, SdfQueryParams& p, void* stream) {
+  if (p.M <= 0) return NEAT_OK;
+  p.prog = c->prog_query;
+  p.packed = c->packed;
+  p.multires = c->plan.cfg.multires;
+  p.sphere_r = c->plan.cfg.sphere_radius;
+  p.sphere_scale = c->plan.cfg.sphere_scale;
+  const int n_tiles = (p.M + TILE_M - 1) / TILE_M;
+  const int grid = n_tiles < c->num_sms ? n_tiles : c->num_sms;
+  sdf_query_kernel<QUERY_STAGES>
+      <<<grid, NUM_THREADS, engine_smem_bytes(QUERY_STAGES), static_cast<cudaStream_t>(stream)>>>(p);
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+int neat_sdf_points(neat_ctx* c, const float* x, int M, float* sdf, void* stream) {
+  if (!c || !x || !sdf || M < 0) return fail(NEAT_EINVAL, "bad argument");
+  SdfQueryParams p{};
+  p.x = x;
+  p.sdf = sdf;
+  p.M = M;
+  p.n_per_ray = 1;
+  return launch_query(c, p, stream);
+}
+
+int neat_sdf_rays(neat_ctx* c, const float* rays_o, int o_stride, const float* rays_d, const float* z, int R, int n,
+                  float* sdf, void* stream) {
+  if (!c || !rays_o || !rays_d || !z || !sdf || R < 0 || n <= 0 || (o_stride != 0 && o_stride != 3))
+    return fail(NEAT_EINVAL, "bad argument");
+  if (static_cast<long long>(R) * n > 0x7fffffffLL) return fail(NEAT_EINVAL, "R*n too large");
+  SdfQueryParams p{};
+  p.rays_o = rays_o;
+  p.o_stride = o_stride;
+  p.rays_d = rays_d;
+  p.z = z;
+  p.sdf = sdf;
+  p.M = R * n;
+  p.n_per_ray = n;
+  return launch_query(c, p, stream);
+}
+
+// ---------------------------------------------------------------- sampler
+namespace {
+struct SamplerWs {
+  SamplerState* st;
+  float *z, *sdf, *samples, *sdf_new, *beta;
+};
+inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
+SamplerWs carve_sampler_ws(void* ws, int R) {
+  uint8_t* b = static_cast<uint8_t*>(ws);
+  SamplerWs w;
+  w.st = reinterpret_cast<SamplerState*>(b); b += 256;
+  w.z = reinterpret_cast<float*>(b); b += al256(sizeof(float) * SMP_MAX_L * R);
+  w.sdf = reinterpret_cast<float*>(b); b += al256(sizeof(float) * SMP_MAX_L * R);
+  w.samples = reinterpret_cast<float*>(b); b += al256(sizeof(float) * SMP_MAX_NEW * R);
+  w.sdf_new = reinterpret_cast<float*>(b); b += al256(sizeof(float) * SMP_MAX_NEW * R);
+  w.beta = reinterpret_cast<float*>(b);
+  return w;
+}
+int check_sampler_cfg(const neat_sampler_config* s) {
+  if (!s || s->n_eval <= 0 || s->n_eval > SMP_MAX_NEW || s->n_eval * s->max_iters > SMP_MAX_L || s->max_iters < 1 ||
+      s->max_iters > 8 || s->n_final <= 0 || s->n_final > SMP_MAX_NEW || s->n_extra < 0 ||
+      s->n_final + 2 + s->n_extra > SMP_MAX_OUT)
+    return fail(NEAT_EINVAL, "unsupported sampler configuration");
+  return NEAT_OK;
+}
+SamplerParams mk_sampler_params(const neat_sampler_config* s, int R, const SamplerWs& w) {
+  SamplerParams p{};
+  p.R = R; p.n_eval = s->n_eval; p.n_final = s->n_final; p.n_extra = s->n_extra;
+  p.beta_iters = s->beta_iters; p.max_iters = s->max_iters;
+  p.near = s->near_; p.far = s->far_; p.eps = s->eps; p.beta_min = s->beta_min;
+  p.st = w.st; p.z = w.z; p.sdf = w.sdf; p.samples = w.samples; p.sdf_new = w.sdf_new; p.beta = w.beta;
+  return p;
+}
+}  // namespace
+
+size_t neat_sampler_workspace_bytes(int R) {
+  if (R < 0) return 0;
+  return 256 + 2 * al256(sizeof(float) * SMP_MAX_L * R) + 2 * al256(sizeof(float) * SMP_MAX_NEW * R) +
+         al256(sizeof(float) * R);
+}
+
+int neat_sampler_run(neat_ctx* c, const neat_sampler_config* s, const float* rays_o, int o_stride,
+                     const float* rays_d, int R, const float* beta_param, const float* t_rand, const float* u_final,
+                     void* workspace, int* n_iters_dev, void* stream) {
+  if (!c || !rays_o || !rays_d || !beta_param || !workspace || R <= 0 || (o_stride != 0 && o_stride != 3))
+    return fail(NEAT_EINVAL, "bad argument");
+  if (int e = check_sampler_cfg(s)) return e;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const SamplerWs w = carve_sampler_ws(workspace, R);
+  SamplerParams p = mk_sampler_params(s, R, w);
+  p.beta_param = beta_param;
+  p.t_rand = t_rand;
+  p.u_final = u_final;
+  p.training = u_final != nullptr;
+  const int grid = (R + SMP_WARPS - 1) / SMP_WARPS;
+  sampler_init_kernel<<<grid, 32 * SMP_WARPS, 0, st>>>(p);
+  for (int it = 0; it < s->max_iters; ++it) {
+    // SDF of the new samples; the query kernel early-outs through a 0-tile launch guard on `done`
+    SdfQueryParams q{};
+    q.rays_o = rays_o; q.o_stride = o_stride; q.rays_d = rays_d;
+    q.z = w.samples; q.sdf = w.sdf_new; q.M = R * SMP_MAX_NEW; q.n_per_ray = SMP_MAX_NEW;
+    q.skip_flag = &w.st->done;
+    if (int e = launch_query(c, q, stream)) return e;
+    sampler_bounds_kernel<<<grid, 32 * SMP_WARPS, 0, st>>>(p, it);
+    sampler_draw_kernel<<<grid, 32 * SMP_WARPS, 0, st>>>(p, it);
+    sampler_finish_kernel<<<1, 1, 0, st>>>(w.st, it, s->max_iters);
+  }
+  if (n_iters_dev) CK(cudaMemcpyAsync(n_iters_dev, &w.st->n_iters, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+int neat_sampler_finish(neat_ctx* c, const neat_sampler_config* s, int R, const int64_t* extra_idx,
+                        const int64_t* eik_idx, void* workspace, float* z_vals, float* z_eik, void* stream) {
+  if (!c || !workspace || !z_vals || !z_eik || R <= 0 || (!extra_idx && s && s->n_extra > 0))
+    return fail(NEAT_EINVAL, "bad argument");
+  if (int e = check_sampler_cfg(s)) return e;
+  const SamplerWs w = carve_sampler_ws(workspace, R);
+  SamplerParams p = mk_sampler_params(s, R, w);
+  p.extra_idx = extra_idx;
+  p.eik_idx = eik_idx;
+  p.training = eik_idx != nullptr;
+  p.z_vals = z_vals;
+  p.z_eik = z_eik;
+  sampler_final_kernel<<<(R + SMP_WARPS - 1) / SMP_WARPS, 32 * SMP_WARPS, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+// ---------------------------------------------------------------- render points
+namespace {
+int fill_points(const neat_ctx* c, const neat_points* pts, SdfQueryParams& q) {
+  if (!pts) return fail(NEAT_EINVAL, "null points");
+  q = SdfQueryParams{};
+  if (pts->x) {
+    q.x = pts->x;
+    q.M = pts->M;
+    q.n_per_ray = 1;
+  } else {
+    if (!pts->rays_o || !pts->rays_d || !pts->z || (pts->o_stride != 0 && pts->o_stride != 3) || pts->S <= 0)
+      return fail(NEAT_EINVAL, "bad ray description");
+    q.rays_o = pts->rays_o; q.o_stride = pts->o_stride; q.rays_d = pts->rays_d; q.z = pts->z;
+    q.n_per_ray = pts->S;
+    q.M = pts->R * pts->S;
+  }
+  if (q.M <= 0) return fail(NEAT_EINVAL, "empty point batch");
+  q.multires = c->plan.cfg.multires;
+  q.sphere_r = c->plan.cfg.sphere_radius;
+  q.sphere_scale = c->plan.cfg.sphere_scale;
+  return NEAT_OK;
+}
+inline int grid_for(const neat_ctx* c, int M) {
+  const int n_tiles = (M + TILE_M - 1) / TILE_M;
+  return n_tiles < c->num_sms ? n_tiles : c->num_sms;
+}
+}  // namespace
+
+size_t neat_feat_tiles_bytes(int M) { return static_cast<size_t>((M + TILE_M - 1) / TILE_M) * TILE_MAIN_BYTES; }
+
+size_t neat_sdf_save_bytes(const neat_ctx* c, int M, int training) {
+  if (!c || M <= 0) return 0;
+  const SdfSaveLayout lay = sdf_save_layout(c->plan.cfg.sdf_layers, training != 0);
+  const size_t n = training ? static_cast<size_t>((M + TILE_M - 1) / TILE_M) : static_cast<size_t>(grid_for(c, M));
+  return n * lay.total;
+}
+
+int neat_sdf_outputs(neat_ctx* c, const neat_points* pts, int clamp, int training, float* sdf, float* grad,
+                     float* act, void* feat_tiles, void* save, void* stream) {
+  if (!c || !grad || !save) return fail(NEAT_EINVAL, "bad argument");
+  SdfRenderParams p{};
+  if (int e = fill_points(c, pts, p.pts)) return e;
+  const neat_net_config& g = c->plan.cfg;
+  p.prog = c->prog_render;
+  p.packed = c->packed;
+  p.L = g.sdf_layers; p.skip = g.sdf_skip; p.H = g.sdf_hidden; p.E = c->plan.E; p.F = g.feat;
+  p.clamp = clamp; p.training = training;
+  p.w_last_row_off = c->plan.w_last_row_off;
+  p.sdf = sdf; p.grad = grad; p.act = act;
+  p.feat_tiles = static_cast<uint8_t*>(feat_tiles);
+  p.save = static_cast<uint8_t*>(save);
+  sdf_render_kernel<RENDER_STAGES><<<grid_for(c, p.pts.M), NUM_THREADS, engine_smem_bytes(RENDER_STAGES),
+                                     static_cast<cudaStream_t>(stream)>>>(p);
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+size_t neat_head_save_bytes(const neat_ctx* c, int M) {
+  if (!c || M <= 0) return 0;
+  return static_cast<size_t>((M + TILE_M - 1) / TILE_M) * head_save_layout(c->plan.cfg.head_layers).total;
+}
+
+int neat_head_forward(neat_ctx* c, int head, const neat_points* pts, const float* normals, const void* feat_tiles,
+                      int training, void* save, float* out, void* stream) {
+  if (!c || (head != 0 && head != 1) || !normals || !feat_tiles || !out || (training && !save))
+    return fail(NEAT_EINVAL, "bad argument");
+  HeadParams p{};
+  if (int e = fill_points(c, pts, p.pts)) return e;
+  if (pts->x && !pts->dirs) return fail(NEAT_EINVAL, "explicit points need explicit view dirs");
+  p.prog = c->prog_head[head];
+  p.packed = c->packed;
+  p.dirs = pts->dirs;
+  p.normals = normals;
+  p.feat_tiles = static_cast<const uint8_t*>(feat_tiles);
+  p.head = head;
+  p.HL = c->plan.cfg.head_layers;
+  p.multires_view = c->plan.cfg.multires_view;
+  p.out_dim = head == 0 ? 3 : 6;
+  p.training = training;
+  p.save = static_cast<uint8_t*>(save);
+  p.out = out;
+  head_fwd_kernel<RENDER_STAGES><<<grid_for(c, p.pts.M), NUM_THREADS, engine_smem_bytes(RENDER_STAGES),
+                                   static_cast<cudaStream_t>(stream)>>>(p);
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+int neat_camera_rays(const float* uv, const float* pose, const float* K, int R, float* dirs, float* cam, void* stream) {
+  if (!uv || !pose || !K || !dirs || !cam || R <= 0) return fail(NEAT_EINVAL, "bad argument");
+  camera_rays_kernel<<<(R + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(uv, pose, K, R, dirs, cam);
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+int neat_composite_forward(const neat_composite_args* a, void* stream) {
+  if (!a || a->R <= 0 || a->S <= 0 || !a->z || !a->sdf || !a->rgb || !a->lines || !a->rays_o || !a->rays_d ||
+      !a->beta_param || !a->weights || !a->rgb_values || !a->lines3d || !a->depth || !a->points3d)
+    return fail(NEAT_EINVAL, "bad argument");
+  CompositeParams p{};
+  p.R = a->R; p.S = a->S; p.z = a->z; p.sdf = a->sdf; p.rgb = a->rgb; p.lines = a->lines; p.normals = a->normals;
+  p.rays_o = a->rays_o; p.rays_d = a->rays_d; p.beta_param = a->beta_param; p.beta_min = a->beta_min;
+  p.weights = a->weights; p.rgb_values = a->rgb_values; p.lines3d = a->lines3d; p.depth = a->depth;
+  p.points3d = a->points3d; p.normal_map = a->normals ? a->normal_map : nullptr;
+  composite_fwd_kernel<<<(a->R + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+int neat_line_geometry(int R, const float* pose, const float* K, const float* uv_proj, const float* points3d,
+                       const float* grad3d, const float* lines3d, float* pose_inv, float* lines2d,
+                       float* lines2d_calib, float* l3d, void* stream) {
+  if (R <= 0 || !pose || !K || !uv_proj || !points3d || !grad3d || !lines3d || !pose_inv || !lines2d ||
+      !lines2d_calib || !l3d)
+    return fail(NEAT_EINVAL, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  pose_inverse_kernel<<<1, 32, 0, st>>>(pose, pose_inv);
+  GeometryParams p{};
+  p.R = R; p.pose = pose; p.K = K; p.uv_proj = uv_proj; p.points3d = points3d; p.grad3d = grad3d;
+  p.lines3d = lines3d; p.lines2d = lines2d; p.lines2d_calib = lines2d_calib; p.l3d = l3d; p.pose_inv = pose_inv;
+  line_geometry_kernel<<<(R + 127) / 128, 128, 0, st>>>(p);
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+// ---------------------------------------------------------------- debug / bring-up
+int neat_debug_set_desc_swap(int swap) {
+  CK(cudaMemcpyToSymbol(g_desc_swap, &swap, sizeof(int)));
+  return NEAT_OK;
+}
+
+}  // extern "C"

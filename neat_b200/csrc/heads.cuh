@@ -1,0 +1,179 @@
+// RenderingNetwork.forward and AttractionFieldNetwork.forward (neat_wfr_rend_a.py:175-197, 235-255) as one
+// fused tensor-core kernel per head:  input = [x, view (PE4 for the rendering head), normal | feature] where
+// the feature tile (bf16 hi/lo operand tile written by sdf_render) is bulk-loaded straight into the A tile,
+// 4 x (Linear + ReLU) + Linear, then sigmoid (rgb) or x + offsets (3D line end points).
+#pragma once
+#include "sdf_render.cuh"
+
+namespace neat {
+
+struct HeadSaveLayout {
+  uint32_t aux;    // TILE_AUX_BYTES : aux part of u_0
+  uint32_t u;      // [HL-1] x TILE_MAIN_BYTES : u_1 .. u_{HL-1}
+  uint32_t total;
+};
+__host__ __device__ inline HeadSaveLayout head_save_layout(int HL) {
+  HeadSaveLayout s;
+  s.aux = 0;
+  s.u = TILE_AUX_BYTES;
+  s.total = s.u + (HL - 1) * TILE_MAIN_BYTES;
+  return s;
+}
+
+struct HeadParams {
+  Program prog;  // H_0 .. H_{HL-1}
+  const uint8_t* packed;
+  SdfQueryParams pts;        // point source; view dir of point pt is rays_d[pt / n_per_ray] unless `dirs` is set
+  const float* dirs;         // optional explicit view dirs [M,3]
+  const float* normals;      // [M,3]
+  const uint8_t* feat_tiles; // [n_tiles][TILE_MAIN_BYTES]
+  int head;                  // 0: rendering (sigmoid), 1: attraction (x + offsets)
+  int HL, multires_view, out_dim;
+  int training;
+  uint8_t* save;             // training: [n_tiles][layout.total]
+  float* out;                // [M, out_dim]
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1) head_fwd_kernel(const __grid_constant__ HeadParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  EngineSmem<STAGES>& sm =
+      *reinterpret_cast<EngineSmem<STAGES>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  engine_init(sm);
+  const int n_tiles = (p.pts.M + TILE_M - 1) / TILE_M;
+  const int my_tiles = (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 4) {
+    if (lane == 0) producer_loop(sm, p.prog, p.packed, my_tiles);
+  } else if (warp == 5) {
+    if (lane == 0) mma_loop(sm, p.prog, my_tiles);
+  } else {
+    const int row = threadIdx.x;
+    const uint32_t tm = sm.tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const HeadSaveLayout lay = head_save_layout(p.HL);
+    EpiState es;
+    uint32_t in_phase = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int tile = blockIdx.x + t * gridDim.x;
+      const int pt = tile * TILE_M + row;
+      const bool valid = pt < p.pts.M;
+      uint8_t* rec = p.training ? p.save + static_cast<size_t>(tile) * lay.total : nullptr;
+      float x[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f}, nrm[3] = {0.f, 0.f, 0.f};
+      if (valid) {
+        load_point(p.pts, pt, x);
+        const float* dp = p.dirs ? p.dirs + 3 * static_cast<size_t>(pt) : p.pts.rays_d + 3 * static_cast<size_t>(pt / p.pts.n_per_ray);
+        d[0] = dp[0]; d[1] = dp[1]; d[2] = dp[2];
+        nrm[0] = p.normals[3 * pt]; nrm[1] = p.normals[3 * pt + 1]; nrm[2] = p.normals[3 * pt + 2];
+      }
+      if (row == 0) {
+        bulk_wait_read0();  // saves of the previous tile finished reading the A planes
+        const uint8_t* src = p.feat_tiles + static_cast<size_t>(tile) * TILE_MAIN_BYTES;
+        mbar_arrive_expect_tx(&sm.in_ready, TILE_MAIN_BYTES);
+        bulk_g2s(sm.a_hi, src, PLANE_MAIN_BYTES, &sm.in_ready);
+        bulk_g2s(sm.a_lo, src + PLANE_MAIN_BYTES, PLANE_MAIN_BYTES, &sm.in_ready);
+      }
+      // aux = [x, view, normal], zero padded
+      {
+        float e[A_AUX_COLS];
+#pragma unroll
+        for (int i = 0; i < A_AUX_COLS; ++i) e[i] = 0.f;
+        e[0] = x[0]; e[1] = x[1]; e[2] = x[2];
+        e[3] = d[0]; e[4] = d[1]; e[5] = d[2];
+        int nv = 3;
+        if (p.head == 0 && p.multires_view > 0) {
+#pragma unroll
+          for (int j = 0; j < 6; ++j) {
+            if (j < p.multires_view) {
+              const float f = static_cast<float>(1 << j);
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                float s, co;
+                sincosf(d[c] * f, &s, &co);
+                e[3 + 3 + 6 * j + c] = s;
+                e[3 + 3 + 6 * j + 3 + c] = co;
+              }
+            }
+          }
+          nv = 3 + 6 * p.multires_view;
+        }
+        // normals follow the view block: dynamic position -> select with predicated writes
+#pragma unroll
+        for (int i = 6; i < A_AUX_COLS - 2; ++i) {
+          if (i == 3 + nv) { e[i] = nrm[0]; e[i + 1] = nrm[1]; e[i + 2] = nrm[2]; }
+        }
+#pragma unroll
+        for (int i = 0; i < A_AUX_COLS / 8; ++i) store_a8(sm.a_hi, sm.a_lo, row, A_MAIN_COLS + 8 * i, e + 8 * i);
+      }
+      fence_proxy_async();
+      if (p.training) {
+        epi_bar();
+        if (row == 0) {
+          bulk_s2g(rec + lay.aux, sm.a_hi + PLANE_MAIN_BYTES, PLANE_AUX_BYTES);
+          bulk_s2g(rec + lay.aux + PLANE_AUX_BYTES, sm.a_lo + PLANE_MAIN_BYTES, PLANE_AUX_BYTES);
+          bulk_commit();
+        }
+      }
+      if (row == 0) mbar_wait(&sm.in_ready, in_phase);
+      in_phase ^= 1;
+      epi_publish_a(sm);
+
+      for (int l = 0; l < p.HL - 1; ++l) {
+        const PLayer w = p.prog.s[l].w;
+        const float4* bias = reinterpret_cast<const float4*>(p.packed + w.bias_off);
+        epi_wait_d(sm, es);
+        if (row == 0) bulk_wait_read0();
+        epi_bar();
+        for (int c0 = 0; c0 < w.npad; c0 += 32) {
+          float acc[32];
+          tmem_ld32(tm + c0, acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(bias + (c0 >> 2) + j);
+            acc[4 * j + 0] = fmaxf(acc[4 * j + 0] + b.x, 0.f);
+            acc[4 * j + 1] = fmaxf(acc[4 * j + 1] + b.y, 0.f);
+            acc[4 * j + 2] = fmaxf(acc[4 * j + 2] + b.z, 0.f);
+            acc[4 * j + 3] = fmaxf(acc[4 * j + 3] + b.w, 0.f);
+          }
+          store_a32(sm.a_hi, sm.a_lo, row, c0, acc);
+        }
+        fence_proxy_async();
+        if (p.training) {
+          epi_bar();
+          if (row == 0) {
+            uint8_t* dst = rec + lay.u + static_cast<size_t>(l) * TILE_MAIN_BYTES;
+            bulk_s2g(dst, sm.a_hi, PLANE_MAIN_BYTES);
+            bulk_s2g(dst + PLANE_MAIN_BYTES, sm.a_lo, PLANE_MAIN_BYTES);
+            bulk_commit();
+          }
+        }
+        epi_publish_a(sm);
+      }
+      {
+        const PLayer w = p.prog.s[p.HL - 1].w;
+        const float* bias = reinterpret_cast<const float*>(p.packed + w.bias_off);
+        epi_wait_d(sm, es);
+        float acc[32];
+        tmem_ld32(tm, acc);
+        tmem_ld_wait();
+        if (valid) {
+          if (p.head == 0) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const float v = acc[c] + __ldg(bias + c);
+              p.out[3 * static_cast<size_t>(pt) + c] = 1.0f / (1.0f + expf(-v));
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) p.out[6 * static_cast<size_t>(pt) + c] = x[c % 3] + acc[c] + __ldg(bias + c);
+          }
+        }
+      }
+    }
+    if (row == 0) bulk_wait0();
+  }
+  engine_fini(sm);
+}
+
+}  // namespace neat

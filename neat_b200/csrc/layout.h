@@ -1,0 +1,37 @@
+// Plain (host + device) layout constants and program descriptors of the tile-MLP engine (engine.cuh).
+#pragma once
+#include <stdint.h>
+
+namespace neat {
+
+constexpr int TILE_M = 128;
+constexpr int A_MAIN_COLS = 256;
+constexpr int A_AUX_COLS = 48;
+constexpr int A_CHUNK_BYTES = TILE_M * 16;                                     // 2048
+constexpr int A_PLANE_BYTES = (A_MAIN_COLS + A_AUX_COLS) / 8 * A_CHUNK_BYTES;  // 77824
+constexpr int W_STAGE_BYTES = 256 * 64;                                        // 16384 (npad = 256)
+constexpr int MAX_STEPS = 28;
+constexpr int NUM_THREADS = 192;
+constexpr uint32_t TMEM_COLS = 512;
+
+struct PLayer {        // a packed weight matrix: (nk_main + nk_aux) slabs of npad*64 bytes, then padded fp32 bias
+  uint32_t off;        // byte offset of slab 0 in the packed buffer
+  uint32_t bias_off;   // byte offset of the zero-padded fp32 bias [npad]
+  uint16_t npad;       // output width (multiple of 32, <= 256)
+  uint8_t nk_main;     // k-steps (16 columns each) over A main columns [0, 16*nk_main)
+  uint8_t nk_aux;      // k-steps over A aux columns
+};
+
+struct Step {          // one GEMM of a kernel's program
+  PLayer w;
+  uint16_t d_col;      // TMEM column of the accumulator
+  uint8_t wait_a;      // 1: wait until the epilogue published the A tile
+  uint8_t commit_d;    // 1: signal the epilogue when this GEMM (and all before it) completed
+};
+
+struct Program {
+  int n;
+  Step s[MAX_STEPS];
+};
+
+}  // namespace neat

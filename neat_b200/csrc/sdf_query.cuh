@@ -1,0 +1,126 @@
+// ImplicitNetwork.get_sdf_vals as one fused kernel (neat_wfr_rend_a.py:78-96, 131-137):
+// point generation (x = o + z d) -> positional encoding -> L weight-normed Linear layers with
+// Softplus(100) on the tensor cores (activations never leave the SM) -> sphere clamp -> sdf.
+// This is the error-bound sampler's query (ray_sampler.py:146-151), the largest consumer of the step.
+#pragma once
+#include "engine.cuh"
+
+namespace neat {
+
+struct SdfQueryParams {
+  Program prog;  // steps 0 .. L-1 (forward layers; the last one is the sdf row only)
+  const uint8_t* packed;
+  const float* x;       // explicit points [M,3], or nullptr to generate x = o + z d
+  const float* rays_o;  // [R,3] (o_stride 3) or [3] (o_stride 0)
+  const float* rays_d;  // [R,3]
+  const float* z;       // [R, n_per_ray]
+  float* sdf;           // [M]
+  const int* skip_flag; // optional device word: non-zero -> the launch is a no-op (sampler already converged)
+  int o_stride;
+  int n_per_ray;
+  int M;
+  int multires;
+  float sphere_r, sphere_scale;
+};
+
+// positional encoding of x into the aux columns of the A tile (zero padded to 48 columns)
+__device__ __forceinline__ void pe_to_aux(uint8_t* a_hi, uint8_t* a_lo, int row, const float x[3], int multires) {
+  float e[A_AUX_COLS];
+#pragma unroll
+  for (int i = 0; i < A_AUX_COLS; ++i) e[i] = 0.f;
+  e[0] = x[0]; e[1] = x[1]; e[2] = x[2];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    if (j < multires) {
+      const float f = static_cast<float>(1 << j);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float s, co;
+        sincosf(x[c] * f, &s, &co);
+        e[3 + 6 * j + c] = s;
+        e[3 + 6 * j + 3 + c] = co;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < A_AUX_COLS / 8; ++i) store_a8(a_hi, a_lo, row, A_MAIN_COLS + 8 * i, e + 8 * i);
+}
+
+// the point handled by this thread: explicit, or o + z * d with the reference's rounding (mul, then add)
+__device__ __forceinline__ void load_point(const SdfQueryParams& p, int pt, float x[3]) {
+  if (p.x) {
+    x[0] = p.x[3 * pt + 0]; x[1] = p.x[3 * pt + 1]; x[2] = p.x[3 * pt + 2];
+  } else {
+    const int r = pt / p.n_per_ray;
+    const float zz = p.z[pt];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      x[c] = __fadd_rn(p.rays_o[static_cast<size_t>(r) * p.o_stride + c], __fmul_rn(zz, p.rays_d[3 * r + c]));
+  }
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1) sdf_query_kernel(const __grid_constant__ SdfQueryParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  if (p.skip_flag && *p.skip_flag) return;
+  EngineSmem<STAGES>& sm =
+      *reinterpret_cast<EngineSmem<STAGES>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  engine_init(sm);
+  const int n_tiles = (p.M + TILE_M - 1) / TILE_M;
+  const int my_tiles = (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 4) {
+    if (lane == 0) producer_loop(sm, p.prog, p.packed, my_tiles);
+  } else if (warp == 5) {
+    if (lane == 0) mma_loop(sm, p.prog, my_tiles);
+  } else {
+    const int row = threadIdx.x;
+    const uint32_t tm = sm.tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    EpiState es;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int pt = (blockIdx.x + t * gridDim.x) * TILE_M + row;
+      const bool valid = pt < p.M;
+      float x[3] = {0.f, 0.f, 0.f};
+      if (valid) load_point(p, pt, x);
+      pe_to_aux(sm.a_hi, sm.a_lo, row, x, p.multires);
+      epi_publish_a(sm);
+      for (int l = 0; l < p.prog.n - 1; ++l) {
+        const PLayer w = p.prog.s[l].w;
+        const float4* bias = reinterpret_cast<const float4*>(p.packed + w.bias_off);
+        epi_wait_d(sm, es);
+        for (int c0 = 0; c0 < w.npad; c0 += 32) {
+          float acc[32];
+          tmem_ld32(tm + c0, acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(bias + (c0 >> 2) + j);
+            acc[4 * j + 0] = softplus100(acc[4 * j + 0] + b.x);
+            acc[4 * j + 1] = softplus100(acc[4 * j + 1] + b.y);
+            acc[4 * j + 2] = softplus100(acc[4 * j + 2] + b.z);
+            acc[4 * j + 3] = softplus100(acc[4 * j + 3] + b.w);
+          }
+          store_a32(sm.a_hi, sm.a_lo, row, c0, acc);
+        }
+        epi_publish_a(sm);
+      }
+      {
+        const PLayer w = p.prog.s[p.prog.n - 1].w;
+        epi_wait_d(sm, es);
+        float acc[32];
+        tmem_ld32(tm, acc);
+        tmem_ld_wait();
+        float s = acc[0] + __ldg(reinterpret_cast<const float*>(p.packed + w.bias_off));
+        if (p.sphere_r > 0.f) {
+          const float nrm = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+          s = fminf(s, p.sphere_scale * (p.sphere_r - nrm));
+        }
+        if (valid) p.sdf[pt] = s;
+      }
+    }
+  }
+  engine_fini(sm);
+}
+
+}  // namespace neat

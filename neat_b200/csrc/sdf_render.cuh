@@ -1,0 +1,289 @@
+// ImplicitNetwork.get_outputs / .gradient as one fused kernel (neat_wfr_rend_a.py:98-129):
+//   forward pass  F : PE -> L Linear layers (+Softplus(100)), keeping sigma'(z_l) per layer
+//   normal pass   N : d sdf / d x by the hand-derived reverse recurrence
+//                     a_{L-2} = sigma'_{L-2} * W_{L-1}[0,:],  v_l = a_l W_l,  a_{l-1} = sigma'_{l-1} * v_l,
+//                     n = J_pe^T (v_0 + skip part)
+// Both passes run on the tensor cores with the point tile resident in shared memory; no autograd graph.
+// Outputs per point: sdf (sphere-clamped), normal (unnormalised), feature tile (bf16 hi/lo, tile layout).
+// In training mode the kernel also writes what the hand-written backward needs (per 128-point tile):
+//   sigma'_l (fp32), the layer inputs u_l and the normal-pass vectors a_l (bf16 hi/lo operand tiles).
+#pragma once
+#include "engine.cuh"
+#include "sdf_query.cuh"
+
+namespace neat {
+
+constexpr int PLANE_MAIN_BYTES = A_MAIN_COLS / 8 * A_CHUNK_BYTES;  // 65536
+constexpr int PLANE_AUX_BYTES = A_AUX_COLS / 8 * A_CHUNK_BYTES;    // 12288
+constexpr int TILE_MAIN_BYTES = 2 * PLANE_MAIN_BYTES;              // hi + lo
+constexpr int TILE_AUX_BYTES = 2 * PLANE_AUX_BYTES;
+constexpr int D1_BYTES = 256 * TILE_M * 4;                         // sigma' of one layer, [col][row] fp32
+constexpr int RSKIP_BYTES = A_AUX_COLS * TILE_M * 4;
+
+// Byte layout of one tile's save record (training) / one CTA's scratch (inference)
+struct SdfSaveLayout {
+  uint32_t d1;     // [L-1] x D1_BYTES
+  uint32_t rskip;  // RSKIP_BYTES
+  uint32_t pe;     // TILE_AUX_BYTES   (u_0 and the aux part of u_skip)
+  uint32_t u;      // [L-1] x TILE_MAIN_BYTES : u_1 .. u_{L-1}   (training only)
+  uint32_t a;      // [L-1] x TILE_MAIN_BYTES : a_0 .. a_{L-2}   (training only)
+  uint32_t total;  // bytes per tile
+};
+__host__ __device__ inline SdfSaveLayout sdf_save_layout(int L, bool training) {
+  SdfSaveLayout s;
+  s.d1 = 0;
+  s.rskip = s.d1 + (L - 1) * D1_BYTES;
+  s.pe = s.rskip + RSKIP_BYTES;
+  s.u = s.pe + TILE_AUX_BYTES;
+  s.a = s.u + (training ? (L - 1) * TILE_MAIN_BYTES : 0);
+  s.total = s.a + (training ? (L - 1) * TILE_MAIN_BYTES : 0);
+  return s;
+}
+
+struct SdfRenderParams {
+  Program prog;  // F_0..F_{L-2}, F_{L-1}^feat, F_{L-1}^sdf, T_{L-2}, ..., T_0
+  const uint8_t* packed;
+  SdfQueryParams pts;  // point source (x | rays_o, rays_d, z), M, multires, sphere_*; prog/packed unused
+  int L, skip, H, E, F;
+  int clamp;     // 1: get_outputs (sphere clamp), 0: gradient() (eikonal points)
+  int training;  // 1: write the full save record per tile
+  uint32_t w_last_row_off;
+  float* sdf;          // [M] or nullptr
+  float* grad;         // [M,3]
+  float* act;          // [M] 1 where the network branch of min() is active (training; may be nullptr)
+  uint8_t* feat_tiles; // [n_tiles][TILE_MAIN_BYTES] or nullptr
+  uint8_t* save;       // training: [n_tiles][layout.total]; inference: [gridDim.x][layout.total]
+};
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid_constant__ SdfRenderParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  EngineSmem<STAGES>& sm =
+      *reinterpret_cast<EngineSmem<STAGES>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  engine_init(sm);
+  const int n_tiles = (p.pts.M + TILE_M - 1) / TILE_M;
+  const int my_tiles = (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = p.L;
+
+  if (warp == 4) {
+    if (lane == 0) producer_loop(sm, p.prog, p.packed, my_tiles);
+  } else if (warp == 5) {
+    if (lane == 0) mma_loop(sm, p.prog, my_tiles);
+  } else {
+    const int row = threadIdx.x;
+    const uint32_t tm = sm.tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const SdfSaveLayout lay = sdf_save_layout(L, p.training != 0);
+    const float* w_row = reinterpret_cast<const float*>(p.packed + p.w_last_row_off);
+    EpiState es;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int tile = blockIdx.x + t * gridDim.x;
+      const int pt = tile * TILE_M + row;
+      const bool valid = pt < p.pts.M;
+      uint8_t* rec = p.save + static_cast<size_t>(p.training ? tile : static_cast<int>(blockIdx.x)) * lay.total;
+      float* d1_base = reinterpret_cast<float*>(rec + lay.d1);
+      float* rskip = reinterpret_cast<float*>(rec + lay.rskip);
+      float x[3] = {0.f, 0.f, 0.f};
+      if (valid) load_point(p.pts, pt, x);
+
+      // previous tile's last bulk store must have finished reading the A planes
+      if (row == 0) bulk_wait_read0();
+      epi_bar();
+      pe_to_aux(sm.a_hi, sm.a_lo, row, x, p.pts.multires);
+      fence_proxy_async();
+      if (p.training) {
+        epi_bar();
+        if (row == 0) {
+          bulk_s2g(rec + lay.pe, sm.a_hi + PLANE_MAIN_BYTES, PLANE_AUX_BYTES);
+          bulk_s2g(rec + lay.pe + PLANE_AUX_BYTES, sm.a_lo + PLANE_MAIN_BYTES, PLANE_AUX_BYTES);
+          bulk_commit();
+        }
+      }
+      epi_publish_a(sm);
+
+      // ------------------------------------------------------------ forward pass, hidden layers
+      for (int l = 0; l < L - 1; ++l) {
+        const PLayer w = p.prog.s[l].w;
+        const float4* bias = reinterpret_cast<const float4*>(p.packed + w.bias_off);
+        float* d1 = d1_base + static_cast<size_t>(l) * (256 * TILE_M);
+        epi_wait_d(sm, es);
+        if (row == 0) bulk_wait_read0();
+        epi_bar();
+        for (int c0 = 0; c0 < w.npad; c0 += 32) {
+          float acc[32];
+          tmem_ld32(tm + c0, acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(bias + (c0 >> 2) + j);
+            const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float h, dd;
+              softplus100_d1(acc[4 * j + q] + bb[q], h, dd);
+              acc[4 * j + q] = h;
+              d1[(c0 + 4 * j + q) * TILE_M + row] = dd;
+            }
+          }
+          store_a32(sm.a_hi, sm.a_lo, row, c0, acc);
+        }
+        fence_proxy_async();
+        if (p.training) {
+          epi_bar();
+          if (row == 0) {
+            uint8_t* dst = rec + lay.u + static_cast<size_t>(l) * TILE_MAIN_BYTES;
+            bulk_s2g(dst, sm.a_hi, PLANE_MAIN_BYTES);
+            bulk_s2g(dst + PLANE_MAIN_BYTES, sm.a_lo, PLANE_MAIN_BYTES);
+            bulk_commit();
+          }
+        }
+        epi_publish_a(sm);
+      }
+
+      // ------------------------------------------------------------ last layer: features + sdf
+      float s_raw;
+      {
+        const PLayer wf = p.prog.s[L - 1].w, ws = p.prog.s[L].w;
+        const float4* bias = reinterpret_cast<const float4*>(p.packed + wf.bias_off);
+        epi_wait_d(sm, es);
+        if (row == 0) bulk_wait_read0();
+        epi_bar();
+        {
+          float acc[32];
+          tmem_ld32(tm + 256, acc);
+          tmem_ld_wait();
+          s_raw = acc[0] + __ldg(reinterpret_cast<const float*>(p.packed + ws.bias_off));
+        }
+        for (int c0 = 0; c0 < wf.npad; c0 += 32) {
+          float acc[32];
+          tmem_ld32(tm + c0, acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(bias + (c0 >> 2) + j);
+            acc[4 * j + 0] += b.x; acc[4 * j + 1] += b.y; acc[4 * j + 2] += b.z; acc[4 * j + 3] += b.w;
+          }
+          store_a32(sm.a_hi, sm.a_lo, row, c0, acc);
+        }
+        fence_proxy_async();
+        epi_bar();
+        if (row == 0 && p.feat_tiles) {
+          uint8_t* dst = p.feat_tiles + static_cast<size_t>(tile) * TILE_MAIN_BYTES;
+          bulk_s2g(dst, sm.a_hi, PLANE_MAIN_BYTES);
+          bulk_s2g(dst + PLANE_MAIN_BYTES, sm.a_lo, PLANE_MAIN_BYTES);
+          bulk_commit();
+          bulk_wait_read0();
+        }
+        epi_bar();
+      }
+
+      // ------------------------------------------------------------ normal pass
+      // seed: a_{L-2} = sigma'_{L-2} * W_{L-1}[0, :]
+      {
+        const float* d1 = d1_base + static_cast<size_t>(L - 2) * (256 * TILE_M);
+        const int npad = p.prog.s[L - 2].w.npad;
+        for (int c0 = 0; c0 < npad; c0 += 32) {
+          float a[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a[j] = d1[(c0 + j) * TILE_M + row] * __ldg(w_row + c0 + j);
+          store_a32(sm.a_hi, sm.a_lo, row, c0, a);
+        }
+        fence_proxy_async();
+        if (p.training) {
+          epi_bar();
+          if (row == 0) {
+            uint8_t* dst = rec + lay.a + static_cast<size_t>(L - 2) * TILE_MAIN_BYTES;
+            bulk_s2g(dst, sm.a_hi, PLANE_MAIN_BYTES);
+            bulk_s2g(dst + PLANE_MAIN_BYTES, sm.a_lo, PLANE_MAIN_BYTES);
+            bulk_commit();
+          }
+        }
+        epi_publish_a(sm);
+      }
+      // transposed layers l = L-2 .. 1 : D = v_l (gradient w.r.t. the input of layer l) -> a_{l-1}
+      for (int l = L - 2; l >= 1; --l) {
+        const int step = (L + 1) + (L - 2 - l);
+        const int npad = p.prog.s[step].w.npad;  // width of the input of layer l
+        const float* d1 = d1_base + static_cast<size_t>(l - 1) * (256 * TILE_M);
+        const int n_main = (l == p.skip) ? p.H - p.E : npad;  // columns that feed a_{l-1}
+        epi_wait_d(sm, es);
+        if (row == 0) bulk_wait_read0();
+        epi_bar();
+        for (int c0 = 0; c0 < npad; c0 += 32) {
+          float acc[32];
+          tmem_ld32(tm + c0, acc);
+          tmem_ld_wait();
+          if (l == p.skip) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int c = c0 + j;
+              if (c >= n_main) rskip[(c - n_main) * TILE_M + row] = acc[j];
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] *= d1[(c0 + j) * TILE_M + row];
+          store_a32(sm.a_hi, sm.a_lo, row, c0, acc);
+        }
+        fence_proxy_async();
+        if (p.training) {
+          epi_bar();
+          if (row == 0) {
+            uint8_t* dst = rec + lay.a + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES;
+            bulk_s2g(dst, sm.a_hi, PLANE_MAIN_BYTES);
+            bulk_s2g(dst + PLANE_MAIN_BYTES, sm.a_lo, PLANE_MAIN_BYTES);
+            bulk_commit();
+          }
+        }
+        epi_publish_a(sm);
+      }
+      // layer 0: D = v_0 [E]; n = J^T (v_0 + r)
+      {
+        epi_wait_d(sm, es);
+        float v[64];
+        tmem_ld32(tm, v);
+        tmem_ld32(tm + 32, v + 32);
+        tmem_ld_wait();
+        if (p.skip >= 0) {
+#pragma unroll
+          for (int e = 0; e < A_AUX_COLS; ++e)
+            if (e < p.E) v[e] += rskip[e * TILE_M + row];
+        }
+        float n[3] = {v[0], v[1], v[2]};
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+          if (j < p.pts.multires) {
+            const float f = static_cast<float>(1 << j);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              float s, co;
+              sincosf(x[c] * f, &s, &co);
+              n[c] += f * co * v[3 + 6 * j + c] - f * s * v[3 + 6 * j + 3 + c];
+            }
+          }
+        }
+        float sdf = s_raw, actv = 1.f;
+        if (p.clamp && p.pts.sphere_r > 0.f) {
+          const float nrm = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+          const float sph = p.pts.sphere_scale * (p.pts.sphere_r - nrm);
+          if (!(s_raw <= sph)) {  // torch.minimum routes the gradient to `self` on ties
+            actv = 0.f;
+            sdf = sph;
+            const float k = -p.pts.sphere_scale / nrm;
+            n[0] = k * x[0]; n[1] = k * x[1]; n[2] = k * x[2];
+          }
+        }
+        if (valid) {
+          if (p.sdf) p.sdf[pt] = sdf;
+          p.grad[3 * pt + 0] = n[0]; p.grad[3 * pt + 1] = n[1]; p.grad[3 * pt + 2] = n[2];
+          if (p.act) p.act[pt] = actv;
+        }
+      }
+    }
+    if (row == 0) bulk_wait0();
+  }
+  engine_fini(sm);
+}
+
+}  // namespace neat

@@ -1,0 +1,112 @@
+"""Forward orchestration of VolSDFNetwork.forward (code/model/networks/neat_wfr_rend_a.py:376-538) on the
+C-ABI kernels.  Only device-memory allocation and launch ordering happen here."""
+import ctypes
+
+import torch
+
+from . import _lib
+from .context import Context, ErrorBoundSampler
+
+_P = ctypes.c_void_p
+
+
+def _ptr(t):
+    return _P(t.data_ptr()) if t is not None else None
+
+
+class Renderer:
+    def __init__(self, ctx: Context, conf):
+        self.ctx = ctx
+        self.conf = conf
+        self.sampler = ErrorBoundSampler(ctx, conf)
+        self.beta_min = float(conf["density"].get("beta_min", 1e-4))
+
+    # ---- small helpers over the C entry points ------------------------------------------------
+    def camera_rays(self, uv, pose, K):
+        ctx = self.ctx
+        R = uv.shape[0]
+        dirs = torch.empty(R, 3, device=ctx.device)
+        cam = torch.empty(3, device=ctx.device)
+        _lib.check(ctx.lib.neat_camera_rays(ctx._chk(uv, (R, 2)), ctx._chk(pose, (4, 4)), ctx._chk(K, (4, 4)), R,
+                                            _ptr(dirs), _ptr(cam), ctx._stream()))
+        return dirs, cam
+
+    def ray_points(self, cam, dirs, z):
+        R, S = z.shape
+        return _lib.Points(None, None, _ptr(cam), _ptr(dirs), _ptr(z), 0, R, S, R * S)
+
+    def explicit_points(self, x, dirs=None):
+        return _lib.Points(_ptr(x), _ptr(dirs), None, None, None, 0, 0, 0, x.shape[0])
+
+    def sdf_outputs(self, pts, M, clamp=True, training=False, want_feat=True, want_sdf=True):
+        ctx = self.ctx
+        dev = ctx.device
+        sdf = torch.empty(M, device=dev) if want_sdf else None
+        grad = torch.empty(M, 3, device=dev)
+        act = torch.empty(M, device=dev) if training else None
+        feat = torch.empty(int(ctx.lib.neat_feat_tiles_bytes(M)), dtype=torch.uint8, device=dev) if want_feat else None
+        save = torch.empty(int(ctx.lib.neat_sdf_save_bytes(ctx._h, M, int(training))), dtype=torch.uint8, device=dev)
+        _lib.check(ctx.lib.neat_sdf_outputs(ctx._h, ctypes.byref(pts), int(clamp), int(training), _ptr(sdf), _ptr(grad),
+                                            _ptr(act), _ptr(feat), _ptr(save), ctx._stream()))
+        return sdf, grad, act, feat, save
+
+    def head_forward(self, head, pts, M, normals, feat, training=False):
+        ctx = self.ctx
+        out = torch.empty(M, 3 if head == 0 else 6, device=ctx.device)
+        save = (torch.empty(int(ctx.lib.neat_head_save_bytes(ctx._h, M)), dtype=torch.uint8, device=ctx.device)
+                if training else None)
+        _lib.check(ctx.lib.neat_head_forward(ctx._h, head, ctypes.byref(pts), _ptr(normals), _ptr(feat), int(training),
+                                             _ptr(save), _ptr(out), ctx._stream()))
+        return out, save
+
+    def composite(self, z, sdf, rgb, lines, normals, cam, dirs, beta_param, want_normal_map):
+        ctx = self.ctx
+        dev = ctx.device
+        R, S = z.shape
+        w = torch.empty(R, S, device=dev)
+        rgb_values = torch.empty(R, 3, device=dev)
+        lines3d = torch.empty(R, 6, device=dev)
+        depth = torch.empty(R, device=dev)
+        points3d = torch.empty(R, 3, device=dev)
+        nmap = torch.empty(R, 3, device=dev) if want_normal_map else None
+        a = _lib.CompositeArgs(R, S, _ptr(z), _ptr(sdf), _ptr(rgb), _ptr(lines), _ptr(normals) if want_normal_map else None,
+                               _ptr(cam), _ptr(dirs), _ptr(beta_param), self.beta_min, _ptr(w), _ptr(rgb_values),
+                               _ptr(lines3d), _ptr(depth), _ptr(points3d), _ptr(nmap))
+        _lib.check(ctx.lib.neat_composite_forward(ctypes.byref(a), ctx._stream()))
+        return w, rgb_values, lines3d, depth, points3d, nmap
+
+    def line_geometry(self, pose, K, uv_proj, points3d, grad3d, lines3d):
+        ctx = self.ctx
+        dev = ctx.device
+        R = uv_proj.shape[0]
+        pose_inv = torch.empty(16, device=dev)
+        l2d = torch.empty(R, 2, 2, device=dev)
+        l2dc = torch.empty(R, 2, 2, device=dev)
+        l3d = torch.empty(R, 3, device=dev)
+        _lib.check(ctx.lib.neat_line_geometry(R, _ptr(pose), _ptr(K), _ptr(uv_proj), _ptr(points3d), _ptr(grad3d),
+                                              _ptr(lines3d), _ptr(pose_inv), _ptr(l2d), _ptr(l2dc), _ptr(l3d),
+                                              ctx._stream()))
+        return l2d, l2dc, l3d, pose_inv.view(4, 4)
+
+    # ---- eval-mode forward (no autograd) --------------------------------------------------------
+    @torch.no_grad()
+    def forward_eval(self, uv, pose, K, uv_proj, beta_param):
+        """uv [R,2], pose [4,4], K [4,4], uv_proj [R,2] (device fp32).  Mirrors the eval branch of
+        VolSDFNetwork.forward; returns the reference's output dict entries computed on device."""
+        dirs, cam = self.camera_rays(uv, pose, K)
+        z, z_eik, n_it = self.sampler.get_z_vals(cam, dirs, beta_param, training=False)
+        R, S = z.shape
+        M = R * S
+        pts = self.ray_points(cam, dirs, z)
+        sdf, grad, _, feat, _ = self.sdf_outputs(pts, M, clamp=True)
+        rgb, _ = self.head_forward(0, pts, M, grad, feat)
+        lines, _ = self.head_forward(1, pts, M, grad, feat)
+        w, rgb_values, lines3d, depth, points3d, nmap = self.composite(z, sdf, rgb, lines, grad, cam, dirs, beta_param, True)
+        p3 = self.explicit_points(points3d)
+        sdf3, grad3, _, _, _ = self.sdf_outputs(p3, R, clamp=True, want_feat=False)
+        l2d, l2dc, l3d, _ = self.line_geometry(pose, K, uv_proj, points3d, grad3, lines3d)
+        return dict(points=cam[None, None, :] + z[:, :, None] * dirs[:, None, :], rgb_values=rgb_values, depth=depth,
+                    xyz=points3d, points3d=points3d, lines3d=lines3d.view(R, 2, 3), lines2d=l2d, lines2d_calib=l2dc,
+                    l3d=l3d, sdf=sdf3, normal_map=nmap, K=K[:3, :3], z_vals=z, weights=w, n_sampler_iters=n_it,
+                    sdf_pts=sdf.view(R, S), grad_pts=grad.view(R, S, 3), rgb_pts=rgb.view(R, S, 3),
+                    lines_pts=lines.view(R, S, 2, 3))
