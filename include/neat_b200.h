@@ -40,6 +40,8 @@ typedef struct {
 int neat_create(const neat_net_config* cfg, neat_ctx** out);
 void neat_destroy(neat_ctx* ctx);
 const char* neat_last_error(void);
+/* number of CUDA kernels this library has launched in this process (all contexts) */
+long long neat_launch_count(void);
 
 /* Flat fp32 parameter buffer shared with the host framework (effective weights, i.e. weight_norm
  * already applied: neat_wfr_rend_a.py:71-72):
@@ -152,6 +154,47 @@ int neat_composite_forward(const neat_composite_args* a, void* stream);
 int neat_line_geometry(int R, const float* pose, const float* K, const float* uv_proj, const float* points3d,
                        const float* grad3d, const float* lines3d, float* pose_inv, float* lines2d,
                        float* lines2d_calib, float* l3d, void* stream);
+
+/* ---- backward (replaces loss.backward() through the model, code/training/volsdf_train.py:373) ---- */
+/* Adjoint of neat_composite_forward for the outputs the reference losses consume (rgb_values, lines3d;
+ * lines3d uses detached weights, neat_wfr_rend_a.py:410).  rgb_pre_bar [R,S,3] = dL/d(pre-sigmoid rgb),
+ * lines_bar [R,S,6], sdf_bar [R,S] (masked by act), beta_bar[1] += dL/d(density.beta).            */
+typedef struct {
+  int R, S;
+  const float *z, *sdf, *weights, *rgb, *act, *rgb_values_bar, *lines3d_bar, *beta_param;
+  float beta_min;
+  float *rgb_pre_bar, *lines_bar, *sdf_bar, *beta_bar;
+} neat_composite_bwd_args;
+int neat_composite_backward(const neat_composite_bwd_args* a, void* stream);
+
+/* Reverse sweep of a head.  out_bar [M,3|6] = dL/d(pre-activation output); fwd_save = the record written by
+ * neat_head_forward(training=1); feat_bar (neat_feat_bar_bytes) and n_bar [M,3] are overwritten
+ * (accumulate=0) or added to (accumulate=1); bwd_save feeds neat_weight_gradients.                */
+size_t neat_head_bwd_save_bytes(const neat_ctx* ctx, int M);
+size_t neat_feat_bar_bytes(int M);
+int neat_head_backward(neat_ctx* ctx, int head, int M, const float* out_bar, const void* fwd_save, void* bwd_save,
+                       float* feat_bar, float* n_bar, int accumulate, void* stream);
+
+/* ImplicitNetwork double backward: n_bar [M,3] = dL/d(normal), s_bar [M] = dL/d(sdf)
+ * (NULL = 0), feat_bar (NULL = 0), act [M] from neat_sdf_outputs (NULL = 1, eikonal points).        */
+size_t neat_sdf_bwd_save_bytes(const neat_ctx* ctx, int M);
+size_t neat_sdf_bwd_scratch_bytes(const neat_ctx* ctx, int M);
+int neat_sdf_backward(neat_ctx* ctx, const neat_points* pts, const float* n_bar, const float* s_bar,
+                      const float* feat_bar, const float* act, const void* fwd_save, void* bwd_save,
+                      void* scratch, void* stream);
+
+/* Weight / bias gradients of all three MLPs as tensor-core GEMMs over the saved operand tiles; ADDS into
+ * flat_grad (layout of neat_param_count).  Any group may be absent (M = 0).                      */
+typedef struct {
+  int M;                     /* points of this group                                        */
+  const void* sdf_fwd_save;  /* neat_sdf_outputs(training=1) record                          */
+  const void* sdf_bwd_save;  /* neat_sdf_backward record                                     */
+  const void* feat_tiles;    /* render points only (NULL for eikonal points)                */
+  const void* head_fwd_save[2];
+  const void* head_bwd_save[2];
+} neat_grad_group;
+int neat_weight_gradients(neat_ctx* ctx, const neat_grad_group* groups, int n_groups, float* flat_grad,
+                          void* stream);
 
 #ifdef __cplusplus
 }

@@ -25,6 +25,7 @@ SIGNATURES = {
     "neat_create": (_I, [ctypes.POINTER(NetConfig), ctypes.POINTER(_P)]),
     "neat_destroy": (None, [_P]),
     "neat_last_error": (ctypes.c_char_p, []),
+    "neat_launch_count": (ctypes.c_longlong, []),
     "neat_param_count": (ctypes.c_size_t, [_P]),
     "neat_param_offset": (ctypes.c_long, [_P, _I, _I, _I]),
     "neat_layer_dims": (_I, [_P, _I, _I, ctypes.POINTER(_I), ctypes.POINTER(_I)]),
@@ -42,7 +43,26 @@ SIGNATURES = {
     "neat_camera_rays": (_I, [_P, _P, _P, _I, _P, _P, _P]),
     "neat_composite_forward": (_I, [_P, _P]),
     "neat_line_geometry": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "neat_composite_backward": (_I, [_P, _P]),
+    "neat_head_bwd_save_bytes": (ctypes.c_size_t, [_P, _I]),
+    "neat_feat_bar_bytes": (ctypes.c_size_t, [_I]),
+    "neat_head_backward": (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _I, _P]),
+    "neat_sdf_bwd_save_bytes": (ctypes.c_size_t, [_P, _I]),
+    "neat_sdf_bwd_scratch_bytes": (ctypes.c_size_t, [_P, _I]),
+    "neat_sdf_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "neat_weight_gradients": (_I, [_P, _P, _I, _P, _P]),
 }
+
+
+class CompositeBwdArgs(ctypes.Structure):
+    _fields_ = [("R", _I), ("S", _I), ("z", _P), ("sdf", _P), ("weights", _P), ("rgb", _P), ("act", _P),
+                ("rgb_values_bar", _P), ("lines3d_bar", _P), ("beta_param", _P), ("beta_min", ctypes.c_float),
+                ("rgb_pre_bar", _P), ("lines_bar", _P), ("sdf_bar", _P), ("beta_bar", _P)]
+
+
+class GradGroup(ctypes.Structure):
+    _fields_ = [("M", _I), ("sdf_fwd_save", _P), ("sdf_bwd_save", _P), ("feat_tiles", _P),
+                ("head_fwd_save", _P * 2), ("head_bwd_save", _P * 2)]
 
 
 class Points(ctypes.Structure):

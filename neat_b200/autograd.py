@@ -1,0 +1,115 @@
+"""The training step of VolSDFNetwork.forward as ONE torch.autograd.Function over the C-ABI kernels.
+
+forward : camera rays -> error-bound sampler -> ImplicitNetwork (sdf, analytic normals, features) ->
+          rendering / attraction heads -> compositing -> second get_outputs at the surface points ->
+          2D line geometry -> eikonal points (reference: neat_wfr_rend_a.py:376-538)
+backward: compositing adjoint -> head reverse sweeps -> ImplicitNetwork double backward (tangent + reverse
+          sweeps) -> weight-gradient GEMMs            (reference: loss.backward())
+
+Differentiable inputs: the flat effective-parameter buffer and density.beta.  Differentiable outputs:
+rgb_values [R,3], lines3d [R,2,3], grad_theta [2R,3]; everything else the reference returns is detached
+there as well or does not reach a loss (depth, xyz, points3d, sdf, l3d, lines2d)."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_P = ctypes.c_void_p
+
+
+def _ptr(t):
+    return _P(t.data_ptr()) if t is not None else None
+
+
+class StepState:
+    """Non-differentiable inputs and every saved buffer of one step (kept alive until backward ran)."""
+    pass
+
+
+class NeatStepFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(fctx, flat, beta_param, renderer, st):
+        ctx = renderer.ctx
+        lib = ctx.lib
+        dev = ctx.device
+        ctx.pack_weights(flat.detach().contiguous())
+        beta = beta_param.detach().reshape(1).contiguous()
+        st.beta = beta
+        uv, pose, K = st.uv, st.pose, st.K
+        dirs, cam = renderer.camera_rays(uv, pose, K)
+        z, z_eik, n_it = renderer.sampler.get_z_vals(cam, dirs, beta, training=True, randoms=st.sampler_randoms)
+        R, S = z.shape
+        M = R * S
+        st.R, st.S, st.dirs, st.cam, st.z, st.n_iters = R, S, dirs, cam, z, n_it
+        pts = renderer.ray_points(cam, dirs, z)
+        st.sdf, st.grad, st.act, st.feat, st.sdf_save = renderer.sdf_outputs(pts, M, clamp=True, training=True)
+        st.rgb, st.rend_save = renderer.head_forward(0, pts, M, st.grad, st.feat, training=True)
+        st.lines, st.att_save = renderer.head_forward(1, pts, M, st.grad, st.feat, training=True)
+        w, rgb_values, lines3d, depth, points3d, _ = renderer.composite(z, st.sdf, st.rgb, st.lines, None, cam, dirs,
+                                                                        beta, False)
+        st.weights, st.depth, st.points3d = w, depth, points3d
+        p3 = renderer.explicit_points(points3d)
+        st.sdf3, st.grad3, _, _, _ = renderer.sdf_outputs(p3, R, clamp=True, want_feat=False)
+        st.lines2d, _, st.l3d, st.pose_inv = renderer.line_geometry(pose, K, st.uv_proj, points3d, st.grad3, lines3d)
+        # eikonal points (neat_wfr_rend_a.py:515-527): R uniform in the bounding cube + R near-surface
+        if st.eik_uniform is None:
+            r = renderer.scene_bounding_sphere
+            st.eik_uniform = torch.empty(R, 3).uniform_(-r, r).to(dev)
+        near = cam[None, :] + z_eik * dirs
+        st.eik_pts = torch.cat([st.eik_uniform.to(dev, torch.float32), near], 0).contiguous()
+        pe = renderer.explicit_points(st.eik_pts)
+        _, grad_theta, _, _, st.eik_save = renderer.sdf_outputs(pe, 2 * R, clamp=False, training=True,
+                                                                want_feat=False, want_sdf=False)
+        fctx.renderer, fctx.st = renderer, st
+        fctx.beta_shape = beta_param.shape
+        return rgb_values, lines3d.view(R, 2, 3), grad_theta
+
+    @staticmethod
+    def backward(fctx, rgb_values_bar, lines3d_bar, grad_theta_bar):
+        renderer, st = fctx.renderer, fctx.st
+        ctx = renderer.ctx
+        lib, dev = ctx.lib, ctx.device
+        R, S = st.R, st.S
+        M = R * S
+        stream = ctx._stream()
+        z = lambda *s: torch.zeros(*s, device=dev)
+        rvb = rgb_values_bar.contiguous().float() if rgb_values_bar is not None else z(R, 3)
+        l3b = lines3d_bar.reshape(R, 6).contiguous().float() if lines3d_bar is not None else z(R, 6)
+        gtb = grad_theta_bar.contiguous().float() if grad_theta_bar is not None else z(2 * R, 3)
+        rgb_pre_bar = torch.empty(M, 3, device=dev)
+        lines_bar = torch.empty(M, 6, device=dev)
+        sdf_bar = torch.empty(M, device=dev)
+        beta_bar = torch.zeros(1, device=dev)
+        a = _lib.CompositeBwdArgs(R, S, _ptr(st.z), _ptr(st.sdf), _ptr(st.weights), _ptr(st.rgb), _ptr(st.act), _ptr(rvb),
+                                  _ptr(l3b), _ptr(st.beta), renderer.beta_min, _ptr(rgb_pre_bar), _ptr(lines_bar),
+                                  _ptr(sdf_bar), _ptr(beta_bar))
+        _lib.check(lib.neat_composite_backward(ctypes.byref(a), stream))
+        feat_bar = torch.empty(int(lib.neat_feat_bar_bytes(M)) // 4, device=dev)
+        n_bar = torch.empty(M, 3, device=dev)
+        hb = [torch.empty(int(lib.neat_head_bwd_save_bytes(ctx._h, M)), dtype=torch.uint8, device=dev) for _ in range(2)]
+        with renderer.timed("head_bwd"):
+            _lib.check(lib.neat_head_backward(ctx._h, 0, M, _ptr(rgb_pre_bar), _ptr(st.rend_save), _ptr(hb[0]),
+                                              _ptr(feat_bar), _ptr(n_bar), 0, stream))
+            _lib.check(lib.neat_head_backward(ctx._h, 1, M, _ptr(lines_bar), _ptr(st.att_save), _ptr(hb[1]),
+                                              _ptr(feat_bar), _ptr(n_bar), 1, stream))
+        pts = renderer.ray_points(st.cam, st.dirs, st.z)
+        sb = torch.empty(int(lib.neat_sdf_bwd_save_bytes(ctx._h, M)), dtype=torch.uint8, device=dev)
+        scratch = torch.empty(int(lib.neat_sdf_bwd_scratch_bytes(ctx._h, M)), dtype=torch.uint8, device=dev)
+        with renderer.timed("sdf_bwd_M%d" % M):
+            _lib.check(lib.neat_sdf_backward(ctx._h, ctypes.byref(pts), _ptr(n_bar), _ptr(sdf_bar), _ptr(feat_bar),
+                                             _ptr(st.act), _ptr(st.sdf_save), _ptr(sb), _ptr(scratch), stream))
+        pe = renderer.explicit_points(st.eik_pts)
+        sbe = torch.empty(int(lib.neat_sdf_bwd_save_bytes(ctx._h, 2 * R)), dtype=torch.uint8, device=dev)
+        _lib.check(lib.neat_sdf_backward(ctx._h, ctypes.byref(pe), _ptr(gtb), None, None, None, _ptr(st.eik_save), _ptr(sbe),
+                                         _ptr(scratch), stream))
+        flat_grad = torch.zeros(ctx.n_params, device=dev)
+        groups = (_lib.GradGroup * 2)()
+        groups[0] = _lib.GradGroup(M, _ptr(st.sdf_save), _ptr(sb), _ptr(st.feat),
+                                   (_P * 2)(st.rend_save.data_ptr(), st.att_save.data_ptr()),
+                                   (_P * 2)(hb[0].data_ptr(), hb[1].data_ptr()))
+        groups[1] = _lib.GradGroup(2 * R, _ptr(st.eik_save), _ptr(sbe), None, (_P * 2)(None, None), (_P * 2)(None, None))
+        with renderer.timed("wgrad"):
+            _lib.check(lib.neat_weight_gradients(ctx._h, groups, 2, _ptr(flat_grad), stream))
+        st.debug = dict(rgb_pre_bar=rgb_pre_bar, lines_bar=lines_bar, sdf_bar=sdf_bar, n_bar=n_bar, feat_bar=feat_bar)
+        return flat_grad, beta_bar.reshape(fctx.beta_shape), None, None

@@ -164,10 +164,13 @@ class ErrorBoundSampler:
             else:
                 t_rand = randoms["t_rand"].to(dev, torch.float32).contiguous()
                 u_final = randoms["u_final"].to(dev, torch.float32).contiguous()
-        _lib.check(lib.neat_sampler_run(
-            ctx._h, ctypes.byref(c), ctx._chk(rays_o), o_stride, ctx._chk(rays_d, (R, 3)), R,
-            P(beta_param.data_ptr()), P(t_rand.data_ptr()) if training else None,
-            P(u_final.data_ptr()) if training else None, P(ws.data_ptr()), P(n_it.data_ptr()), ctx._stream()))
+        import contextlib
+        rn = getattr(self, "renderer", None)
+        with (rn.timed("sampler") if rn is not None else contextlib.nullcontext()):
+            _lib.check(lib.neat_sampler_run(
+                ctx._h, ctypes.byref(c), ctx._chk(rays_o), o_stride, ctx._chk(rays_d, (R, 3)), R,
+                P(beta_param.data_ptr()), P(t_rand.data_ptr()) if training else None,
+                P(u_final.data_ptr()) if training else None, P(ws.data_ptr()), P(n_it.data_ptr()), ctx._stream()))
         if training:
             k = int(n_it.item())
             table = torch.zeros(c.max_iters, max(c.n_extra, 1), dtype=torch.int64)

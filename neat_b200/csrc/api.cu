@@ -1,6 +1,7 @@
 // C ABI of neat_b200 (include/neat_b200.h): context, weight packing, kernel launches.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
@@ -8,15 +9,18 @@
 #include <vector>
 
 #include "plan.h"
+#include "backward.cuh"
 #include "composite.cuh"
 #include "heads.cuh"
 #include "sampler.cuh"
 #include "sdf_query.cuh"
 #include "sdf_render.cuh"
+#include "wgrad.cuh"
 
 using namespace neat;
 
 namespace {
+std::atomic<long long> g_launches{0};  // kernels launched by this library (bench.py's gpu_launches)
 thread_local std::string g_err;
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -65,7 +69,10 @@ struct neat_ctx {
   float* g_scale = nullptr;
   int32_t* g_fsrc = nullptr;
   uint32_t* g_fdst = nullptr;
-  Program prog_query, prog_render, prog_head[2];
+  Program prog_query, prog_render, prog_head[2], prog_head_bwd[2], prog_sdf_bwd;
+  uint8_t* ones_tile = nullptr;  // X operand with column 0 = 1 (aux-plane sized, hi then lo)
+  WJob* jobs_dev = nullptr;
+  int jobs_cap = 0;
 };
 
 // ---------------------------------------------------------------- packing kernels
@@ -142,6 +149,31 @@ int neat_create(const neat_net_config* cfg, neat_ctx** out) {
       for (const PLayer& w : fw) g2.s[g2.n++] = mk_step(w, 0, 1, 1);
     }
   }
+  {
+    const int L = P.cfg.sdf_layers, HL = P.cfg.head_layers;
+    Program& b = c->prog_sdf_bwd;
+    b.n = 0;
+    for (int l = 0; l < L - 1; ++l) b.s[b.n++] = mk_step(P.sdf_f[l], 0, 1, 1);
+    for (int l = L - 1; l >= 1; --l) b.s[b.n++] = mk_step(P.sdf_t[l], 0, 1, 1);
+    for (int h = 0; h < 2; ++h) {
+      Program& hb = c->prog_head_bwd[h];
+      const std::vector<PLayer>& tr = h == 0 ? P.rend_t : P.att_t;
+      hb.n = 0;
+      for (int l = HL - 1; l >= 1; --l) hb.s[hb.n++] = mk_step(tr[l], 0, 1, 1);
+      hb.s[hb.n++] = mk_step(tr[0], 0, 1, 0);
+      hb.s[hb.n++] = mk_step(h == 0 ? P.rend_t0_aux : P.att_t0_aux, 256, 0, 1);
+    }
+    std::vector<uint16_t> ones(TILE_AUX_BYTES / 2, 0);
+    for (int r = 0; r < TILE_M; ++r) ones[r * 8] = 0x3F80;  // hi plane, chunk 0, column 0 = bf16(1.0)
+    CK(cudaMalloc(&c->ones_tile, TILE_AUX_BYTES));
+    CK(cudaMemcpy(c->ones_tile, ones.data(), TILE_AUX_BYTES, cudaMemcpyHostToDevice));
+  }
+  CK(cudaFuncSetAttribute(head_bwd_kernel<RENDER_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          static_cast<int>(engine_smem_bytes(RENDER_STAGES))));
+  CK(cudaFuncSetAttribute(sdf_bwd_kernel<RENDER_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          static_cast<int>(engine_smem_bytes(RENDER_STAGES))));
+  CK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          static_cast<int>(sizeof(WgradSmem) + 1024)));
   CK(cudaFuncSetAttribute(sdf_render_kernel<RENDER_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           static_cast<int>(engine_smem_bytes(RENDER_STAGES))));
   CK(cudaFuncSetAttribute(head_fwd_kernel<RENDER_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -161,6 +193,8 @@ void neat_destroy(neat_ctx* c) {
   cudaFree(c->g_scale);
   cudaFree(c->g_fsrc);
   cudaFree(c->g_fdst);
+  cudaFree(c->ones_tile);
+  cudaFree(c->jobs_dev);
   delete c;
 }
 
@@ -190,7 +224,9 @@ int neat_pack_weights(neat_ctx* c, const float* flat, void* stream) {
   const int nf = static_cast<int>(c->plan.g.fsrc.size());
   pack_bf16_kernel<<<(n + 255) / 256, 256, 0, st>>>(flat, c->g_src, c->g_dst_hi, c->g_dst_lo, c->g_scale, n,
                                                    reinterpret_cast<__nv_bfloat16*>(c->packed));
+  ++g_launches;
   pack_f32_kernel<<<(nf + 255) / 256, 256, 0, st>>>(flat, c->g_fsrc, c->g_fdst, nf, reinterpret_cast<float*>(c->packed));
+  ++g_launches;
   CK(cudaGetLastError());
   return NEAT_OK;
 }
@@ -206,6 +242,7 @@ static int launch_query(neat_ctx* c, SdfQueryParams& p, void* stream) {
   const int grid = n_tiles < c->num_sms ? n_tiles : c->num_sms;
   sdf_query_kernel<QUERY_STAGES>
       <<<grid, NUM_THREADS, engine_smem_bytes(QUERY_STAGES), static_cast<cudaStream_t>(stream)>>>(p);
+  ++g_launches;
   CK(cudaGetLastError());
   return NEAT_OK;
 }
@@ -292,6 +329,7 @@ int neat_sampler_run(neat_ctx* c, const neat_sampler_config* s, const float* ray
   p.training = u_final != nullptr;
   const int grid = (R + SMP_WARPS - 1) / SMP_WARPS;
   sampler_init_kernel<<<grid, 32 * SMP_WARPS, 0, st>>>(p);
+  ++g_launches;
   for (int it = 0; it < s->max_iters; ++it) {
     // SDF of the new samples; the query kernel early-outs through a 0-tile launch guard on `done`
     SdfQueryParams q{};
@@ -300,8 +338,11 @@ int neat_sampler_run(neat_ctx* c, const neat_sampler_config* s, const float* ray
     q.skip_flag = &w.st->done;
     if (int e = launch_query(c, q, stream)) return e;
     sampler_bounds_kernel<<<grid, 32 * SMP_WARPS, 0, st>>>(p, it);
+  ++g_launches;
     sampler_draw_kernel<<<grid, 32 * SMP_WARPS, 0, st>>>(p, it);
+  ++g_launches;
     sampler_finish_kernel<<<1, 1, 0, st>>>(w.st, it, s->max_iters);
+  ++g_launches;
   }
   if (n_iters_dev) CK(cudaMemcpyAsync(n_iters_dev, &w.st->n_iters, sizeof(int), cudaMemcpyDeviceToDevice, st));
   CK(cudaGetLastError());
@@ -321,6 +362,7 @@ int neat_sampler_finish(neat_ctx* c, const neat_sampler_config* s, int R, const 
   p.z_vals = z_vals;
   p.z_eik = z_eik;
   sampler_final_kernel<<<(R + SMP_WARPS - 1) / SMP_WARPS, 32 * SMP_WARPS, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  ++g_launches;
   CK(cudaGetLastError());
   return NEAT_OK;
 }
@@ -378,6 +420,7 @@ int neat_sdf_outputs(neat_ctx* c, const neat_points* pts, int clamp, int trainin
   p.save = static_cast<uint8_t*>(save);
   sdf_render_kernel<RENDER_STAGES><<<grid_for(c, p.pts.M), NUM_THREADS, engine_smem_bytes(RENDER_STAGES),
                                      static_cast<cudaStream_t>(stream)>>>(p);
+  ++g_launches;
   CK(cudaGetLastError());
   return NEAT_OK;
 }
@@ -408,6 +451,7 @@ int neat_head_forward(neat_ctx* c, int head, const neat_points* pts, const float
   p.out = out;
   head_fwd_kernel<RENDER_STAGES><<<grid_for(c, p.pts.M), NUM_THREADS, engine_smem_bytes(RENDER_STAGES),
                                    static_cast<cudaStream_t>(stream)>>>(p);
+  ++g_launches;
   CK(cudaGetLastError());
   return NEAT_OK;
 }
@@ -415,6 +459,7 @@ int neat_head_forward(neat_ctx* c, int head, const neat_points* pts, const float
 int neat_camera_rays(const float* uv, const float* pose, const float* K, int R, float* dirs, float* cam, void* stream) {
   if (!uv || !pose || !K || !dirs || !cam || R <= 0) return fail(NEAT_EINVAL, "bad argument");
   camera_rays_kernel<<<(R + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(uv, pose, K, R, dirs, cam);
+  ++g_launches;
   CK(cudaGetLastError());
   return NEAT_OK;
 }
@@ -429,6 +474,7 @@ int neat_composite_forward(const neat_composite_args* a, void* stream) {
   p.weights = a->weights; p.rgb_values = a->rgb_values; p.lines3d = a->lines3d; p.depth = a->depth;
   p.points3d = a->points3d; p.normal_map = a->normals ? a->normal_map : nullptr;
   composite_fwd_kernel<<<(a->R + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  ++g_launches;
   CK(cudaGetLastError());
   return NEAT_OK;
 }
@@ -441,13 +487,225 @@ int neat_line_geometry(int R, const float* pose, const float* K, const float* uv
     return fail(NEAT_EINVAL, "bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   pose_inverse_kernel<<<1, 32, 0, st>>>(pose, pose_inv);
+  ++g_launches;
   GeometryParams p{};
   p.R = R; p.pose = pose; p.K = K; p.uv_proj = uv_proj; p.points3d = points3d; p.grad3d = grad3d;
   p.lines3d = lines3d; p.lines2d = lines2d; p.lines2d_calib = lines2d_calib; p.l3d = l3d; p.pose_inv = pose_inv;
   line_geometry_kernel<<<(R + 127) / 128, 128, 0, st>>>(p);
+  ++g_launches;
   CK(cudaGetLastError());
   return NEAT_OK;
 }
+
+// ---------------------------------------------------------------- backward
+int neat_composite_backward(const neat_composite_bwd_args* a, void* stream) {
+  if (!a || a->R <= 0 || a->S <= 0 || a->S > 256 || !a->z || !a->sdf || !a->weights || !a->rgb || !a->rgb_values_bar ||
+      !a->lines3d_bar || !a->beta_param || !a->rgb_pre_bar || !a->lines_bar || !a->sdf_bar || !a->beta_bar)
+    return fail(NEAT_EINVAL, "bad argument");
+  CompositeBwdParams p{};
+  p.R = a->R; p.S = a->S; p.z = a->z; p.sdf = a->sdf; p.weights = a->weights; p.rgb = a->rgb; p.act = a->act;
+  p.rgb_values_bar = a->rgb_values_bar; p.lines3d_bar = a->lines3d_bar; p.beta_param = a->beta_param;
+  p.beta_min = a->beta_min; p.rgb_pre_bar = a->rgb_pre_bar; p.lines_bar = a->lines_bar; p.sdf_bar = a->sdf_bar;
+  p.beta_bar = a->beta_bar;
+  composite_bwd_kernel<<<(a->R + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+size_t neat_head_bwd_save_bytes(const neat_ctx* c, int M) {
+  if (!c || M <= 0) return 0;
+  return static_cast<size_t>((M + TILE_M - 1) / TILE_M) * head_bwd_layout(c->plan.cfg.head_layers).total;
+}
+size_t neat_feat_bar_bytes(int M) { return static_cast<size_t>((M + TILE_M - 1) / TILE_M) * 256 * TILE_M * sizeof(float); }
+
+int neat_head_backward(neat_ctx* c, int head, int M, const float* out_bar, const void* fwd_save, void* bwd_save,
+                       float* feat_bar, float* n_bar, int accumulate, void* stream) {
+  if (!c || (head != 0 && head != 1) || M <= 0 || !out_bar || !fwd_save || !bwd_save || !feat_bar || !n_bar)
+    return fail(NEAT_EINVAL, "bad argument");
+  HeadBwdParams p{};
+  p.prog = c->prog_head_bwd[head];
+  p.packed = c->packed;
+  p.M = M; p.HL = c->plan.cfg.head_layers; p.out_dim = head == 0 ? 3 : 6;
+  p.out_bar = out_bar;
+  p.fwd_save = static_cast<const uint8_t*>(fwd_save);
+  p.bwd_save = static_cast<uint8_t*>(bwd_save);
+  p.feat_bar = feat_bar; p.n_bar = n_bar; p.accumulate = accumulate;
+  head_bwd_kernel<RENDER_STAGES><<<grid_for(c, M), NUM_THREADS, engine_smem_bytes(RENDER_STAGES),
+                                   static_cast<cudaStream_t>(stream)>>>(p);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+size_t neat_sdf_bwd_save_bytes(const neat_ctx* c, int M) {
+  if (!c || M <= 0) return 0;
+  return static_cast<size_t>((M + TILE_M - 1) / TILE_M) * sdf_bwd_layout(c->plan.cfg.sdf_layers).total;
+}
+size_t neat_sdf_bwd_scratch_bytes(const neat_ctx* c, int M) {
+  if (!c || M <= 0) return 0;
+  return static_cast<size_t>(grid_for(c, M)) * (c->plan.cfg.sdf_layers - 1) * 256 * TILE_M * sizeof(float);
+}
+
+int neat_sdf_backward(neat_ctx* c, const neat_points* pts, const float* n_bar, const float* s_bar, const float* feat_bar,
+                      const float* act, const void* fwd_save, void* bwd_save, void* scratch, void* stream) {
+  if (!c || !n_bar || !fwd_save || !bwd_save || !scratch) return fail(NEAT_EINVAL, "bad argument");
+  SdfBwdParams p{};
+  if (int e = fill_points(c, pts, p.pts)) return e;
+  const neat_net_config& g = c->plan.cfg;
+  p.prog = c->prog_sdf_bwd;
+  p.packed = c->packed;
+  p.L = g.sdf_layers; p.skip = g.sdf_skip; p.H = g.sdf_hidden; p.E = c->plan.E; p.F = g.feat;
+  p.n_bar = n_bar; p.s_bar = s_bar; p.feat_bar = feat_bar; p.act = act;
+  p.fwd_save = static_cast<const uint8_t*>(fwd_save);
+  p.bwd_save = static_cast<uint8_t*>(bwd_save);
+  p.zhat = static_cast<float*>(scratch);
+  sdf_bwd_kernel<RENDER_STAGES><<<grid_for(c, p.pts.M), NUM_THREADS, engine_smem_bytes(RENDER_STAGES),
+                                  static_cast<cudaStream_t>(stream)>>>(p);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+namespace {
+struct Planes {  // an operand: per-tile base + stride, offsets of the hi / lo planes, columns available
+  const uint8_t* base;
+  uint64_t stride;
+  uint32_t hi, lo;
+  int cols;
+};
+Planes main_planes(const void* base, uint64_t stride, uint32_t off, int cols) {
+  return Planes{static_cast<const uint8_t*>(base), stride, off, off + PLANE_MAIN_BYTES, cols};
+}
+Planes aux_planes(const void* base, uint64_t stride, uint32_t off, int cols) {
+  return Planes{static_cast<const uint8_t*>(base), stride, off, off + PLANE_AUX_BYTES, cols};
+}
+inline int c16(int x) { return (x + 15) / 16 * 16; }
+inline int c8(int x) { return (x + 7) / 8 * 8; }
+
+// dW[row0 + i][col0 + j] += scale * sum_pt X[pt][i] Y[pt][j],  i < x_valid, j < y_valid ; optional bias
+void add_gemm(std::vector<WJob>& jobs, const Planes& X, int x_valid, const Planes& Y, int y_valid, float* out, int ld,
+              int row0, int col0, float scale, float* bias, int n_tiles, int n_split) {
+  for (int m0 = 0; m0 < x_valid; m0 += 128) {
+    for (int sp = 0; sp < n_split; ++sp) {
+      WJob j{};
+      j.x_base = X.base; j.x_stride = X.stride; j.x_hi = X.hi; j.x_lo = X.lo;
+      j.y_base = Y.base; j.y_stride = Y.stride; j.y_hi = Y.hi; j.y_lo = Y.lo;
+      j.m0 = m0;
+      j.x_cols = std::min(128, c8(X.cols - m0));
+      j.n_cols = std::min(256, c16(Y.cols));
+      j.x_valid = std::min(128, x_valid - m0);
+      j.y_valid = y_valid;
+      j.out = out; j.ld = ld; j.row0 = row0 + m0; j.col0 = col0; j.scale = scale;
+      j.bias = bias;
+      j.n_tiles = n_tiles; j.split = sp; j.n_split = n_split;
+      jobs.push_back(j);
+    }
+  }
+}
+}  // namespace
+
+int neat_weight_gradients(neat_ctx* c, const neat_grad_group* groups, int n_groups, float* flat, void* stream) {
+  if (!c || !groups || n_groups <= 0 || !flat) return fail(NEAT_EINVAL, "bad argument");
+  const Plan& P = c->plan;
+  const neat_net_config& g = P.cfg;
+  const int L = g.sdf_layers, HL = g.head_layers, H = g.sdf_hidden, E = P.E, F = g.feat, S = g.sdf_skip;
+  const SdfSaveLayout fl = sdf_save_layout(L, true);
+  const SdfBwdSaveLayout bl = sdf_bwd_layout(L);
+  const HeadSaveLayout hfl = head_save_layout(HL);
+  const HeadBwdSaveLayout hbl = head_bwd_layout(HL);
+  const float rs2 = 0.70710678118654752f;
+  std::vector<WJob> jobs;
+  for (int gi = 0; gi < n_groups; ++gi) {
+    const neat_grad_group& G = groups[gi];
+    if (G.M <= 0) continue;
+    const int nt = (G.M + TILE_M - 1) / TILE_M;
+    const int ns = std::max(1, std::min(8, nt / 48));
+    if (G.sdf_fwd_save && G.sdf_bwd_save) {
+      const Planes pe = aux_planes(G.sdf_fwd_save, fl.total, fl.pe, c16(E));
+      const Planes p0 = aux_planes(G.sdf_bwd_save, bl.total, bl.p_aux, c16(E));
+      const Planes ones = aux_planes(c->ones_tile, 0, 0, 16);
+      for (int l = 0; l < L; ++l) {
+        const LinearDims d = P.sdf[l];
+        float* Wg = flat + d.w_off;
+        float* bg = flat + d.b_off;
+        // ---- reverse-sweep term: z_bar_l^T u_l
+        std::vector<std::pair<Planes, std::pair<int, int>>> xs;  // (planes, (rows valid, row0))
+        if (l < L - 1) {
+          xs.push_back({main_planes(G.sdf_bwd_save, bl.total, bl.zb + l * TILE_MAIN_BYTES, P.sdf_f[l].npad), {d.out, 0}});
+        } else {
+          xs.push_back({aux_planes(G.sdf_bwd_save, bl.total, bl.zb_aux, 16), {1, 0}});
+          xs.push_back({main_planes(G.sdf_bwd_save, bl.total, bl.zb + l * TILE_MAIN_BYTES, F), {F, 1}});
+        }
+        for (auto& xe : xs) {
+          const Planes& X = xe.first;
+          const int xv = xe.second.first, r0 = xe.second.second;
+          if (l == 0) {
+            add_gemm(jobs, X, xv, pe, E, Wg, d.in, r0, 0, 1.f, bg, nt, ns);
+          } else if (l == S) {
+            const Planes um = main_planes(G.sdf_fwd_save, fl.total, fl.u + (l - 1) * TILE_MAIN_BYTES, H - E);
+            add_gemm(jobs, X, xv, um, H - E, Wg, d.in, r0, 0, rs2, nullptr, nt, ns);
+            add_gemm(jobs, X, xv, pe, E, Wg, d.in, r0, H - E, rs2, nullptr, nt, ns);
+            // bias gradient is unscaled: a separate ones-only job through the aux planes (E columns, none written)
+            add_gemm(jobs, X, xv, pe, 0, Wg, d.in, r0, 0, 1.f, bg, nt, ns);
+          } else {
+            const Planes um = main_planes(G.sdf_fwd_save, fl.total, fl.u + (l - 1) * TILE_MAIN_BYTES, d.in);
+            add_gemm(jobs, X, xv, um, d.in, Wg, d.in, r0, 0, 1.f, bg, nt, ns);
+          }
+        }
+        // ---- tangent term: a_l^T p_in
+        const Planes A = l < L - 1 ? main_planes(G.sdf_fwd_save, fl.total, fl.a + l * TILE_MAIN_BYTES, P.sdf_f[l].npad) : ones;
+        const int av = l < L - 1 ? d.out : 1;
+        if (l == 0) {
+          add_gemm(jobs, A, av, p0, E, Wg, d.in, 0, 0, 1.f, nullptr, nt, ns);
+        } else if (l == S) {
+          const Planes pm = main_planes(G.sdf_bwd_save, bl.total, bl.p + (l - 1) * TILE_MAIN_BYTES, H - E);
+          add_gemm(jobs, A, av, pm, H - E, Wg, d.in, 0, 0, rs2, nullptr, nt, ns);
+          add_gemm(jobs, A, av, p0, E, Wg, d.in, 0, H - E, rs2, nullptr, nt, ns);
+        } else {
+          const Planes pm = main_planes(G.sdf_bwd_save, bl.total, bl.p + (l - 1) * TILE_MAIN_BYTES, d.in);
+          add_gemm(jobs, A, av, pm, d.in, Wg, d.in, 0, 0, 1.f, nullptr, nt, ns);
+        }
+      }
+    }
+    for (int h = 0; h < 2; ++h) {
+      if (!G.head_fwd_save[h] || !G.head_bwd_save[h] || !G.feat_tiles) continue;
+      const std::vector<LinearDims>& net = h == 0 ? P.rend : P.att;
+      const int aux_in = net[0].in - F;
+      for (int l = 0; l < HL; ++l) {
+        const LinearDims d = net[l];
+        float* Wg = flat + d.w_off;
+        float* bg = flat + d.b_off;
+        const Planes X = l < HL - 1 ? main_planes(G.head_bwd_save[h], hbl.total, hbl.zb + l * TILE_MAIN_BYTES, d.out)
+                                    : aux_planes(G.head_bwd_save[h], hbl.total, hbl.zb_aux, 16);
+        if (l == 0) {
+          const Planes ft = main_planes(G.feat_tiles, TILE_MAIN_BYTES, 0, F);
+          const Planes ax = aux_planes(G.head_fwd_save[h], hfl.total, hfl.aux, c16(aux_in));
+          add_gemm(jobs, X, d.out, ft, F, Wg, d.in, 0, aux_in, 1.f, bg, nt, ns);
+          add_gemm(jobs, X, d.out, ax, aux_in, Wg, d.in, 0, 0, 1.f, nullptr, nt, ns);
+        } else {
+          const Planes um = main_planes(G.head_fwd_save[h], hfl.total, hfl.u + (l - 1) * TILE_MAIN_BYTES, d.in);
+          add_gemm(jobs, X, d.out, um, d.in, Wg, d.in, 0, 0, 1.f, bg, nt, ns);
+        }
+      }
+    }
+  }
+  if (jobs.empty()) return NEAT_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (static_cast<int>(jobs.size()) > c->jobs_cap) {
+    CK(cudaStreamSynchronize(st));
+    cudaFree(c->jobs_dev);
+    c->jobs_cap = static_cast<int>(jobs.size()) * 2;
+    CK(cudaMalloc(&c->jobs_dev, sizeof(WJob) * c->jobs_cap));
+  }
+  CK(cudaMemcpyAsync(c->jobs_dev, jobs.data(), sizeof(WJob) * jobs.size(), cudaMemcpyHostToDevice, st));
+  wgrad_kernel<<<static_cast<int>(jobs.size()), NUM_THREADS, sizeof(WgradSmem) + 1024, st>>>(c->jobs_dev);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+long long neat_launch_count(void) { return g_launches.load(); }
 
 // ---------------------------------------------------------------- debug / bring-up
 int neat_debug_set_desc_swap(int swap) {

@@ -209,3 +209,114 @@ __global__ void line_geometry_kernel(GeometryParams p) {
 }
 
 }  // namespace neat
+
+namespace neat {
+
+// Adjoint of composite_fwd_kernel w.r.t. the per-point head outputs, the sdf and beta.  Only the outputs the
+// reference losses consume carry gradients: rgb_values (through weights and rgb) and lines3d (through the
+// per-point lines only: the weights are detached there, neat_wfr_rend_a.py:410).
+struct CompositeBwdParams {
+  int R, S;
+  const float* z;            // [R,S]
+  const float* sdf;          // [R,S]
+  const float* weights;      // [R,S] (forward output)
+  const float* rgb;          // [R,S,3] (sigmoid output)
+  const float* act;          // [R,S] or nullptr: 1 where the sdf comes from the network
+  const float* rgb_values_bar;  // [R,3]
+  const float* lines3d_bar;     // [R,6]
+  const float* beta_param;
+  float beta_min;
+  float* rgb_pre_bar;   // [R,S,3]  dL/d(pre-sigmoid rgb) = w * rgb_values_bar * rgb (1 - rgb)
+  float* lines_bar;     // [R,S,6]  = w * lines3d_bar
+  float* sdf_bar;       // [R,S]    dL/d(raw network sdf) (masked by act)
+  float* beta_bar;      // [1]      accumulated with atomicAdd: dL/d(density.beta parameter)
+};
+
+__global__ void __launch_bounds__(128) composite_bwd_kernel(CompositeBwdParams p) {
+  __shared__ float red[4];
+  const int wq = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + wq;
+  float bsum = 0.f;
+  if (r < p.R) {
+    const int S = p.S;
+    const float bp = *p.beta_param;
+    const float beta = fabsf(bp) + p.beta_min;
+    const float* z = p.z + static_cast<size_t>(r) * S;
+    const float* s = p.sdf + static_cast<size_t>(r) * S;
+    const float* w = p.weights + static_cast<size_t>(r) * S;
+    float gb[3], lb[6];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) gb[c] = p.rgb_values_bar[3 * r + c];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) lb[c] = p.lines3d_bar[6 * r + c];
+    // pass 1 (forward order): exclusive prefix of the free energy -> T_i ; pass 2 (reverse): suffix of w_bar w
+    // Both are done block-wise; T is recomputed in the reverse pass from the stored prefix per block.
+    const int nblk = (S + 31) / 32;
+    float blk_prefix[8];  // S <= 256
+    float carry = 0.f;
+    for (int b = 0; b < nblk; ++b) {
+      const int i = b * 32 + lane;
+      float fe = 0.f;
+      if (i < S) {
+        const float delta = i + 1 < S ? z[i + 1] - z[i] : 1e10f;
+        fe = delta * laplace_density(s[i], beta);
+      }
+      blk_prefix[b] = carry;
+      carry += warp_sum(fe);
+    }
+    float suffix_carry = 0.f;  // sum_{k in later blocks} w_bar_k w_k
+    for (int b = nblk - 1; b >= 0; --b) {
+      const int i = b * 32 + lane;
+      const size_t q = static_cast<size_t>(r) * S + i;
+      float fe = 0.f, delta = 0.f, sig = 0.f, wi = 0.f, wbar = 0.f, si = 0.f;
+      float rgbv[3] = {0.f, 0.f, 0.f};
+      if (i < S) {
+        si = s[i];
+        delta = i + 1 < S ? z[i + 1] - z[i] : 1e10f;
+        sig = laplace_density(si, beta);
+        fe = delta * sig;
+        wi = w[i];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { rgbv[c] = p.rgb[3 * q + c]; wbar += gb[c] * rgbv[c]; }
+      }
+      float tot;
+      const float ex = warp_excl_scan(fe, tot);
+      const float ww = wbar * wi;
+      // suffix_i = sum_{k>i} ww_k by a reverse scan.  It must be EXACTLY 0 for the last sample (its sigma_bar is
+      // multiplied by delta = 1e10), so it is built from shuffles, never as total - prefix - own.
+      float inc = ww;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float tdn = __shfl_down_sync(0xffffffffu, inc, o);
+        if (lane + o < 32) inc += tdn;
+      }
+      const float tot2 = __shfl_sync(0xffffffffu, inc, 0);
+      const float nxt = __shfl_down_sync(0xffffffffu, inc, 1);
+      const float suffix = (lane == 31 ? 0.f : nxt) + suffix_carry;
+      if (i < S) {
+        const float T = expf(-(blk_prefix[b] + ex));
+        const float em = expf(-fe);
+        const float fe_bar = wbar * em * T - suffix;
+        const float sigma_bar = fe_bar * delta;
+        const float e = expf(-fabsf(si) / beta);
+        const float sg2 = si != 0.f ? 1.f : 0.f;
+        const float dsig_ds = -e / (2.0f * beta * beta) * sg2;
+        const float dsig_db = -sig / beta + si * e / (2.0f * beta * beta * beta);
+        const float a = p.act ? p.act[q] : 1.f;
+        p.sdf_bar[q] = sigma_bar * dsig_ds * a;
+        bsum += sigma_bar * dsig_db;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) p.rgb_pre_bar[3 * q + c] = wi * gb[c] * rgbv[c] * (1.0f - rgbv[c]);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) p.lines_bar[6 * q + c] = wi * lb[c];
+      }
+      suffix_carry += tot2;
+    }
+    bsum = warp_sum(bsum) * (bp >= 0.f ? 1.f : -1.f);
+  }
+  if (lane == 0) red[wq] = bsum;
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(p.beta_bar, red[0] + red[1] + red[2] + red[3]);
+}
+
+}  // namespace neat

@@ -79,7 +79,9 @@ __device__ __forceinline__ float warp_excl_scan(float v, float& total) {
     if (lane >= o) inc += t;
   }
   total = __shfl_sync(0xffffffffu, inc, 31);
-  return inc - v;
+  // exclusive = inclusive of the previous lane (NOT inc - v: v may be ~1e10 * sigma for the last interval)
+  const float prev = __shfl_up_sync(0xffffffffu, inc, 1);
+  return lane == 0 ? 0.f : prev;
 }
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll

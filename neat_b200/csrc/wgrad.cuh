@@ -1,0 +1,149 @@
+// Weight-gradient GEMMs of the hand-written backward:   dW[n][k] += scale * sum_pt X[pt][n] * Y[pt][k]
+// where X (dL/dz of a layer, or the normal-pass vector a_l) and Y (the layer input u_l, or the tangent p_l)
+// are operand tiles saved by the forward / backward kernels (bf16 hi/lo planes, chunk-major, see engine.cuh).
+// The reduction runs over points, so both operands are MN-major for tcgen05 and the very bytes written as a
+// K-major A tile are reused unchanged.  One CTA owns (job, 128-row half of dW, split of the tile range),
+// accumulates in TMEM over all its tiles, then flushes once with vector atomics.  A 16-column "ones" operand
+// appended to Y yields the bias gradient db[n] = sum_pt X[pt][n] from the same MMAs.
+#pragma once
+#include "engine.cuh"
+
+namespace neat {
+
+struct WJob {
+  const uint8_t* x_base;  // per tile: x_base + tile * x_stride (+ x_hi / x_lo) = plane of the X segment
+  const uint8_t* y_base;
+  uint64_t x_stride, y_stride;
+  uint32_t x_hi, x_lo, y_hi, y_lo;
+  int m0;        // first X column handled (multiple of 8); this CTA covers columns [m0, m0+128)
+  int x_cols;    // columns available in the X plane from m0 (multiple of 8, <= 128); the rest is zero-filled
+  int n_cols;    // Y columns fed to the MMA (multiple of 16, <= 256)
+  int x_valid;   // rows of dW written:   i < x_valid
+  int y_valid;   // columns of dW written: j < y_valid
+  float* out;    // out[(row0 + i) * ld + col0 + j] += scale * D[i][j]
+  float* bias;   // bias[row0 + i] += scale * sum_pt X[pt][m0 + i]   (nullptr: none)
+  int ld, row0, col0;
+  float scale;
+  int n_tiles;
+  int split, n_split;
+};
+
+constexpr int WG_X_PLANE = 128 / 8 * A_CHUNK_BYTES;  // 32768
+constexpr int WG_Y_PLANE = 256 / 8 * A_CHUNK_BYTES;    // 65536
+constexpr int WG_ONES_BYTES = 2 * A_CHUNK_BYTES;  // 16 columns
+
+struct alignas(1024) WgradSmem {
+  uint8_t x_hi[WG_X_PLANE], x_lo[WG_X_PLANE];
+  uint8_t y_hi[WG_Y_PLANE], y_lo[WG_Y_PLANE];
+  uint8_t ones[WG_ONES_BYTES];
+  uint64_t full, empty, d_ready;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_kernel(const WJob* __restrict__ jobs) {
+  extern __shared__ uint8_t smem_raw[];
+  WgradSmem& sm = *reinterpret_cast<WgradSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const WJob job = jobs[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int my_tiles = job.n_tiles > job.split ? (job.n_tiles - job.split + job.n_split - 1) / job.n_split : 0;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&sm.full, 1);
+    mbar_init(&sm.empty, 1);
+    mbar_init(&sm.d_ready, 1);
+    fence_mbar_init();
+  }
+  // ones operand: element (pt, col) -> chunk(col/8) * 2048 + pt * 16 + (col % 8) * 2 ; column 0 = 1.0
+  for (int i = threadIdx.x; i < WG_ONES_BYTES / 4; i += blockDim.x) {
+    const int byte = i * 4;
+    const bool first = byte < A_CHUNK_BYTES && (byte % 16) == 0;
+    reinterpret_cast<uint32_t*>(sm.ones)[i] = first ? 0x00003F80u : 0u;
+  }
+  // zero the part of the X planes that is never loaded (x_cols < 128)
+  if (job.x_cols < 128) {
+    const int from = job.x_cols / 8 * A_CHUNK_BYTES;
+    for (int i = from / 16 + threadIdx.x; i < WG_X_PLANE / 16; i += blockDim.x) {
+      reinterpret_cast<uint4*>(sm.x_hi)[i] = make_uint4(0, 0, 0, 0);
+      reinterpret_cast<uint4*>(sm.x_lo)[i] = make_uint4(0, 0, 0, 0);
+    }
+  }
+  fence_proxy_async();
+  if (warp == 4) tmem_alloc(&sm.tmem_base, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  const uint32_t xb = static_cast<uint32_t>(job.x_cols / 8) * A_CHUNK_BYTES;
+  const uint32_t yb = static_cast<uint32_t>(job.n_cols / 8) * A_CHUNK_BYTES;
+  if (warp == 4 && lane == 0) {
+    for (int t = 0; t < my_tiles; ++t) {
+      const uint64_t tile = static_cast<uint64_t>(job.split) + static_cast<uint64_t>(t) * job.n_split;
+      const uint8_t* xs = job.x_base + tile * job.x_stride + static_cast<uint64_t>(job.m0 / 8) * A_CHUNK_BYTES;
+      const uint8_t* ys = job.y_base + tile * job.y_stride;
+      mbar_wait(&sm.empty, (t & 1) ^ 1);
+      mbar_arrive_expect_tx(&sm.full, 2 * xb + 2 * yb);
+      bulk_g2s(sm.x_hi, xs + job.x_hi, xb, &sm.full);
+      bulk_g2s(sm.x_lo, xs + job.x_lo, xb, &sm.full);
+      bulk_g2s(sm.y_hi, ys + job.y_hi, yb, &sm.full);
+      bulk_g2s(sm.y_lo, ys + job.y_lo, yb, &sm.full);
+    }
+  } else if (warp == 5 && lane == 0) {
+    // MN-major operands: core matrix = 8 points (K) x 8 columns (16 B); K-direction stride 128 B,
+    // MN-direction stride = one chunk (2048 B)
+    const uint32_t idesc = make_idesc(128, job.n_cols, 1, 1);
+    const uint32_t idesc1 = make_idesc(128, 16, 1, 1);
+    const uint32_t d = sm.tmem_base, d1 = sm.tmem_base + 256;
+    const uint32_t xh = smem_u32(sm.x_hi), xl = smem_u32(sm.x_lo), yh = smem_u32(sm.y_hi), yl = smem_u32(sm.y_lo);
+    const uint32_t on = smem_u32(sm.ones);
+    for (int t = 0; t < my_tiles; ++t) {
+      mbar_wait(&sm.full, t & 1);
+      tc_fence_after();
+      for (int ks = 0; ks < TILE_M / 16; ++ks) {
+        const uint32_t ko = ks * 256;  // 16 points = 2 core matrices of 128 B
+        const uint64_t dxh = make_desc_k(xh + ko, 128, A_CHUNK_BYTES), dxl = make_desc_k(xl + ko, 128, A_CHUNK_BYTES);
+        const uint64_t dyh = make_desc_k(yh + ko, 128, A_CHUNK_BYTES), dyl = make_desc_k(yl + ko, 128, A_CHUNK_BYTES);
+        const uint32_t acc = (t | ks) ? 1u : 0u;
+        umma_bf16(d, dxh, dyh, idesc, acc);
+        umma_bf16(d, dxh, dyl, idesc, 1u);
+        umma_bf16(d, dxl, dyh, idesc, 1u);
+        if (job.bias) {
+          const uint64_t don = make_desc_k(on + ko, 128, A_CHUNK_BYTES);
+          umma_bf16(d1, dxh, don, idesc1, acc);
+          umma_bf16(d1, dxl, don, idesc1, 1u);
+        }
+      }
+      umma_commit(&sm.empty);
+    }
+    umma_commit(&sm.d_ready);
+  } else if (warp < 4) {
+    if (my_tiles > 0) {
+      mbar_wait(&sm.d_ready, 0);
+      tc_fence_after();
+      const int i = threadIdx.x;  // row of this dW block
+      const uint32_t tm = sm.tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+      const bool row_ok = i < job.x_valid;
+      float* orow = job.out + static_cast<size_t>(job.row0 + i) * job.ld + job.col0;
+      for (int c0 = 0; c0 < job.n_cols; c0 += 32) {
+        float v[32];
+        tmem_ld32(tm + c0, v);   // n_cols is a multiple of 16: the upper half of the last load may be stale
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < job.y_valid) atomicAdd(orow + c0 + j, job.scale * v[j]);
+        }
+      }
+      if (job.bias) {
+        float v[32];
+        tmem_ld32(tm + 256, v);
+        tmem_ld_wait();
+        if (row_ok) atomicAdd(job.bias + job.row0 + i, job.scale * v[0]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(sm.tmem_base, TMEM_COLS);
+}
+
+}  // namespace neat

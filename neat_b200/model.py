@@ -1,0 +1,324 @@
+"""Drop-in mirror of the reference's model plugin (`train.model_class`):
+
+    model.networks.neat_wfr_rend_a.VolSDFNetwork   ->   neat_b200.model.VolSDFNetwork
+
+Same constructor (`conf=` sub-tree), same parameter / state_dict names (implicit_network.lin{l}.{bias,
+weight_g,weight_v}, rendering_network.*, attraction_network.*, density.beta, latents, ffn.{0,2,4}.*), same
+input / output dict keys (code/model/networks/neat_wfr_rend_a.py:257-538).  All heavy work runs in the
+sm_100a kernels behind include/neat_b200.h; there is no PyTorch / CPU fallback."""
+import math
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from .autograd import NeatStepFunction, StepState
+from .context import Context
+from .render import Renderer
+
+
+def _plain(conf):
+    """pyhocon ConfigTree / nested dict -> nested plain dict."""
+    if hasattr(conf, "items"):
+        return {k: _plain(v) for k, v in conf.items()}
+    return conf
+
+
+def _embed_dim(multires, d=3):
+    return d + 2 * d * multires if multires > 0 else d
+
+
+class _WeightNormMLP(nn.Module):
+    """lin0..lin{n-1} with nn.utils.weight_norm, parameters only: the math runs in the kernels."""
+
+    def __init__(self, dims_in_out, weight_norm=True):
+        super().__init__()
+        self.num_layers = len(dims_in_out) + 1
+        for l, (i, o) in enumerate(dims_in_out):
+            lin = nn.Linear(i, o)
+            setattr(self, "lin%d" % l, lin)
+        self._weight_norm = weight_norm
+
+    def _apply_weight_norm(self):
+        if self._weight_norm:
+            for l in range(self.num_layers - 1):
+                setattr(self, "lin%d" % l, nn.utils.weight_norm(getattr(self, "lin%d" % l)))
+
+
+class ImplicitNetwork(_WeightNormMLP):
+    """Parameters + standalone entry points of ImplicitNetwork (neat_wfr_rend_a.py:14-137)."""
+
+    def __init__(self, feature_vector_size, sdf_bounding_sphere, d_in, d_out, dims, geometric_init=True, bias=1.0,
+                 skip_in=(), weight_norm=True, multires=0, sphere_scale=1.0, inside_out=False):
+        if d_in != 3 or d_out != 1:
+            raise _lib.NeatError("ImplicitNetwork: d_in=3, d_out=1 expected")
+        d0 = _embed_dim(multires)
+        full = [d0] + list(dims) + [d_out + feature_vector_size]
+        io = []
+        for l in range(len(full) - 1):
+            io.append((full[l], full[l + 1] - d0 if (l + 1) in skip_in else full[l + 1]))
+        super().__init__(io, weight_norm)
+        self.sdf_bounding_sphere, self.sphere_scale, self.skip_in = sdf_bounding_sphere, sphere_scale, tuple(skip_in)
+        self.multires = multires
+        if geometric_init:
+            n = len(io)
+            for l, (i, o) in enumerate(io):
+                lin = getattr(self, "lin%d" % l)
+                with torch.no_grad():
+                    if l == n - 1:
+                        lin.weight.normal_(math.sqrt(math.pi) / math.sqrt(i), 1e-4)
+                        lin.bias.fill_(-bias)
+                    else:
+                        lin.bias.zero_()
+                        lin.weight.normal_(0.0, math.sqrt(2.0) / math.sqrt(o))
+                        if multires > 0 and l == 0:
+                            lin.weight[:, 3:].zero_()
+                        elif multires > 0 and l in skip_in:
+                            lin.weight[:, -(d0 - 3):].zero_()
+        self._apply_weight_norm()
+        self._owner = None  # set by VolSDFNetwork (gives access to the kernel context)
+
+    # --- standalone (inference) entry points used by evaluation / mesh extraction callers ---
+    def _renderer(self):
+        return self._owner()._sync_weights()
+
+    @torch.no_grad()
+    def get_sdf_vals(self, x):
+        rn = self._renderer()
+        return rn.ctx.sdf_points(x.detach().reshape(-1, 3).float().contiguous())[:, None]
+
+    def get_outputs(self, x):
+        rn = self._renderer()
+        x = x.detach().reshape(-1, 3).float().contiguous()
+        sdf, grad, _, feat, _ = rn.sdf_outputs(rn.explicit_points(x), x.shape[0], clamp=True)
+        return sdf[:, None], rn.unpack_features(feat, x.shape[0]), grad
+
+    def gradient(self, x):
+        rn = self._renderer()
+        x = x.detach().reshape(-1, 3).float().contiguous()
+        _, grad, _, _, _ = rn.sdf_outputs(rn.explicit_points(x), x.shape[0], clamp=False, want_feat=False, want_sdf=False)
+        return grad
+
+    @torch.no_grad()
+    def forward(self, x):
+        """[M, 1 + feature_vector_size] raw network output (no sphere clamp), as mesh extraction expects."""
+        rn = self._renderer()
+        x = x.detach().reshape(-1, 3).float().contiguous()
+        sdf, _, _, feat, _ = rn.sdf_outputs(rn.explicit_points(x), x.shape[0], clamp=False)
+        return torch.cat([sdf[:, None], rn.unpack_features(feat, x.shape[0])], dim=1)
+
+
+class _Head(_WeightNormMLP):
+    def __init__(self, feature_vector_size, mode, d_in, d_out, dims, weight_norm=True, multires_view=0):
+        if mode != "idr":
+            raise _lib.NeatError("only mode='idr' is supported")
+        d0 = d_in + feature_vector_size + (_embed_dim(multires_view) - 3 if multires_view > 0 else 0)
+        full = [d0] + list(dims) + [d_out]
+        super().__init__([(full[l], full[l + 1]) for l in range(len(full) - 1)], weight_norm)
+        self.mode, self.multires_view = mode, multires_view
+        self._apply_weight_norm()
+        self._owner = None
+        self._head = 0
+
+    @torch.no_grad()
+    def forward(self, points, normals, view_dirs, feature_vectors):
+        rn = self._owner()._sync_weights()
+        x = points.detach().reshape(-1, 3).float().contiguous()
+        M = x.shape[0]
+        feat = rn.pack_features(feature_vectors.detach().float())
+        out, _ = rn.head_forward(self._head, rn.explicit_points(x, view_dirs.detach().float().contiguous()), M,
+                                 normals.detach().float().contiguous(), feat)
+        return out if self._head == 0 else out.view(M, 2, 3)
+
+
+class RenderingNetwork(_Head):
+    pass
+
+
+class AttractionFieldNetwork(_Head):
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self._head = 1
+
+
+class LaplaceDensity(nn.Module):
+    """code/model/density.py:16-30 (parameter `beta`; the density itself is evaluated inside the kernels)."""
+
+    def __init__(self, params_init=None, beta_min=0.0001):
+        super().__init__()
+        for k, v in (params_init or {}).items():
+            setattr(self, k, nn.Parameter(torch.tensor(float(v))))
+        self.beta_min = float(beta_min)
+
+    def get_beta(self):
+        return self.beta.abs() + self.beta_min
+
+    def forward(self, sdf, beta=None):
+        beta = self.get_beta() if beta is None else beta
+        return (1.0 / beta) * (0.5 + 0.5 * sdf.sign() * torch.expm1(-sdf.abs() / beta))
+
+
+class VolSDFNetwork(nn.Module):
+    def __init__(self, conf):
+        super().__init__()
+        c = _plain(conf)
+        self.conf = c
+        self.feature_vector_size = int(c["feature_vector_size"])
+        self.scene_bounding_sphere = float(c.get("scene_bounding_sphere", 1.0))
+        self.white_bkgd = bool(c.get("white_bkgd", False))
+        if self.white_bkgd:
+            raise _lib.NeatError("white_bkgd is not supported by the kernels")
+        self.implicit_network = ImplicitNetwork(self.feature_vector_size, self.scene_bounding_sphere, **c["implicit_network"])
+        self.rendering_network = RenderingNetwork(self.feature_vector_size, **c["rendering_network"])
+        self.attraction_network = AttractionFieldNetwork(self.feature_vector_size, **c["attraction_network"])
+        self.density = LaplaceDensity(**c["density"])
+        cj = c.get("global_junctions", {})
+        nl, hid = int(cj.get("num_layers", 2)), int(cj.get("dim_hidden", 256))
+        self.latents = nn.Parameter(torch.empty(int(cj.get("num_junctions", 1024)), hid))
+        nn.init.normal_(self.latents, mean=0.0, std=1)
+        ffn = []
+        for i in range(nl + 1):
+            ffn.append(nn.Linear(hid, hid if i != nl else 3))
+            if i != nl:
+                ffn.append(nn.ReLU())
+        self.ffn = nn.Sequential(*ffn)
+        self.dbscan_enabled = bool(c.get("dbscan_enabled", True))
+        self.use_median = bool(c.get("use_median", False))
+        self.junction_eikonal = bool(c.get("junction_eikonal", False))
+        self.use_l3d = bool(c.get("use_l3d", False))
+        if not self.dbscan_enabled or self.junction_eikonal:
+            raise _lib.NeatError("only dbscan_enabled=True, junction_eikonal=False are supported (the shipped confs)")
+        import weakref
+        ref = weakref.ref(self)
+        for m in (self.implicit_network, self.rendering_network, self.attraction_network):
+            m._owner = ref
+        self._renderer = None
+        self._packed_version = None
+        self.replay = None  # tests: dict(sampler=..., eik_uniform=...) recorded draws to replay
+
+    # ------------------------------------------------------------------ kernel context plumbing
+    def _get_renderer(self):
+        dev = self.latents.device
+        if dev.type != "cuda":
+            raise _lib.NeatError("neat_b200.VolSDFNetwork must be moved to a CUDA device first (.cuda()); "
+                                 "there is no CPU path")
+        if self._renderer is None or self._renderer.ctx.device != dev:
+            self._renderer = Renderer(Context(self.conf, device=dev), self.conf)
+            self._renderer.scene_bounding_sphere = self.scene_bounding_sphere
+            self._packed_version = None
+        return self._renderer
+
+    def _param_version(self):
+        return tuple(p._version for p in self.parameters()) + tuple(id(p) for p in self.parameters())
+
+    def _flat_params(self):
+        rn = self._get_renderer()
+        sd = {}
+        for name, mod in (("implicit_network", self.implicit_network), ("rendering_network", self.rendering_network),
+                          ("attraction_network", self.attraction_network)):
+            for l in range(mod.num_layers - 1):
+                lin = getattr(mod, "lin%d" % l)
+                pre = "%s.lin%d" % (name, l)
+                if hasattr(lin, "weight_g"):
+                    sd[pre + ".weight_g"], sd[pre + ".weight_v"] = lin.weight_g, lin.weight_v
+                else:
+                    sd[pre + ".weight"] = lin.weight
+                sd[pre + ".bias"] = lin.bias
+        return rn.ctx.flatten_state_dict(sd)
+
+    def _sync_weights(self):
+        """(inference entry points) re-pack the weight slabs if any parameter changed."""
+        rn = self._get_renderer()
+        v = self._param_version()
+        if v != self._packed_version:
+            with torch.no_grad():
+                rn.ctx.pack_weights(self._flat_params().detach())
+            self._packed_version = v
+        return rn
+
+    # ------------------------------------------------------------------ reference helpers kept for callers
+    def project2D(self, K, R, T, points3d):
+        shape = points3d.shape
+        X = points3d.reshape(-1, 3)
+        x = (K @ (R @ X.t() + T)).t()
+        den = x[:, -1:]
+        sign = torch.where(den >= 0, torch.ones_like(den), -torch.ones_like(den))
+        eps = torch.where(den.abs() < 1e-8, torch.full_like(den, 1e-8), torch.zeros_like(den))
+        return (x / (den + eps * sign)).reshape(*shape)[..., :2]
+
+    def cluster_dbscan(self, points, eps=0.01, min_samples=2):
+        from sklearn.cluster import DBSCAN
+        labels = DBSCAN(eps=eps, min_samples=min_samples).fit(points).labels_
+        cl = [points[labels == i].mean(axis=0) for i in range(labels.max() + 1)]
+        return torch.tensor(np.array(cl).reshape(-1, 3)).float().to(self.latents.device)
+
+    def volume_rendering(self, z_vals, sdf):
+        sigma = self.density(sdf.reshape(-1, z_vals.shape[1]))
+        d = torch.cat([z_vals[:, 1:] - z_vals[:, :-1], torch.full_like(z_vals[:, :1], 1e10)], -1)
+        fe = d * sigma
+        sh = torch.cat([torch.zeros_like(fe[:, :1]), fe[:, :-1]], -1)
+        return (1 - torch.exp(-fe)) * torch.exp(-torch.cumsum(sh, -1))
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, input):
+        rn = self._get_renderer()
+        dev = rn.ctx.device
+        K4 = input["intrinsics"][0].to(dev, torch.float32).contiguous()
+        pose = input["pose"][0].to(dev, torch.float32).contiguous()
+        uv = input["uv"].reshape(-1, 2).to(dev, torch.float32).contiguous()
+        uv_proj = input["uv_proj"].reshape(-1, 2).to(dev, torch.float32).contiguous()
+        R = uv.shape[0]
+        out = {}
+        if not self.training:
+            self._sync_weights()
+            beta = self.density.beta.detach().reshape(1).float().contiguous()
+            o = rn.forward_eval(uv, pose, K4, uv_proj, beta)
+            for k in ("points", "rgb_values", "depth", "xyz", "points3d", "lines3d", "lines2d", "lines2d_calib", "l3d",
+                      "sdf", "normal_map"):
+                out[k] = o[k]
+            out["wireframe-gt"] = input.get("wireframe")
+            out["K"] = K4[:3, :3]
+            return out
+
+        st = StepState()
+        st.uv, st.pose, st.K, st.uv_proj = uv, pose, K4, uv_proj
+        st.sampler_randoms = self.replay["sampler"] if self.replay else None
+        st.eik_uniform = self.replay["eik_uniform"] if self.replay else None
+        flat = self._flat_params()
+        self._packed_version = None  # the step packs its own copy
+        # the eikonal draw follows the junction block in the reference's RNG order; it is made lazily inside the
+        # step when not replayed, so do the (host-side) junction block on the detached outputs afterwards.
+        rgb_values, lines3d, grad_theta = NeatStepFunction.apply(flat, self.density.beta, rn, st)
+        self.last_step = st
+        pinv = st.pose_inv[:3]
+        Rm, T = pinv[:, :3], pinv[:, 3:]
+        K3 = K4[:3, :3]
+        I3 = torch.eye(3, device=dev)
+        out.update(points=st.cam[None, None, :] + st.z[:, :, None] * st.dirs[:, None, :], rgb_values=rgb_values,
+                   depth=st.depth, xyz=st.points3d, points3d=st.points3d, lines3d=lines3d, l3d=st.l3d,
+                   lines2d=st.lines2d, lines2d_calib=self.project2D(I3, Rm, T, lines3d), sdf=st.sdf3,
+                   K=K3, grad_theta=grad_theta)
+        out["wireframe-gt"] = input.get("wireframe")
+        # ---- junction block (neat_wfr_rend_a.py:457-496): DBSCAN + Hungarian on the host, as the reference
+        from scipy.optimize import linear_sum_assignment
+        j3d = self.cluster_dbscan(lines3d.detach().cpu().numpy().reshape(-1, 3), eps=0.01, min_samples=2)
+        j2d = self.project2D(K3, Rm, T, j3d)
+        j2d_cal = self.project2D(I3, Rm, T, j3d)
+        gt = input["wireframe"][0].vertices.to(dev, torch.float32)
+        jcost = torch.sum((j2d[None] - gt[:, None]) ** 2, dim=-1).sqrt()
+        a0, a1 = linear_sum_assignment(jcost.detach().cpu().numpy())
+        sel = jcost[a0, a1]
+        if self.use_median:
+            med = sel.detach().median()
+            if torch.isnan(med):
+                med = torch.tensor(10.0, device=dev)
+            ok = sel < med
+            out["median"] = med
+        else:
+            ok = sel < 10
+        glob = self.ffn(self.latents)
+        out.update(j2d_local=j2d[a1][ok], j3d_local=j3d[a1][ok], j3d_global=glob,
+                   j2d_global=self.project2D(K3, Rm, T, glob), j2d_local_calib=j2d_cal[a1][ok],
+                   j2d_global_calib=self.project2D(I3, Rm, T, glob))
+        return out

@@ -14,12 +14,38 @@ def _ptr(t):
     return _P(t.data_ptr()) if t is not None else None
 
 
+class _Timed:
+    def __init__(self, rn, name):
+        self.rn, self.name = rn, name
+
+    def __enter__(self):
+        if self.rn.timers is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record(torch.cuda.current_stream(self.rn.ctx.device))
+
+    def __exit__(self, *exc):
+        if self.rn.timers is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record(torch.cuda.current_stream(self.rn.ctx.device))
+            self.rn.timers.setdefault(self.name, []).append((self.e0, e1))
+
+
 class Renderer:
     def __init__(self, ctx: Context, conf):
         self.ctx = ctx
         self.conf = conf
         self.sampler = ErrorBoundSampler(ctx, conf)
+        self.sampler.renderer = self
         self.beta_min = float(conf["density"].get("beta_min", 1e-4))
+        self.scene_bounding_sphere = float(conf.get("scene_bounding_sphere", 1.0))
+        self.timers = None  # bench.py: dict name -> [(start, end) CUDA events] on the launching stream
+
+    def timed(self, name):
+        return _Timed(self, name)
+
+    def timer_ms(self):
+        """name -> (launch groups, total ms); call after a synchronize."""
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (self.timers or {}).items()}
 
     # ---- small helpers over the C entry points ------------------------------------------------
     def camera_rays(self, uv, pose, K):
@@ -46,8 +72,9 @@ class Renderer:
         act = torch.empty(M, device=dev) if training else None
         feat = torch.empty(int(ctx.lib.neat_feat_tiles_bytes(M)), dtype=torch.uint8, device=dev) if want_feat else None
         save = torch.empty(int(ctx.lib.neat_sdf_save_bytes(ctx._h, M, int(training))), dtype=torch.uint8, device=dev)
-        _lib.check(ctx.lib.neat_sdf_outputs(ctx._h, ctypes.byref(pts), int(clamp), int(training), _ptr(sdf), _ptr(grad),
-                                            _ptr(act), _ptr(feat), _ptr(save), ctx._stream()))
+        with self.timed("sdf_render_M%d" % M):
+            _lib.check(ctx.lib.neat_sdf_outputs(ctx._h, ctypes.byref(pts), int(clamp), int(training), _ptr(sdf), _ptr(grad),
+                                                _ptr(act), _ptr(feat), _ptr(save), ctx._stream()))
         return sdf, grad, act, feat, save
 
     def head_forward(self, head, pts, M, normals, feat, training=False):
@@ -55,8 +82,9 @@ class Renderer:
         out = torch.empty(M, 3 if head == 0 else 6, device=ctx.device)
         save = (torch.empty(int(ctx.lib.neat_head_save_bytes(ctx._h, M)), dtype=torch.uint8, device=ctx.device)
                 if training else None)
-        _lib.check(ctx.lib.neat_head_forward(ctx._h, head, ctypes.byref(pts), _ptr(normals), _ptr(feat), int(training),
-                                             _ptr(save), _ptr(out), ctx._stream()))
+        with self.timed("head_fwd"):
+            _lib.check(ctx.lib.neat_head_forward(ctx._h, head, ctypes.byref(pts), _ptr(normals), _ptr(feat), int(training),
+                                                 _ptr(save), _ptr(out), ctx._stream()))
         return out, save
 
     def composite(self, z, sdf, rgb, lines, normals, cam, dirs, beta_param, want_normal_map):
@@ -87,6 +115,23 @@ class Renderer:
                                               _ptr(lines3d), _ptr(pose_inv), _ptr(l2d), _ptr(l2dc), _ptr(l3d),
                                               ctx._stream()))
         return l2d, l2dc, l3d, pose_inv.view(4, 4)
+
+    # ---- feature tiles <-> [M, F] (standalone ImplicitNetwork / head entry points only) ------------
+    def unpack_features(self, tiles, M):
+        F = self.ctx.cfg.feat
+        t = tiles.view(torch.bfloat16).view(-1, 2, 32, 128, 8).float()
+        full = (t[:, 0] + t[:, 1]).permute(0, 2, 1, 3).reshape(-1, 256)
+        return full[:M, :F].contiguous()
+
+    def pack_features(self, feat):
+        M, F = feat.shape
+        nt = (M + 127) // 128
+        full = torch.zeros(nt * 128, 256, device=feat.device)
+        full[:M, :F] = feat
+        hi = full.to(torch.bfloat16)
+        lo = (full - hi.float()).to(torch.bfloat16)
+        t = torch.stack([hi, lo], 0).view(2, nt, 128, 32, 8).permute(1, 0, 3, 2, 4).contiguous()
+        return t.view(torch.uint8).reshape(-1)
 
     # ---- eval-mode forward (no autograd) --------------------------------------------------------
     @torch.no_grad()

@@ -751,13 +751,19 @@ def junction_block(P: NeatParams, K, pose, lines3d, gt_vertices):
 
 
 def neat_forward(P: NeatParams, sconf: SamplerConf, K, pose, uv, uv_proj, gt_vertices=None,
-                 training=False, rnd: Optional[TrainRandoms] = None):
-    """K [4,4], pose [4,4], uv [R,2], uv_proj [R,2].  Output dict mirrors the reference's."""
+                 training=False, rnd: Optional[TrainRandoms] = None, samples=None):
+    """K [4,4], pose [4,4], uv [R,2], uv_proj [R,2].  Output dict mirrors the reference's.
+    samples=(z_vals, z_eik) bypasses the error-bound sampler (whose discrete decisions make the sample
+    positions sensitive to 1e-6-level differences in the SDF) so that everything downstream can be
+    compared at identical sample positions."""
     dirs, cam = camera_rays(uv, pose, K)
     R = dirs.shape[0]
     camr = cam[None].expand(R, 3)
-    z_vals, z_eik, k = error_bound_sampler(P, sconf, dirs, camr, training=training,
-                                           rnd=rnd.sampler if training else None)
+    if samples is not None:
+        z_vals, z_eik, k = samples[0], samples[1], -1
+    else:
+        z_vals, z_eik, k = error_bound_sampler(P, sconf, dirs, camr, training=training,
+                                               rnd=rnd.sampler if training else None)
     rr = render_rays(P, dirs, camr, z_vals)
     geo = line_geometry(P, K, pose, uv_proj, rr["points3d"], rr["lines3d"])
     out = dict(points=rr["points"], rgb_values=rr["rgb_values"], depth=rr["depth"], xyz=rr["xyz"],
