@@ -155,6 +155,14 @@ int neat_line_geometry(int R, const float* pose, const float* K, const float* uv
                        const float* grad3d, const float* lines3d, float* pose_inv, float* lines2d,
                        float* lines2d_calib, float* l3d, void* stream);
 
+/* ---- junction clustering (VolSDFNetwork.cluster_dbscan, neat_wfr_rend_a.py:333-342) ------------- */
+/* sklearn DBSCAN(eps, min_samples=2) + per-cluster mean == connected components (>= 2 points) of the
+ * eps-graph + centroids.  points [N,3]; centroids [N/2,3] (first *n_clusters rows valid, clusters ordered by
+ * their smallest point index, as sklearn labels them); n_clusters: device int.                     */
+size_t neat_dbscan_workspace_bytes(int N);
+int neat_dbscan(const float* points, int N, float eps, void* workspace, float* centroids, int* n_clusters,
+                void* stream);
+
 /* ---- backward (replaces loss.backward() through the model, code/training/volsdf_train.py:373) ---- */
 /* Adjoint of neat_composite_forward for the outputs the reference losses consume (rgb_values, lines3d;
  * lines3d uses detached weights, neat_wfr_rend_a.py:410).  rgb_pre_bar [R,S,3] = dL/d(pre-sigmoid rgb),

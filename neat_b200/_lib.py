@@ -43,6 +43,8 @@ SIGNATURES = {
     "neat_camera_rays": (_I, [_P, _P, _P, _I, _P, _P, _P]),
     "neat_composite_forward": (_I, [_P, _P]),
     "neat_line_geometry": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "neat_dbscan_workspace_bytes": (ctypes.c_size_t, [_I]),
+    "neat_dbscan": (_I, [_P, _I, ctypes.c_float, _P, _P, _P, _P]),
     "neat_composite_backward": (_I, [_P, _P]),
     "neat_head_bwd_save_bytes": (ctypes.c_size_t, [_P, _I]),
     "neat_feat_bar_bytes": (ctypes.c_size_t, [_I]),

@@ -11,6 +11,7 @@
 #include "plan.h"
 #include "backward.cuh"
 #include "composite.cuh"
+#include "dbscan.cuh"
 #include "heads.cuh"
 #include "sampler.cuh"
 #include "sdf_query.cuh"
@@ -49,11 +50,13 @@ inline size_t engine_smem_bytes(int stages) {
   return (stages == 4 ? sizeof(EngineSmem<4>) : sizeof(EngineSmem<3>)) + 1024;
 }
 
-Step mk_step(const PLayer& w, int d_col, int wait_a, int commit_d) {
+// buf: which 256-column half of TMEM holds the accumulator (consecutive dependent steps alternate, see engine.cuh)
+Step mk_step(const PLayer& w, int buf, int wait_a, int wait_aux, int commit_d) {
   Step s{};
   s.w = w;
-  s.d_col = static_cast<uint16_t>(d_col);
+  s.d_col = static_cast<uint16_t>((buf & 1) * 256);
   s.wait_a = static_cast<uint8_t>(wait_a);
+  s.wait_aux = static_cast<uint8_t>(wait_aux);
   s.commit_d = static_cast<uint8_t>(commit_d);
   return s;
 }
@@ -132,36 +135,39 @@ int neat_create(const neat_net_config* cfg, neat_ctx** out) {
   const Plan& P = c->plan;
   Program& q = c->prog_query;
   q.n = 0;
-  for (int l = 0; l < P.cfg.sdf_layers; ++l) q.s[q.n++] = mk_step(P.sdf_f[l], 0, 1, 1);
+  for (int l = 0; l < P.cfg.sdf_layers; ++l) q.s[q.n++] = mk_step(P.sdf_f[l], l, 1, l == 0, 1);
 
   {
     Program& r = c->prog_render;
     const int L = P.cfg.sdf_layers;
     r.n = 0;
-    for (int l = 0; l < L - 1; ++l) r.s[r.n++] = mk_step(P.sdf_f[l], 0, 1, 1);
-    r.s[r.n++] = mk_step(P.sdf_f_feat, 0, 1, 0);
-    r.s[r.n++] = mk_step(P.sdf_f[L - 1], 256, 0, 1);
-    for (int l = L - 2; l >= 0; --l) r.s[r.n++] = mk_step(P.sdf_t[l], 0, 1, 1);
+    for (int l = 0; l < L - 1; ++l) r.s[r.n++] = mk_step(P.sdf_f[l], l, 1, l == 0, 1);
+    const int b = (L - 2) & 1;                                    // accumulator half of F_{L-2}
+    r.s[r.n++] = mk_step(P.sdf_f[L - 1], 1 - b, 1, 0, 0);         // sdf row   -> the other half (32 columns)
+    r.s[r.n++] = mk_step(P.sdf_f_feat, b, 0, 0, 1);               // features  -> issued after every reader of b is done
+    for (int l = L - 2, i = 0; l >= 0; --l, ++i) r.s[r.n++] = mk_step(P.sdf_t[l], (i & 1) ? b : 1 - b, 1, 0, 1);
     for (int h = 0; h < 2; ++h) {
       Program& g2 = c->prog_head[h];
       const std::vector<PLayer>& fw = h == 0 ? P.rend_f : P.att_f;
       g2.n = 0;
-      for (const PLayer& w : fw) g2.s[g2.n++] = mk_step(w, 0, 1, 1);
+      for (const PLayer& w : fw) { g2.s[g2.n] = mk_step(w, g2.n, 1, g2.n == 0, 1); ++g2.n; }
     }
   }
   {
     const int L = P.cfg.sdf_layers, HL = P.cfg.head_layers;
     Program& b = c->prog_sdf_bwd;
     b.n = 0;
-    for (int l = 0; l < L - 1; ++l) b.s[b.n++] = mk_step(P.sdf_f[l], 0, 1, 1);
-    for (int l = L - 1; l >= 1; --l) b.s[b.n++] = mk_step(P.sdf_t[l], 0, 1, 1);
+    for (int l = 0; l < L - 1; ++l, ++b.n) b.s[b.n] = mk_step(P.sdf_f[l], b.n, 1, b.n == 0, 1);
+    for (int l = L - 1; l >= 1; --l, ++b.n) b.s[b.n] = mk_step(P.sdf_t[l], b.n, 1, l == L - 1, 1);
     for (int h = 0; h < 2; ++h) {
       Program& hb = c->prog_head_bwd[h];
       const std::vector<PLayer>& tr = h == 0 ? P.rend_t : P.att_t;
       hb.n = 0;
-      for (int l = HL - 1; l >= 1; --l) hb.s[hb.n++] = mk_step(tr[l], 0, 1, 1);
-      hb.s[hb.n++] = mk_step(tr[0], 0, 1, 0);
-      hb.s[hb.n++] = mk_step(h == 0 ? P.rend_t0_aux : P.att_t0_aux, 256, 0, 1);
+      for (int l = HL - 1; l >= 1; --l, ++hb.n) hb.s[hb.n] = mk_step(tr[l], hb.n, 1, hb.n == 0, 1);
+      hb.s[hb.n] = mk_step(tr[0], hb.n, 1, 0, 0);
+      ++hb.n;
+      hb.s[hb.n] = mk_step(h == 0 ? P.rend_t0_aux : P.att_t0_aux, hb.n, 0, 0, 1);
+      ++hb.n;
     }
     std::vector<uint16_t> ones(TILE_AUX_BYTES / 2, 0);
     for (int r = 0; r < TILE_M; ++r) ones[r * 8] = 0x3F80;  // hi plane, chunk 0, column 0 = bf16(1.0)
@@ -497,6 +503,61 @@ int neat_line_geometry(int R, const float* pose, const float* K, const float* uv
   return NEAT_OK;
 }
 
+// ---------------------------------------------------------------- junction clustering
+namespace {
+int db_table_size(int N) {
+  int T = 64;
+  while (T < 2 * N) T <<= 1;
+  return T;
+}
+DbscanWs carve_dbscan_ws(void* ws, int N) {
+  uint8_t* b = static_cast<uint8_t*>(ws);
+  DbscanWs w;
+  w.T = db_table_size(N);
+  w.tkey = reinterpret_cast<unsigned long long*>(b); b += al256(sizeof(unsigned long long) * w.T);
+  w.sums = reinterpret_cast<double*>(b); b += al256(sizeof(double) * 3 * (N / 2 + 1));
+  w.head = reinterpret_cast<int*>(b); b += al256(sizeof(int) * w.T);
+  w.next = reinterpret_cast<int*>(b); b += al256(sizeof(int) * N);
+  w.parent = reinterpret_cast<int*>(b); b += al256(sizeof(int) * N);
+  w.count = reinterpret_cast<int*>(b); b += al256(sizeof(int) * N);
+  w.cid = reinterpret_cast<int*>(b); b += al256(sizeof(int) * N);
+  w.csize = reinterpret_cast<int*>(b);
+  return w;
+}
+}  // namespace
+
+size_t neat_dbscan_workspace_bytes(int N) {
+  if (N <= 0) return 0;
+  const int T = db_table_size(N);
+  return al256(sizeof(unsigned long long) * T) + al256(sizeof(double) * 3 * (N / 2 + 1)) + al256(sizeof(int) * T) +
+         4 * al256(sizeof(int) * N) + al256(sizeof(int) * (N / 2 + 1));
+}
+
+int neat_dbscan(const float* points, int N, float eps, void* workspace, float* centroids, int* n_clusters, void* stream) {
+  if (!points || N <= 0 || !(eps > 0.f) || !workspace || !centroids || !n_clusters) return fail(NEAT_EINVAL, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const DbscanWs w = carve_dbscan_ws(workspace, N);
+  const int nb = (std::max(w.T, N) + 255) / 256, nbN = (N + 255) / 256;
+  const float inv_eps = 1.0f / eps;
+  const double eps2 = static_cast<double>(eps) * static_cast<double>(eps);
+  db_init_kernel<<<nb, 256, 0, st>>>(w, N);
+  ++g_launches;
+  db_insert_kernel<<<nbN, 256, 0, st>>>(w, points, N, inv_eps);
+  ++g_launches;
+  db_link_kernel<<<nbN, 256, 0, st>>>(w, points, N, inv_eps, eps2);
+  ++g_launches;
+  db_count_kernel<<<nbN, 256, 0, st>>>(w, N);
+  ++g_launches;
+  db_rank_kernel<<<1, 1024, 0, st>>>(w, N, n_clusters);
+  ++g_launches;
+  db_sum_kernel<<<nbN, 256, 0, st>>>(w, points, N);
+  ++g_launches;
+  db_mean_kernel<<<(N / 2 + 255) / 256, 256, 0, st>>>(w, n_clusters, centroids);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
 // ---------------------------------------------------------------- backward
 int neat_composite_backward(const neat_composite_bwd_args* a, void* stream) {
   if (!a || a->R <= 0 || a->S <= 0 || a->S > 256 || !a->z || !a->sdf || !a->weights || !a->rgb || !a->rgb_values_bar ||
@@ -699,7 +760,7 @@ int neat_weight_gradients(neat_ctx* c, const neat_grad_group* groups, int n_grou
     CK(cudaMalloc(&c->jobs_dev, sizeof(WJob) * c->jobs_cap));
   }
   CK(cudaMemcpyAsync(c->jobs_dev, jobs.data(), sizeof(WJob) * jobs.size(), cudaMemcpyHostToDevice, st));
-  wgrad_kernel<<<static_cast<int>(jobs.size()), NUM_THREADS, sizeof(WgradSmem) + 1024, st>>>(c->jobs_dev);
+  wgrad_kernel<<<static_cast<int>(jobs.size()), WG_THREADS, sizeof(WgradSmem) + 1024, st>>>(c->jobs_dev);
   ++g_launches;
   CK(cudaGetLastError());
   return NEAT_OK;

@@ -72,103 +72,97 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_bwd_kernel(const __grid_c
   const int my_tiles = (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 4) {
+  if (warp == EPI_WARPS) {
     if (lane == 0) producer_loop(sm, p.prog, p.packed, my_tiles);
-  } else if (warp == 5) {
+  } else if (warp == EPI_WARPS + 1) {
     if (lane == 0) mma_loop(sm, p.prog, my_tiles);
   } else {
-    const int row = threadIdx.x;
-    const uint32_t tm = sm.tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    Epi e = epi_make(sm);
     const HeadSaveLayout fl = head_save_layout(p.HL);
     const HeadBwdSaveLayout bl = head_bwd_layout(p.HL);
-    EpiState es;
     for (int t = 0; t < my_tiles; ++t) {
       const int tile = blockIdx.x + t * gridDim.x;
-      const int pt = tile * TILE_M + row;
+      const int pt = tile * TILE_M + e.row;
       const bool valid = pt < p.M;
       const uint8_t* frec = p.fwd_save + static_cast<size_t>(tile) * fl.total;
       uint8_t* brec = p.bwd_save + static_cast<size_t>(tile) * bl.total;
-      // ---- dL/d(out) -> aux columns 0..15
-      if (row == 0) bulk_wait_read0();
-      epi_bar();
-      {
-        float e[A_AUX_COLS];
+      // ---- stage 0: dL/d(out) -> aux columns 0..15
+      epi_planes_free(e);
+      if (e.j == 0) {
+        float a[A_AUX_COLS];
 #pragma unroll
-        for (int i = 0; i < A_AUX_COLS; ++i) e[i] = 0.f;
+        for (int i = 0; i < A_AUX_COLS; ++i) a[i] = 0.f;
         if (valid) {
 #pragma unroll
           for (int c = 0; c < 6; ++c)
-            if (c < p.out_dim) e[c] = p.out_bar[static_cast<size_t>(pt) * p.out_dim + c];
+            if (c < p.out_dim) a[c] = p.out_bar[static_cast<size_t>(pt) * p.out_dim + c];
         }
 #pragma unroll
-        for (int i = 0; i < A_AUX_COLS / 8; ++i) store_a8(sm.a_hi, sm.a_lo, row, A_MAIN_COLS + 8 * i, e + 8 * i);
+        for (int i = 0; i < A_AUX_COLS / 8; ++i) store_a8(sm.a_hi, sm.a_lo, e.row, A_MAIN_COLS + 8 * i, a + 8 * i);
+        epi_publish_aux(sm);
       }
-      fence_proxy_async();
-      epi_bar();
-      if (row == 0) {
-        bulk_s2g(brec + bl.zb_aux, sm.a_hi + PLANE_MAIN_BYTES, PLANE_AUX_BYTES);
-        bulk_s2g(brec + bl.zb_aux + PLANE_AUX_BYTES, sm.a_lo + PLANE_MAIN_BYTES, PLANE_AUX_BYTES);
-        bulk_commit();
-      }
-      epi_publish_a(sm);
+      epi_publish_all(sm);
+      epi_store_main(e, sm.a_hi + PLANE_MAIN_BYTES, sm.a_lo + PLANE_MAIN_BYTES, brec + bl.zb_aux, PLANE_AUX_BYTES);
       // ---- layers HL-1 .. 1: D = dL/d(u_l);  z_bar_{l-1} = D * [u_l > 0]
       for (int l = p.HL - 1; l >= 1; --l) {
-        const int npad = p.prog.s[p.HL - 1 - l].w.npad;
-        const uint8_t* u_hi = frec + fl.u + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES;
-        epi_wait_d(sm, es);
-        if (row == 0) bulk_wait_read0();
-        epi_bar();
-        for (int c0 = 0; c0 < npad; c0 += 32) {
-          float acc[32];
-          tmem_ld32(tm + c0, acc);
-          tmem_ld_wait();
+        const Step st = p.prog.s[p.HL - 1 - l];
+        const uint8_t* __restrict__ u_hi = frec + fl.u + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES;
+        epi_wait_d(sm, e);
+        epi_planes_free(e);
+        for (int g = 0; g < N_GROUPS; ++g) {
+          const int c0 = epi_col(e, g);
+          if (c0 < st.w.npad) {
+            uint32_t m[2];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t m = load_mask8(u_hi, (c0 >> 3) + j, row);
+            for (int j = 0; j < 2; ++j) m[j] = load_mask8(u_hi, (c0 >> 3) + j, e.row);
+            float acc[16];
+            tmem_ld16(e.tm + st.d_col + c0, acc);
+            tmem_ld_wait();
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-              if (!((m >> q) & 1u)) acc[8 * j + q] = 0.f;
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                if (!((m[j] >> k) & 1u)) acc[8 * j + k] = 0.f;
+            store_a16(sm.a_hi, sm.a_lo, e.row, c0, acc);
           }
-          store_a32(sm.a_hi, sm.a_lo, row, c0, acc);
+          epi_publish_group(sm, g);
         }
-        fence_proxy_async();
-        epi_bar();
-        if (row == 0) {
-          uint8_t* dst = brec + bl.zb + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES;
-          bulk_s2g(dst, sm.a_hi, PLANE_MAIN_BYTES);
-          bulk_s2g(dst + PLANE_MAIN_BYTES, sm.a_lo, PLANE_MAIN_BYTES);
-          bulk_commit();
-        }
-        epi_publish_a(sm);
+        epi_store_main(e, sm.a_hi, sm.a_lo, brec + bl.zb + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);
       }
-      // ---- first layer: dL/d(feature) (D cols 0..F) and dL/d(normal) (D cols 256..258)
+      // ---- first layer: dL/d(feature) (step HL-1) and dL/d(normal) (step HL)
       {
-        const int npad = p.prog.s[p.HL - 1].w.npad;
-        epi_wait_d(sm, es);
+        const Step sf = p.prog.s[p.HL - 1], sa = p.prog.s[p.HL];
+        epi_wait_d(sm, e);
         float* fb = p.feat_bar + static_cast<size_t>(tile) * (256 * TILE_M);
-        for (int c0 = 0; c0 < npad; c0 += 32) {
-          float acc[32];
-          tmem_ld32(tm + c0, acc);
-          tmem_ld_wait();
+        for (int g = 0; g < N_GROUPS; ++g) {
+          const int c0 = epi_col(e, g);
+          if (c0 < sf.w.npad) {
+            float acc[16];
+            tmem_ld16(e.tm + sf.d_col + c0, acc);
+            tmem_ld_wait();
+            if (p.accumulate) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float* dst = fb + (c0 + j) * TILE_M + row;
-            *dst = p.accumulate ? *dst + acc[j] : acc[j];
+              for (int j = 0; j < 16; ++j) acc[j] += fb[(c0 + j) * TILE_M + e.row];
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) fb[(c0 + j) * TILE_M + e.row] = acc[j];
           }
         }
-        float acc[32];
-        tmem_ld32(tm + 256, acc);
-        tmem_ld_wait();
-        if (valid) {
+        if (e.j == 0) {
+          float acc[16];
+          tmem_ld16(e.tm + sa.d_col, acc);
+          tmem_ld_wait();
+          if (valid) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float* dst = p.n_bar + 3 * static_cast<size_t>(pt) + c;
-            *dst = p.accumulate ? *dst + acc[c] : acc[c];
+            for (int c = 0; c < 3; ++c) {
+              float* dst = p.n_bar + 3 * static_cast<size_t>(pt) + c;
+              *dst = p.accumulate ? *dst + acc[c] : acc[c];
+            }
           }
         }
       }
     }
-    if (row == 0) bulk_wait0();
+    if (e.lead) bulk_wait0();
   }
   engine_fini(sm);
 }
@@ -216,124 +210,112 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = p.L;
 
-  if (warp == 4) {
+  if (warp == EPI_WARPS) {
     if (lane == 0) producer_loop(sm, p.prog, p.packed, my_tiles);
-  } else if (warp == 5) {
+  } else if (warp == EPI_WARPS + 1) {
     if (lane == 0) mma_loop(sm, p.prog, my_tiles);
   } else {
-    const int row = threadIdx.x;
-    const uint32_t tm = sm.tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    Epi e = epi_make(sm);
     const SdfSaveLayout fl = sdf_save_layout(L, true);
     const SdfBwdSaveLayout bl = sdf_bwd_layout(L);
-    float* zhat_base = p.zhat + static_cast<size_t>(blockIdx.x) * (L - 1) * (256 * TILE_M);
-    EpiState es;
-    auto store_tile = [&](uint8_t* dst) {  // all 128 threads: publish the main planes of A to global
-      fence_proxy_async();
-      epi_bar();
-      if (row == 0) {
-        bulk_s2g(dst, sm.a_hi, PLANE_MAIN_BYTES);
-        bulk_s2g(dst + PLANE_MAIN_BYTES, sm.a_lo, PLANE_MAIN_BYTES);
-        bulk_commit();
-      }
-    };
+    float* __restrict__ zhat_base = p.zhat + static_cast<size_t>(blockIdx.x) * (L - 1) * (256 * TILE_M);
     for (int t = 0; t < my_tiles; ++t) {
       const int tile = blockIdx.x + t * gridDim.x;
-      const int pt = tile * TILE_M + row;
+      const int pt = tile * TILE_M + e.row;
       const bool valid = pt < p.pts.M;
-      const uint8_t* frec = p.fwd_save + static_cast<size_t>(tile) * fl.total;
+      const uint8_t* __restrict__ frec = p.fwd_save + static_cast<size_t>(tile) * fl.total;
       uint8_t* brec = p.bwd_save + static_cast<size_t>(tile) * bl.total;
-      const float* d1_base = reinterpret_cast<const float*>(frec + fl.d1);
-      float x[3] = {0.f, 0.f, 0.f}, nb[3] = {0.f, 0.f, 0.f};
-      float actv = 0.f;
-      if (valid) {
-        load_point(p.pts, pt, x);
-        actv = p.act ? p.act[pt] : 1.f;
-        nb[0] = actv * p.n_bar[3 * pt]; nb[1] = actv * p.n_bar[3 * pt + 1]; nb[2] = actv * p.n_bar[3 * pt + 2];
-      }
-      // ---------------------------------------------------------------- tangent seed p_0 = J (act * n_bar)
-      if (row == 0) bulk_wait_read0();
-      epi_bar();
-      {
-        float e[A_AUX_COLS];
+      const float* __restrict__ d1_base = reinterpret_cast<const float*>(frec + fl.d1);
+      // ---------------------------------------------------------------- stage 0: tangent seed p_0 = J (act * n_bar)
+      epi_planes_free(e);
+      if (e.j == 0) {
+        float x[3] = {0.f, 0.f, 0.f}, nb[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+          load_point(p.pts, pt, x);
+          const float actv = p.act ? p.act[pt] : 1.f;
+          nb[0] = actv * p.n_bar[3 * pt]; nb[1] = actv * p.n_bar[3 * pt + 1]; nb[2] = actv * p.n_bar[3 * pt + 2];
+        }
+        float a[A_AUX_COLS];
 #pragma unroll
-        for (int i = 0; i < A_AUX_COLS; ++i) e[i] = 0.f;
-        e[0] = nb[0]; e[1] = nb[1]; e[2] = nb[2];
+        for (int i = 0; i < A_AUX_COLS; ++i) a[i] = 0.f;
+        a[0] = nb[0]; a[1] = nb[1]; a[2] = nb[2];
 #pragma unroll
         for (int j = 0; j < 7; ++j) {
           if (j < p.pts.multires) {
             const float f = static_cast<float>(1 << j);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-              float s, co;
-              sincosf(x[c] * f, &s, &co);
-              e[3 + 6 * j + c] = f * co * nb[c];
-              e[3 + 6 * j + 3 + c] = -f * s * nb[c];
+              float sn, co;
+              sincosf(x[c] * f, &sn, &co);
+              a[3 + 6 * j + c] = f * co * nb[c];
+              a[3 + 6 * j + 3 + c] = -f * sn * nb[c];
             }
           }
         }
 #pragma unroll
-        for (int i = 0; i < A_AUX_COLS / 8; ++i) store_a8(sm.a_hi, sm.a_lo, row, A_MAIN_COLS + 8 * i, e + 8 * i);
+        for (int i = 0; i < A_AUX_COLS / 8; ++i) store_a8(sm.a_hi, sm.a_lo, e.row, A_MAIN_COLS + 8 * i, a + 8 * i);
+        epi_publish_aux(sm);
       }
-      fence_proxy_async();
-      epi_bar();
-      if (row == 0) {
-        bulk_s2g(brec + bl.p_aux, sm.a_hi + PLANE_MAIN_BYTES, PLANE_AUX_BYTES);
-        bulk_s2g(brec + bl.p_aux + PLANE_AUX_BYTES, sm.a_lo + PLANE_MAIN_BYTES, PLANE_AUX_BYTES);
-        bulk_commit();
-      }
-      epi_publish_a(sm);
+      epi_publish_all(sm);
+      epi_store_main(e, sm.a_hi + PLANE_MAIN_BYTES, sm.a_lo + PLANE_MAIN_BYTES, brec + bl.p_aux, PLANE_AUX_BYTES);
       // ---------------------------------------------------------------- tangent sweep, layers 0 .. L-2
       for (int l = 0; l < L - 1; ++l) {
-        const int npad = p.prog.s[l].w.npad;
-        const float* d1 = d1_base + static_cast<size_t>(l) * (256 * TILE_M);
-        const uint8_t* a_hi = frec + fl.a + static_cast<size_t>(l) * TILE_MAIN_BYTES;
-        const uint8_t* a_lo = a_hi + PLANE_MAIN_BYTES;
-        float* zh = zhat_base + static_cast<size_t>(l) * (256 * TILE_M);
-        epi_wait_d(sm, es);  // D = q_l = W_l p_l
-        if (row == 0) bulk_wait_read0();
-        epi_bar();
-        for (int c0 = 0; c0 < npad; c0 += 32) {
-          float q[32];
-          tmem_ld32(tm + c0, q);
-          tmem_ld_wait();
+        const Step st = p.prog.s[l];
+        const float* __restrict__ d1 = d1_base + static_cast<size_t>(l) * (256 * TILE_M);
+        const uint8_t* __restrict__ a_hi = frec + fl.a + static_cast<size_t>(l) * TILE_MAIN_BYTES;
+        const uint8_t* __restrict__ a_lo = a_hi + PLANE_MAIN_BYTES;
+        float* __restrict__ zh = zhat_base + static_cast<size_t>(l) * (256 * TILE_M);
+        epi_wait_d(sm, e);  // D = q_l = W_l p_l
+        epi_planes_free(e);
+        for (int g = 0; g < N_GROUPS; ++g) {
+          const int c0 = epi_col(e, g);
+          if (c0 < st.w.npad) {
+            float s1[16], a[16];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float a[8];
-            load_tile8(a_hi, a_lo, (c0 >> 3) + j, row, a);
+            for (int j = 0; j < 16; ++j) s1[j] = __ldg(d1 + (c0 + j) * TILE_M + e.row);
+            load_tile8(a_hi, a_lo, (c0 >> 3), e.row, a);
+            load_tile8(a_hi, a_lo, (c0 >> 3) + 1, e.row, a + 8);
+            float q[16];
+            tmem_ld16(e.tm + st.d_col + c0, q);
+            tmem_ld_wait();
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const int c = c0 + 8 * j + k;
-              const float s1 = d1[c * TILE_M + row];
-              zh[c * TILE_M + row] = SP_BETA * (1.0f - s1) * a[k] * q[8 * j + k];  // sigma'' g_{l+1} q_l
-              q[8 * j + k] *= s1;                                                   // p_{l+1}
+            for (int i = 0; i < 16; ++i) {
+              zh[(c0 + i) * TILE_M + e.row] = SP_BETA * (1.0f - s1[i]) * a[i] * q[i];  // sigma'' g_{l+1} q_l
+              q[i] *= s1[i];                                                            // p_{l+1}
             }
+            store_a16(sm.a_hi, sm.a_lo, e.row, c0, q);
           }
-          store_a32(sm.a_hi, sm.a_lo, row, c0, q);
+          if (l < L - 2) epi_publish_group(sm, g);  // -> F_{l+1}
         }
-        store_tile(brec + bl.p + static_cast<size_t>(l) * TILE_MAIN_BYTES);  // p_{l+1}
-        if (l < L - 2) epi_publish_a(sm);                                     // -> F_{l+1}
+        if (l == L - 2) fence_proxy_async();
+        epi_store_main(e, sm.a_hi, sm.a_lo, brec + bl.p + static_cast<size_t>(l) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);  // p_{l+1}
       }
       // ---------------------------------------------------------------- z_bar_{L-1} = o_bar = [s_bar | feat_bar]
-      if (row == 0) bulk_wait_read0();
-      epi_bar();
+      epi_planes_free(e);
       {
         const int npadF = p.prog.s[L - 1].w.nk_main * 16;  // feature columns read by T_{L-1}
-        const float* fb = p.feat_bar ? p.feat_bar + static_cast<size_t>(tile) * (256 * TILE_M) : nullptr;
-        for (int c0 = 0; c0 < npadF; c0 += 32) {
-          float v[32];
+        const float* __restrict__ fb = p.feat_bar ? p.feat_bar + static_cast<size_t>(tile) * (256 * TILE_M) : nullptr;
+        for (int g = 0; g < N_GROUPS; ++g) {
+          const int c0 = epi_col(e, g);
+          if (c0 < npadF) {
+            float v[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = (fb && valid) ? fb[(c0 + j) * TILE_M + row] : 0.f;
-          store_a32(sm.a_hi, sm.a_lo, row, c0, v);
+            for (int j = 0; j < 16; ++j) v[j] = (fb && valid) ? __ldg(fb + (c0 + j) * TILE_M + e.row) : 0.f;
+            store_a16(sm.a_hi, sm.a_lo, e.row, c0, v);
+          }
         }
-        float e[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (valid && p.s_bar) e[0] = p.s_bar[pt];  // already masked by act (composite_bwd)
-        store_a8(sm.a_hi, sm.a_lo, row, A_MAIN_COLS, e);
-        const float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        store_a8(sm.a_hi, sm.a_lo, row, A_MAIN_COLS + 8, zero8);
+        if (e.j == 0) {
+          float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          const float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (valid && p.s_bar) a8[0] = p.s_bar[pt];  // already masked by act (composite_bwd)
+          store_a8(sm.a_hi, sm.a_lo, e.row, A_MAIN_COLS, a8);
+          store_a8(sm.a_hi, sm.a_lo, e.row, A_MAIN_COLS + 8, zero8);
+          epi_publish_aux(sm);
+        }
       }
-      fence_proxy_async();
+      epi_publish_all(sm);  // -> T_{L-1}
       epi_bar();
-      if (row == 0) {
+      if (e.lead) {
         uint8_t* dst = brec + bl.zb + static_cast<size_t>(L - 1) * TILE_MAIN_BYTES;
         bulk_s2g(dst, sm.a_hi, PLANE_MAIN_BYTES);
         bulk_s2g(dst + PLANE_MAIN_BYTES, sm.a_lo, PLANE_MAIN_BYTES);
@@ -341,31 +323,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
         bulk_s2g(brec + bl.zb_aux + PLANE_AUX_BYTES, sm.a_lo + PLANE_MAIN_BYTES, PLANE_AUX_BYTES);
         bulk_commit();
       }
-      epi_publish_a(sm);  // -> T_{L-1}
       // ---------------------------------------------------------------- reverse sweep: layers L-1 .. 1
       for (int l = L - 1; l >= 1; --l) {
+        const Step st = p.prog.s[(L - 1) + (L - 1 - l)];
         const int ncols = p.prog.s[l - 1].w.npad;  // width of z_bar_{l-1}
-        const float* d1 = d1_base + static_cast<size_t>(l - 1) * (256 * TILE_M);
-        const float* zh = zhat_base + static_cast<size_t>(l - 1) * (256 * TILE_M);
-        epi_wait_d(sm, es);  // D = W_l^T z_bar_l  (gradient w.r.t. the input of layer l)
-        if (row == 0) bulk_wait_read0();
-        epi_bar();
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
-          float g[32];
-          tmem_ld32(tm + c0, g);
-          tmem_ld_wait();
+        const float* __restrict__ d1 = d1_base + static_cast<size_t>(l - 1) * (256 * TILE_M);
+        const float* __restrict__ zh = zhat_base + static_cast<size_t>(l - 1) * (256 * TILE_M);
+        epi_wait_d(sm, e);  // D = W_l^T z_bar_l  (gradient w.r.t. the input of layer l)
+        epi_planes_free(e);
+        for (int g = 0; g < N_GROUPS; ++g) {
+          const int c0 = epi_col(e, g);
+          if (c0 < ncols) {
+            float s1[16], zz[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = c0 + j;
-            g[j] = d1[c * TILE_M + row] * g[j] + zh[c * TILE_M + row];
+            for (int j = 0; j < 16; ++j) {
+              s1[j] = __ldg(d1 + (c0 + j) * TILE_M + e.row);
+              zz[j] = zh[(c0 + j) * TILE_M + e.row];
+            }
+            float gq[16];
+            tmem_ld16(e.tm + st.d_col + c0, gq);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) gq[j] = s1[j] * gq[j] + zz[j];
+            store_a16(sm.a_hi, sm.a_lo, e.row, c0, gq);
           }
-          store_a32(sm.a_hi, sm.a_lo, row, c0, g);
+          if (l >= 2) epi_publish_group(sm, g);  // -> T_{l-1}
         }
-        store_tile(brec + bl.zb + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES);  // z_bar_{l-1}
-        if (l >= 2) epi_publish_a(sm);                                            // -> T_{l-1}
+        if (l < 2) fence_proxy_async();
+        epi_store_main(e, sm.a_hi, sm.a_lo, brec + bl.zb + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);  // z_bar_{l-1}
       }
     }
-    if (row == 0) bulk_wait0();
+    if (e.lead) bulk_wait0();
   }
   engine_fini(sm);
 }

@@ -1,20 +1,23 @@
-// Tile-MLP engine shared by all tensor-core kernels.
+// Tile-MLP engine shared by all tensor-core kernels (v2: column-group pipelining).
 //
-// One CTA owns a tile of 128 points (TMEM lane i == tile row i == thread i of the 4 epilogue warps).
-// The activation tile ("A") stays resident in shared memory as two bf16 planes (hi / lo split of the
-// fp32 value) in the UMMA no-swizzle canonical layout, chunk-major:
+// One CTA owns a tile of 128 points.  TMEM lane i == tile row i.  16 epilogue warps: warp w serves row quadrant
+// q = w % 4 (the TMEM lanes a warp may touch) and, inside every 64-column group, the 16-column slice j = w / 4.
+// The activation tile ("A") stays resident in shared memory as two bf16 planes (hi / lo split of the fp32
+// value) in the UMMA no-swizzle canonical layout, chunk-major:
 //     element (row r, column k)  ->  plane + (k / 8) * 2048 + r * 16 + (k % 8) * 2      [bytes]
-// i.e. an 8-column chunk of all 128 rows is one contiguous 2 KB block.  The same bytes are a valid
-// K-major operand (M = rows, K = columns: layer GEMMs) and a valid MN-major operand
-// (M/N = columns, K = rows: weight-gradient GEMMs).
-// Columns [0,256) are the "main" segment, columns [256,304) the "aux" segment (positional encoding,
-// view dirs, normals ... whatever the first layer of a net concatenates to its main input).
+// i.e. an 8-column chunk of all 128 rows is one contiguous 2 KB block.  The same bytes are a valid K-major
+// operand (layer GEMMs) and a valid MN-major operand (weight-gradient GEMMs).  Columns [0,256) are the "main"
+// segment, columns [256,304) the "aux" segment (positional encoding, view dirs, normals, ...).
 //
-// Weights are pre-packed (pack.cu) into per-k-step slabs in exactly the B-operand layout, so a slab is
-// one contiguous cp.async.bulk (1-D TMA) into a ring of shared-memory stages:
+// Pipelining: the accumulator of layer l lives in one 256-column half of TMEM while layer l+1 accumulates into
+// the other.  All 16 warps work on column group 0 first, then 1, 2, 3; after each group they arrive on a_ready[g]
+// and the MMA issuer starts the k-steps that read those 64 columns: the MMAs of layer l+1 run underneath the
+// epilogue of layer l from its first quarter on.
+//
+// Weights are pre-packed (api.cu) into per-k-step slabs in exactly the B-operand layout, so a slab is one
+// contiguous cp.async.bulk (1-D TMA) into a ring of shared-memory stages:
 //     slab(k-step) = hi plane [2 chunks][npad rows][8] bf16, then lo plane (same shape)
-// Warp roles: warps 0-3 epilogue (TMEM -> registers -> activation -> A tile), warp 4 lane 0 weight
-// producer (TMA), warp 5 lane 0 MMA issuer (tcgen05.mma, 3 MMAs per k-step: hi*hi + hi*lo + lo*hi).
+// Warp 16 lane 0 is the weight producer, warp 17 lane 0 issues tcgen05.mma (3 per k-step: hi*hi+hi*lo+lo*hi).
 #pragma once
 #include "layout.h"
 #include "umma.cuh"
@@ -23,7 +26,7 @@ namespace neat {
 
 // Debug knob (neat_debug_set_desc_swap): exchanges the LBO / SBO fields of every matrix descriptor.
 __constant__ int g_desc_swap = 0;
-// k_stride: bytes between core matrices adjacent along K; mn_stride: along M/N  (K-major operands)
+// k_stride: bytes between core matrices adjacent along K; mn_stride: along M/N
 __device__ __forceinline__ uint64_t make_desc_k(uint32_t saddr, uint32_t k_stride, uint32_t mn_stride) {
   return g_desc_swap ? make_desc(saddr, mn_stride, k_stride) : make_desc(saddr, k_stride, mn_stride);
 }
@@ -35,9 +38,10 @@ struct alignas(1024) EngineSmem {
   uint8_t w[STAGES][W_STAGE_BYTES];
   uint64_t full[STAGES];
   uint64_t empty[STAGES];
-  uint64_t a_ready;
+  uint64_t a_ready[N_GROUPS];  // 512 arrivals each: every epilogue thread, once per column group and stage
+  uint64_t aux_ready;          // 128 arrivals: the group-0 warps
   uint64_t d_ready;
-  uint64_t in_ready;  // bulk loads of input operand tiles (heads / backward kernels)
+  uint64_t in_ready;           // bulk loads of input operand tiles (heads / backward kernels)
   uint32_t tmem_base;
 };
 
@@ -49,12 +53,13 @@ __device__ __forceinline__ void engine_init(EngineSmem<STAGES>& sm) {
       mbar_init(&sm.full[i], 1);
       mbar_init(&sm.empty[i], 1);
     }
-    mbar_init(&sm.a_ready, TILE_M);
+    for (int g = 0; g < N_GROUPS; ++g) mbar_init(&sm.a_ready[g], EPI_THREADS);
+    mbar_init(&sm.aux_ready, 128);
     mbar_init(&sm.d_ready, 1);
     mbar_init(&sm.in_ready, 1);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(&sm.tmem_base, TMEM_COLS);
+  if (warp == EPI_WARPS) tmem_alloc(&sm.tmem_base, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -64,10 +69,10 @@ template <int STAGES>
 __device__ __forceinline__ void engine_fini(EngineSmem<STAGES>& sm) {
   tc_fence_before();
   __syncthreads();
-  if ((threadIdx.x >> 5) == 4) tmem_dealloc(sm.tmem_base, TMEM_COLS);
+  if ((threadIdx.x >> 5) == EPI_WARPS) tmem_dealloc(sm.tmem_base, TMEM_COLS);
 }
 
-// warp 4, lane 0: stream every slab of every step, for every tile this CTA owns
+// producer warp, lane 0: stream every slab of every step, for every tile this CTA owns
 template <int STAGES>
 __device__ __forceinline__ void producer_loop(EngineSmem<STAGES>& sm, const Program& prog, const uint8_t* packed,
                                               int n_tiles) {
@@ -88,68 +93,136 @@ __device__ __forceinline__ void producer_loop(EngineSmem<STAGES>& sm, const Prog
   }
 }
 
-// warp 5, lane 0: issue the MMAs
+// MMA warp, lane 0
 template <int STAGES>
 __device__ __forceinline__ void mma_loop(EngineSmem<STAGES>& sm, const Program& prog, int n_tiles) {
-  uint32_t stage = 0, phase = 0, a_phase = 0;
+  uint32_t stage = 0, phase = 0, a_phase = 0, aux_phase = 0;
   const uint32_t tmem = sm.tmem_base;
   const uint32_t a_hi = smem_u32(sm.a_hi), a_lo = smem_u32(sm.a_lo);
   for (int t = 0; t < n_tiles; ++t) {
     for (int i = 0; i < prog.n; ++i) {
       const Step st = prog.s[i];
-      if (st.wait_a) {
-        mbar_wait(&sm.a_ready, a_phase);
-        a_phase ^= 1;
-        tc_fence_after();
-      }
       const uint32_t npad = st.w.npad;
       const uint32_t idesc = make_idesc(TILE_M, npad, 0, 0);
       const uint32_t d = tmem + st.d_col;
-      const int nk = st.w.nk_main + st.w.nk_aux;
-      for (int ks = 0; ks < nk; ++ks) {
+      uint32_t acc = 0;
+      auto kstep = [&](uint32_t col0) {
         mbar_wait(&sm.full[stage], phase);
         tc_fence_after();
-        const uint32_t col0 = ks < st.w.nk_main ? 16u * ks : A_MAIN_COLS + 16u * (ks - st.w.nk_main);
         const uint32_t a_off = (col0 >> 3) * A_CHUNK_BYTES;
         const uint64_t da_hi = make_desc_k(a_hi + a_off, A_CHUNK_BYTES, 128);
         const uint64_t da_lo = make_desc_k(a_lo + a_off, A_CHUNK_BYTES, 128);
         const uint32_t wb = smem_u32(sm.w[stage]);
         const uint64_t db_hi = make_desc_k(wb, npad * 16, 128);
         const uint64_t db_lo = make_desc_k(wb + npad * 32, npad * 16, 128);
-        umma_bf16(d, da_hi, db_hi, idesc, ks > 0 ? 1u : 0u);
+        umma_bf16(d, da_hi, db_hi, idesc, acc);
         umma_bf16(d, da_hi, db_lo, idesc, 1u);
         umma_bf16(d, da_lo, db_hi, idesc, 1u);
         umma_commit(&sm.empty[stage]);
+        acc = 1u;
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      };
+      if (st.wait_aux) {
+        mbar_wait(&sm.aux_ready, aux_phase);
+        aux_phase ^= 1;
+        tc_fence_after();
       }
+      const int nk_main = st.w.nk_main;
+      for (int g = 0; g < N_GROUPS; ++g) {
+        if (st.wait_a) {
+          mbar_wait(&sm.a_ready[g], a_phase);
+          tc_fence_after();
+        }
+        const int k_end = min(nk_main, (g + 1) * (GROUP_COLS / 16));
+        for (int ks = g * (GROUP_COLS / 16); ks < k_end; ++ks) kstep(16u * ks);
+      }
+      if (st.wait_a) a_phase ^= 1;
+      for (int ks = 0; ks < st.w.nk_aux; ++ks) kstep(A_MAIN_COLS + 16u * ks);
       if (st.commit_d) umma_commit(&sm.d_ready);
     }
   }
 }
 
-// ---------------------------------------------------------------- epilogue-side helpers (warps 0-3)
-struct EpiState {
-  uint32_t d_phase = 0;
+// ---------------------------------------------------------------- epilogue-side helpers (warps 0..15)
+struct Epi {
+  int q, j, lane, row;  // row quadrant, 16-column slice inside a group, lane, tile row
+  uint32_t tm;          // TMEM address of this warp's lanes, column 0
+  uint32_t d_phase;
+  bool lead;            // thread 0: issues bulk stores
 };
-
 template <int STAGES>
-__device__ __forceinline__ void epi_wait_d(EngineSmem<STAGES>& sm, EpiState& es) {
-  mbar_wait(&sm.d_ready, es.d_phase);
-  es.d_phase ^= 1;
+__device__ __forceinline__ Epi epi_make(const EngineSmem<STAGES>& sm) {
+  Epi e;
+  const int warp = threadIdx.x >> 5;
+  e.lane = threadIdx.x & 31;
+  e.q = warp & 3;
+  e.j = warp >> 2;
+  e.row = e.q * 32 + e.lane;
+  e.tm = sm.tmem_base + (static_cast<uint32_t>(e.q * 32) << 16);
+  e.d_phase = 0;
+  e.lead = threadIdx.x == 0;
+  return e;
+}
+template <int STAGES>
+__device__ __forceinline__ void epi_wait_d(EngineSmem<STAGES>& sm, Epi& e) {
+  mbar_wait(&sm.d_ready, e.d_phase);
+  e.d_phase ^= 1;
   tc_fence_after();
 }
-// call after the thread finished writing its row of the A tile (and reading the accumulator)
+// column offset of this warp's 16-column slice in group g
+__device__ __forceinline__ int epi_col(const Epi& e, int g) { return g * GROUP_COLS + 16 * e.j; }
+// after this thread finished writing its slice of group g of the A tile (and reading that part of the accumulator)
 template <int STAGES>
-__device__ __forceinline__ void epi_publish_a(EngineSmem<STAGES>& sm) {
+__device__ __forceinline__ void epi_publish_group(EngineSmem<STAGES>& sm, int g) {
   fence_proxy_async();
   tc_fence_before();
-  mbar_arrive(&sm.a_ready);
+  mbar_arrive(&sm.a_ready[g]);
+}
+// a stage that wrote no main columns still has to arrive on every group (the MMA issuer waits on all of them)
+template <int STAGES>
+__device__ __forceinline__ void epi_publish_all(EngineSmem<STAGES>& sm) {
+  fence_proxy_async();
+  tc_fence_before();
+#pragma unroll
+  for (int g = 0; g < N_GROUPS; ++g) mbar_arrive(&sm.a_ready[g]);
+}
+template <int STAGES>
+__device__ __forceinline__ void epi_publish_aux(EngineSmem<STAGES>& sm) {  // slice-0 warps (j == 0) only
+  fence_proxy_async();
+  tc_fence_before();
+  mbar_arrive(&sm.aux_ready);
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+// the previous bulk store out of the A planes must have finished reading before the planes are overwritten
+__device__ __forceinline__ void epi_planes_free(const Epi& e) {
+  if (e.lead) bulk_wait_read0();
+  epi_bar();
+}
+// all epilogue threads: after everyone wrote (and fenced) its columns, store both main planes to global
+__device__ __forceinline__ void epi_store_main(const Epi& e, const uint8_t* a_hi, const uint8_t* a_lo, uint8_t* dst,
+                                               int plane_bytes) {
+  epi_bar();
+  if (e.lead) {
+    bulk_s2g(dst, a_hi, plane_bytes);
+    bulk_s2g(dst + plane_bytes, a_lo, plane_bytes);
+    bulk_commit();
+  }
 }
 
 // write 32 consecutive columns [c0, c0+32) of row `row` (c0 % 8 == 0) into the A tile
 __device__ __forceinline__ void store_a32(uint8_t* a_hi, uint8_t* a_lo, int row, int c0, const float* v) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
+    uint4 hi, lo;
+    split8(v + 8 * j, hi, lo);
+    const int off = ((c0 >> 3) + j) * A_CHUNK_BYTES + row * 16;
+    *reinterpret_cast<uint4*>(a_hi + off) = hi;
+    *reinterpret_cast<uint4*>(a_lo + off) = lo;
+  }
+}
+__device__ __forceinline__ void store_a16(uint8_t* a_hi, uint8_t* a_lo, int row, int c0, const float* v) {
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
     uint4 hi, lo;
     split8(v + 8 * j, hi, lo);
     const int off = ((c0 >> 3) + j) * A_CHUNK_BYTES + row * 16;
@@ -188,23 +261,6 @@ __device__ __forceinline__ void softplus100_d1(float z, float& h, float& d1) {
   const bool lin = bz > SP_THRESH;
   h = lin ? z : sp;
   d1 = lin ? 1.0f : sg;
-}
-
-// NeRF positional encoding of a 3-vector: [x, sin(2^j x), cos(2^j x)]_{j<L}  (embedder.py:5-36)
-// out must hold 3 + 6 L floats
-__device__ __forceinline__ void embed3(const float x[3], int L, float* out) {
-  out[0] = x[0]; out[1] = x[1]; out[2] = x[2];
-  float f = 1.0f;
-  for (int j = 0; j < L; ++j) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float s, co;
-      sincosf(x[c] * f, &s, &co);
-      out[3 + 6 * j + c] = s;
-      out[3 + 6 * j + 3 + c] = co;
-    }
-    f *= 2.0f;
-  }
 }
 
 }  // namespace neat

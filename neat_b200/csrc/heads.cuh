@@ -44,42 +44,43 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_fwd_kernel(const __grid_c
   const int my_tiles = (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 4) {
+  if (warp == EPI_WARPS) {
     if (lane == 0) producer_loop(sm, p.prog, p.packed, my_tiles);
-  } else if (warp == 5) {
+  } else if (warp == EPI_WARPS + 1) {
     if (lane == 0) mma_loop(sm, p.prog, my_tiles);
   } else {
-    const int row = threadIdx.x;
-    const uint32_t tm = sm.tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    Epi e = epi_make(sm);
     const HeadSaveLayout lay = head_save_layout(p.HL);
-    EpiState es;
+    const bool tr = p.training != 0;
     uint32_t in_phase = 0;
     for (int t = 0; t < my_tiles; ++t) {
       const int tile = blockIdx.x + t * gridDim.x;
-      const int pt = tile * TILE_M + row;
+      const int pt = tile * TILE_M + e.row;
       const bool valid = pt < p.pts.M;
-      uint8_t* rec = p.training ? p.save + static_cast<size_t>(tile) * lay.total : nullptr;
-      float x[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f}, nrm[3] = {0.f, 0.f, 0.f};
-      if (valid) {
-        load_point(p.pts, pt, x);
-        const float* dp = p.dirs ? p.dirs + 3 * static_cast<size_t>(pt) : p.pts.rays_d + 3 * static_cast<size_t>(pt / p.pts.n_per_ray);
-        d[0] = dp[0]; d[1] = dp[1]; d[2] = dp[2];
-        nrm[0] = p.normals[3 * pt]; nrm[1] = p.normals[3 * pt + 1]; nrm[2] = p.normals[3 * pt + 2];
-      }
-      if (row == 0) {
-        bulk_wait_read0();  // saves of the previous tile finished reading the A planes
+      uint8_t* rec = tr ? p.save + static_cast<size_t>(tile) * lay.total : nullptr;
+      float x[3] = {0.f, 0.f, 0.f};
+      // ---- stage 0: feature tile by bulk copy into the main planes, [x, view, normal] into the aux columns
+      epi_planes_free(e);
+      if (e.lead) {
         const uint8_t* src = p.feat_tiles + static_cast<size_t>(tile) * TILE_MAIN_BYTES;
         mbar_arrive_expect_tx(&sm.in_ready, TILE_MAIN_BYTES);
         bulk_g2s(sm.a_hi, src, PLANE_MAIN_BYTES, &sm.in_ready);
         bulk_g2s(sm.a_lo, src + PLANE_MAIN_BYTES, PLANE_MAIN_BYTES, &sm.in_ready);
       }
-      // aux = [x, view, normal], zero padded
-      {
-        float e[A_AUX_COLS];
+      if (e.j == 0) {
+        float d[3] = {0.f, 0.f, 0.f}, nrm[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+          load_point(p.pts, pt, x);
+          const float* dp = p.dirs ? p.dirs + 3 * static_cast<size_t>(pt)
+                                   : p.pts.rays_d + 3 * static_cast<size_t>(pt / p.pts.n_per_ray);
+          d[0] = dp[0]; d[1] = dp[1]; d[2] = dp[2];
+          nrm[0] = p.normals[3 * pt]; nrm[1] = p.normals[3 * pt + 1]; nrm[2] = p.normals[3 * pt + 2];
+        }
+        float a[A_AUX_COLS];
 #pragma unroll
-        for (int i = 0; i < A_AUX_COLS; ++i) e[i] = 0.f;
-        e[0] = x[0]; e[1] = x[1]; e[2] = x[2];
-        e[3] = d[0]; e[4] = d[1]; e[5] = d[2];
+        for (int i = 0; i < A_AUX_COLS; ++i) a[i] = 0.f;
+        a[0] = x[0]; a[1] = x[1]; a[2] = x[2];
+        a[3] = d[0]; a[4] = d[1]; a[5] = d[2];
         int nv = 3;
         if (p.head == 0 && p.multires_view > 0) {
 #pragma unroll
@@ -88,90 +89,78 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_fwd_kernel(const __grid_c
               const float f = static_cast<float>(1 << j);
 #pragma unroll
               for (int c = 0; c < 3; ++c) {
-                float s, co;
-                sincosf(d[c] * f, &s, &co);
-                e[3 + 3 + 6 * j + c] = s;
-                e[3 + 3 + 6 * j + 3 + c] = co;
+                float sn, co;
+                sincosf(d[c] * f, &sn, &co);
+                a[3 + 3 + 6 * j + c] = sn;
+                a[3 + 3 + 6 * j + 3 + c] = co;
               }
             }
           }
           nv = 3 + 6 * p.multires_view;
         }
-        // normals follow the view block: dynamic position -> select with predicated writes
 #pragma unroll
-        for (int i = 6; i < A_AUX_COLS - 2; ++i) {
-          if (i == 3 + nv) { e[i] = nrm[0]; e[i + 1] = nrm[1]; e[i + 2] = nrm[2]; }
+        for (int i = 6; i < A_AUX_COLS - 2; ++i) {  // normals follow the view block (position known at run time)
+          if (i == 3 + nv) { a[i] = nrm[0]; a[i + 1] = nrm[1]; a[i + 2] = nrm[2]; }
         }
 #pragma unroll
-        for (int i = 0; i < A_AUX_COLS / 8; ++i) store_a8(sm.a_hi, sm.a_lo, row, A_MAIN_COLS + 8 * i, e + 8 * i);
+        for (int i = 0; i < A_AUX_COLS / 8; ++i) store_a8(sm.a_hi, sm.a_lo, e.row, A_MAIN_COLS + 8 * i, a + 8 * i);
+        epi_publish_aux(sm);
       }
-      fence_proxy_async();
-      if (p.training) {
-        epi_bar();
-        if (row == 0) {
-          bulk_s2g(rec + lay.aux, sm.a_hi + PLANE_MAIN_BYTES, PLANE_AUX_BYTES);
-          bulk_s2g(rec + lay.aux + PLANE_AUX_BYTES, sm.a_lo + PLANE_MAIN_BYTES, PLANE_AUX_BYTES);
-          bulk_commit();
-        }
-      }
-      if (row == 0) mbar_wait(&sm.in_ready, in_phase);
+      if (e.lead) mbar_wait(&sm.in_ready, in_phase);  // the feature planes have landed
       in_phase ^= 1;
-      epi_publish_a(sm);
+      epi_bar();
+      epi_publish_all(sm);
+      if (tr) epi_store_main(e, sm.a_hi + PLANE_MAIN_BYTES, sm.a_lo + PLANE_MAIN_BYTES, rec + lay.aux, PLANE_AUX_BYTES);
 
       for (int l = 0; l < p.HL - 1; ++l) {
-        const PLayer w = p.prog.s[l].w;
-        const float4* bias = reinterpret_cast<const float4*>(p.packed + w.bias_off);
-        epi_wait_d(sm, es);
-        if (row == 0) bulk_wait_read0();
-        epi_bar();
-        for (int c0 = 0; c0 < w.npad; c0 += 32) {
-          float acc[32];
-          tmem_ld32(tm + c0, acc);
-          tmem_ld_wait();
+        const Step st = p.prog.s[l];
+        const float4* bias = reinterpret_cast<const float4*>(p.packed + st.w.bias_off);
+        epi_wait_d(sm, e);
+        if (tr) epi_planes_free(e);
+        for (int g = 0; g < N_GROUPS; ++g) {
+          const int c0 = epi_col(e, g);
+          if (c0 < st.w.npad) {
+            float acc[16];
+            tmem_ld16(e.tm + st.d_col + c0, acc);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(bias + (c0 >> 2) + j);
-            acc[4 * j + 0] = fmaxf(acc[4 * j + 0] + b.x, 0.f);
-            acc[4 * j + 1] = fmaxf(acc[4 * j + 1] + b.y, 0.f);
-            acc[4 * j + 2] = fmaxf(acc[4 * j + 2] + b.z, 0.f);
-            acc[4 * j + 3] = fmaxf(acc[4 * j + 3] + b.w, 0.f);
+            for (int j = 0; j < 4; ++j) {
+              const float4 b = __ldg(bias + (c0 >> 2) + j);
+              acc[4 * j + 0] = fmaxf(acc[4 * j + 0] + b.x, 0.f);
+              acc[4 * j + 1] = fmaxf(acc[4 * j + 1] + b.y, 0.f);
+              acc[4 * j + 2] = fmaxf(acc[4 * j + 2] + b.z, 0.f);
+              acc[4 * j + 3] = fmaxf(acc[4 * j + 3] + b.w, 0.f);
+            }
+            store_a16(sm.a_hi, sm.a_lo, e.row, c0, acc);
           }
-          store_a32(sm.a_hi, sm.a_lo, row, c0, acc);
+          epi_publish_group(sm, g);
         }
-        fence_proxy_async();
-        if (p.training) {
-          epi_bar();
-          if (row == 0) {
-            uint8_t* dst = rec + lay.u + static_cast<size_t>(l) * TILE_MAIN_BYTES;
-            bulk_s2g(dst, sm.a_hi, PLANE_MAIN_BYTES);
-            bulk_s2g(dst + PLANE_MAIN_BYTES, sm.a_lo, PLANE_MAIN_BYTES);
-            bulk_commit();
-          }
-        }
-        epi_publish_a(sm);
+        if (tr) epi_store_main(e, sm.a_hi, sm.a_lo, rec + lay.u + static_cast<size_t>(l) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);
       }
       {
-        const PLayer w = p.prog.s[p.HL - 1].w;
-        const float* bias = reinterpret_cast<const float*>(p.packed + w.bias_off);
-        epi_wait_d(sm, es);
-        float acc[32];
-        tmem_ld32(tm, acc);
-        tmem_ld_wait();
-        if (valid) {
-          if (p.head == 0) {
+        const Step st = p.prog.s[p.HL - 1];
+        const float* bias = reinterpret_cast<const float*>(p.packed + st.w.bias_off);
+        epi_wait_d(sm, e);
+        if (e.j == 0) {
+          float acc[16];
+          tmem_ld16(e.tm + st.d_col, acc);
+          tmem_ld_wait();
+          if (valid) {
+            if (p.head == 0) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              const float v = acc[c] + __ldg(bias + c);
-              p.out[3 * static_cast<size_t>(pt) + c] = 1.0f / (1.0f + expf(-v));
+              for (int c = 0; c < 3; ++c) {
+                const float v = acc[c] + __ldg(bias + c);
+                p.out[3 * static_cast<size_t>(pt) + c] = 1.0f / (1.0f + expf(-v));
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 6; ++c) p.out[6 * static_cast<size_t>(pt) + c] = x[c % 3] + acc[c] + __ldg(bias + c);
             }
-          } else {
-#pragma unroll
-            for (int c = 0; c < 6; ++c) p.out[6 * static_cast<size_t>(pt) + c] = x[c % 3] + acc[c] + __ldg(bias + c);
           }
         }
       }
     }
-    if (row == 0) bulk_wait0();
+    if (e.lead) bulk_wait0();
   }
   engine_fini(sm);
 }

@@ -11,8 +11,12 @@ constexpr int A_CHUNK_BYTES = TILE_M * 16;                                     /
 constexpr int A_PLANE_BYTES = (A_MAIN_COLS + A_AUX_COLS) / 8 * A_CHUNK_BYTES;  // 77824
 constexpr int W_STAGE_BYTES = 256 * 64;                                        // 16384 (npad = 256)
 constexpr int MAX_STEPS = 28;
-constexpr int NUM_THREADS = 192;
-constexpr uint32_t TMEM_COLS = 512;
+constexpr int EPI_WARPS = 16;                        // 4 row quadrants (TMEM lane groups) x 4 column groups
+constexpr int N_GROUPS = EPI_WARPS / 4;              // column groups
+constexpr int GROUP_COLS = A_MAIN_COLS / N_GROUPS;   // 64 columns per group
+constexpr int EPI_THREADS = EPI_WARPS * 32;          // 512
+constexpr int NUM_THREADS = EPI_THREADS + 64;        // + weight producer warp + MMA issuer warp
+constexpr uint32_t TMEM_COLS = 512;                  // two 256-column fp32 accumulators
 
 struct PLayer {        // a packed weight matrix: (nk_main + nk_aux) slabs of npad*64 bytes, then padded fp32 bias
   uint32_t off;        // byte offset of slab 0 in the packed buffer
@@ -25,7 +29,8 @@ struct PLayer {        // a packed weight matrix: (nk_main + nk_aux) slabs of np
 struct Step {          // one GEMM of a kernel's program
   PLayer w;
   uint16_t d_col;      // TMEM column of the accumulator
-  uint8_t wait_a;      // 1: wait until the epilogue published the A tile
+  uint8_t wait_a;      // 1: wait (group by group) until the epilogue published the main columns of the A tile
+  uint8_t wait_aux;    // 1: wait until the aux columns were published
   uint8_t commit_d;    // 1: signal the epilogue when this GEMM (and all before it) completed
 };
 

@@ -70,53 +70,61 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_query_kernel(const __grid_
   const int my_tiles = (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 4) {
+  if (warp == EPI_WARPS) {
     if (lane == 0) producer_loop(sm, p.prog, p.packed, my_tiles);
-  } else if (warp == 5) {
+  } else if (warp == EPI_WARPS + 1) {
     if (lane == 0) mma_loop(sm, p.prog, my_tiles);
   } else {
-    const int row = threadIdx.x;
-    const uint32_t tm = sm.tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    EpiState es;
+    Epi e = epi_make(sm);
     for (int t = 0; t < my_tiles; ++t) {
-      const int pt = (blockIdx.x + t * gridDim.x) * TILE_M + row;
+      const int pt = (blockIdx.x + t * gridDim.x) * TILE_M + e.row;
       const bool valid = pt < p.M;
       float x[3] = {0.f, 0.f, 0.f};
-      if (valid) load_point(p, pt, x);
-      pe_to_aux(sm.a_hi, sm.a_lo, row, x, p.multires);
-      epi_publish_a(sm);
+      // ---- stage 0: the group-0 warps generate the point and its positional encoding (aux columns)
+      if (e.j == 0) {
+        if (valid) load_point(p, pt, x);
+        pe_to_aux(sm.a_hi, sm.a_lo, e.row, x, p.multires);
+        epi_publish_aux(sm);
+      }
+      epi_publish_all(sm);
+      // ---- hidden layers: each warp turns its 64 accumulator columns into the next layer's input
       for (int l = 0; l < p.prog.n - 1; ++l) {
-        const PLayer w = p.prog.s[l].w;
-        const float4* bias = reinterpret_cast<const float4*>(p.packed + w.bias_off);
-        epi_wait_d(sm, es);
-        for (int c0 = 0; c0 < w.npad; c0 += 32) {
-          float acc[32];
-          tmem_ld32(tm + c0, acc);
-          tmem_ld_wait();
+        const Step st = p.prog.s[l];
+        const float4* bias = reinterpret_cast<const float4*>(p.packed + st.w.bias_off);
+        epi_wait_d(sm, e);
+        for (int g = 0; g < N_GROUPS; ++g) {
+          const int c0 = epi_col(e, g);
+          if (c0 < st.w.npad) {
+            float acc[16];
+            tmem_ld16(e.tm + st.d_col + c0, acc);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(bias + (c0 >> 2) + j);
-            acc[4 * j + 0] = softplus100(acc[4 * j + 0] + b.x);
-            acc[4 * j + 1] = softplus100(acc[4 * j + 1] + b.y);
-            acc[4 * j + 2] = softplus100(acc[4 * j + 2] + b.z);
-            acc[4 * j + 3] = softplus100(acc[4 * j + 3] + b.w);
+            for (int j = 0; j < 4; ++j) {
+              const float4 b = __ldg(bias + (c0 >> 2) + j);
+              acc[4 * j + 0] = softplus100(acc[4 * j + 0] + b.x);
+              acc[4 * j + 1] = softplus100(acc[4 * j + 1] + b.y);
+              acc[4 * j + 2] = softplus100(acc[4 * j + 2] + b.z);
+              acc[4 * j + 3] = softplus100(acc[4 * j + 3] + b.w);
+            }
+            store_a16(sm.a_hi, sm.a_lo, e.row, c0, acc);
           }
-          store_a32(sm.a_hi, sm.a_lo, row, c0, acc);
+          epi_publish_group(sm, g);
         }
-        epi_publish_a(sm);
       }
       {
-        const PLayer w = p.prog.s[p.prog.n - 1].w;
-        epi_wait_d(sm, es);
-        float acc[32];
-        tmem_ld32(tm, acc);
-        tmem_ld_wait();
-        float s = acc[0] + __ldg(reinterpret_cast<const float*>(p.packed + w.bias_off));
-        if (p.sphere_r > 0.f) {
-          const float nrm = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
-          s = fminf(s, p.sphere_scale * (p.sphere_r - nrm));
+        const Step st = p.prog.s[p.prog.n - 1];
+        epi_wait_d(sm, e);
+        if (e.j == 0) {
+          float acc[16];
+          tmem_ld16(e.tm + st.d_col, acc);
+          tmem_ld_wait();
+          float s = acc[0] + __ldg(reinterpret_cast<const float*>(p.packed + st.w.bias_off));
+          if (p.sphere_r > 0.f) {
+            const float nrm = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+            s = fminf(s, p.sphere_scale * (p.sphere_r - nrm));
+          }
+          if (valid) p.sdf[pt] = s;
         }
-        if (valid) p.sdf[pt] = s;
       }
     }
   }

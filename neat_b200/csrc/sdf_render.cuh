@@ -55,8 +55,6 @@ struct SdfRenderParams {
   uint8_t* save;       // training: [n_tiles][layout.total]; inference: [gridDim.x][layout.total]
 };
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
 template <int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid_constant__ SdfRenderParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -68,108 +66,97 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = p.L;
 
-  if (warp == 4) {
+  if (warp == EPI_WARPS) {
     if (lane == 0) producer_loop(sm, p.prog, p.packed, my_tiles);
-  } else if (warp == 5) {
+  } else if (warp == EPI_WARPS + 1) {
     if (lane == 0) mma_loop(sm, p.prog, my_tiles);
   } else {
-    const int row = threadIdx.x;
-    const uint32_t tm = sm.tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    Epi e = epi_make(sm);
     const SdfSaveLayout lay = sdf_save_layout(L, p.training != 0);
-    const float* w_row = reinterpret_cast<const float*>(p.packed + p.w_last_row_off);
-    EpiState es;
+    const float* __restrict__ w_row = reinterpret_cast<const float*>(p.packed + p.w_last_row_off);
+    const bool tr = p.training != 0;
     for (int t = 0; t < my_tiles; ++t) {
       const int tile = blockIdx.x + t * gridDim.x;
-      const int pt = tile * TILE_M + row;
+      const int pt = tile * TILE_M + e.row;
       const bool valid = pt < p.pts.M;
-      uint8_t* rec = p.save + static_cast<size_t>(p.training ? tile : static_cast<int>(blockIdx.x)) * lay.total;
+      uint8_t* rec = p.save + static_cast<size_t>(tr ? tile : static_cast<int>(blockIdx.x)) * lay.total;
       float* d1_base = reinterpret_cast<float*>(rec + lay.d1);
       float* rskip = reinterpret_cast<float*>(rec + lay.rskip);
       float x[3] = {0.f, 0.f, 0.f};
-      if (valid) load_point(p.pts, pt, x);
+      if (e.j == 0 && valid) load_point(p.pts, pt, x);
 
-      // previous tile's last bulk store must have finished reading the A planes
-      if (row == 0) bulk_wait_read0();
-      epi_bar();
-      pe_to_aux(sm.a_hi, sm.a_lo, row, x, p.pts.multires);
-      fence_proxy_async();
-      if (p.training) {
-        epi_bar();
-        if (row == 0) {
-          bulk_s2g(rec + lay.pe, sm.a_hi + PLANE_MAIN_BYTES, PLANE_AUX_BYTES);
-          bulk_s2g(rec + lay.pe + PLANE_AUX_BYTES, sm.a_lo + PLANE_MAIN_BYTES, PLANE_AUX_BYTES);
-          bulk_commit();
-        }
+      // ------------------------------------------------------------ stage 0: positional encoding
+      epi_planes_free(e);
+      if (e.j == 0) {
+        pe_to_aux(sm.a_hi, sm.a_lo, e.row, x, p.pts.multires);
+        epi_publish_aux(sm);
       }
-      epi_publish_a(sm);
+      epi_publish_all(sm);
+      if (tr) epi_store_main(e, sm.a_hi + PLANE_MAIN_BYTES, sm.a_lo + PLANE_MAIN_BYTES, rec + lay.pe, PLANE_AUX_BYTES);
 
       // ------------------------------------------------------------ forward pass, hidden layers
       for (int l = 0; l < L - 1; ++l) {
-        const PLayer w = p.prog.s[l].w;
-        const float4* bias = reinterpret_cast<const float4*>(p.packed + w.bias_off);
+        const Step st = p.prog.s[l];
+        const float4* bias = reinterpret_cast<const float4*>(p.packed + st.w.bias_off);
         float* d1 = d1_base + static_cast<size_t>(l) * (256 * TILE_M);
-        epi_wait_d(sm, es);
-        if (row == 0) bulk_wait_read0();
-        epi_bar();
-        for (int c0 = 0; c0 < w.npad; c0 += 32) {
-          float acc[32];
-          tmem_ld32(tm + c0, acc);
-          tmem_ld_wait();
+        epi_wait_d(sm, e);
+        if (tr) epi_planes_free(e);
+        for (int g = 0; g < N_GROUPS; ++g) {
+          const int c0 = epi_col(e, g);
+          if (c0 < st.w.npad) {
+            float acc[16];
+            tmem_ld16(e.tm + st.d_col + c0, acc);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(bias + (c0 >> 2) + j);
-            const float bb[4] = {b.x, b.y, b.z, b.w};
+            for (int j = 0; j < 4; ++j) {
+              const float4 b = __ldg(bias + (c0 >> 2) + j);
+              const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float h, dd;
-              softplus100_d1(acc[4 * j + q] + bb[q], h, dd);
-              acc[4 * j + q] = h;
-              d1[(c0 + 4 * j + q) * TILE_M + row] = dd;
+              for (int k = 0; k < 4; ++k) {
+                float hv, dd;
+                softplus100_d1(acc[4 * j + k] + bb[k], hv, dd);
+                acc[4 * j + k] = hv;
+                d1[(c0 + 4 * j + k) * TILE_M + e.row] = dd;
+              }
             }
+            store_a16(sm.a_hi, sm.a_lo, e.row, c0, acc);
           }
-          store_a32(sm.a_hi, sm.a_lo, row, c0, acc);
+          epi_publish_group(sm, g);
         }
-        fence_proxy_async();
-        if (p.training) {
-          epi_bar();
-          if (row == 0) {
-            uint8_t* dst = rec + lay.u + static_cast<size_t>(l) * TILE_MAIN_BYTES;
-            bulk_s2g(dst, sm.a_hi, PLANE_MAIN_BYTES);
-            bulk_s2g(dst + PLANE_MAIN_BYTES, sm.a_lo, PLANE_MAIN_BYTES);
-            bulk_commit();
-          }
-        }
-        epi_publish_a(sm);
+        if (tr) epi_store_main(e, sm.a_hi, sm.a_lo, rec + lay.u + static_cast<size_t>(l) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);
       }
 
-      // ------------------------------------------------------------ last layer: features + sdf
-      float s_raw;
+      // ------------------------------------------------------------ last layer: sdf (step L-1) + features (step L)
+      float s_raw = 0.f;
       {
-        const PLayer wf = p.prog.s[L - 1].w, ws = p.prog.s[L].w;
-        const float4* bias = reinterpret_cast<const float4*>(p.packed + wf.bias_off);
-        epi_wait_d(sm, es);
-        if (row == 0) bulk_wait_read0();
-        epi_bar();
-        {
-          float acc[32];
-          tmem_ld32(tm + 256, acc);
+        const Step ss = p.prog.s[L - 1], sf = p.prog.s[L];
+        const float4* bias = reinterpret_cast<const float4*>(p.packed + sf.w.bias_off);
+        epi_wait_d(sm, e);
+        if (tr) epi_planes_free(e);
+        if (e.j == 0) {
+          float acc[16];
+          tmem_ld16(e.tm + ss.d_col, acc);
           tmem_ld_wait();
-          s_raw = acc[0] + __ldg(reinterpret_cast<const float*>(p.packed + ws.bias_off));
+          s_raw = acc[0] + __ldg(reinterpret_cast<const float*>(p.packed + ss.w.bias_off));
         }
-        for (int c0 = 0; c0 < wf.npad; c0 += 32) {
-          float acc[32];
-          tmem_ld32(tm + c0, acc);
-          tmem_ld_wait();
+        for (int g = 0; g < N_GROUPS; ++g) {
+          const int c0 = epi_col(e, g);
+          if (c0 < sf.w.npad) {
+            float acc[16];
+            tmem_ld16(e.tm + sf.d_col + c0, acc);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(bias + (c0 >> 2) + j);
-            acc[4 * j + 0] += b.x; acc[4 * j + 1] += b.y; acc[4 * j + 2] += b.z; acc[4 * j + 3] += b.w;
+            for (int j = 0; j < 4; ++j) {
+              const float4 b = __ldg(bias + (c0 >> 2) + j);
+              acc[4 * j + 0] += b.x; acc[4 * j + 1] += b.y; acc[4 * j + 2] += b.z; acc[4 * j + 3] += b.w;
+            }
+            store_a16(sm.a_hi, sm.a_lo, e.row, c0, acc);
           }
-          store_a32(sm.a_hi, sm.a_lo, row, c0, acc);
         }
         fence_proxy_async();
+        tc_fence_before();
         epi_bar();
-        if (row == 0 && p.feat_tiles) {
+        if (e.lead && p.feat_tiles) {
           uint8_t* dst = p.feat_tiles + static_cast<size_t>(tile) * TILE_MAIN_BYTES;
           bulk_s2g(dst, sm.a_hi, PLANE_MAIN_BYTES);
           bulk_s2g(dst + PLANE_MAIN_BYTES, sm.a_lo, PLANE_MAIN_BYTES);
@@ -177,111 +164,110 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
           bulk_wait_read0();
         }
         epi_bar();
+        tc_fence_after();
       }
 
-      // ------------------------------------------------------------ normal pass
-      // seed: a_{L-2} = sigma'_{L-2} * W_{L-1}[0, :]
+      // ------------------------------------------------------------ normal pass seed: a_{L-2} = sigma'_{L-2} * W_{L-1}[0,:]
       {
         const float* d1 = d1_base + static_cast<size_t>(L - 2) * (256 * TILE_M);
         const int npad = p.prog.s[L - 2].w.npad;
-        for (int c0 = 0; c0 < npad; c0 += 32) {
-          float a[32];
+        for (int g = 0; g < N_GROUPS; ++g) {
+          const int c0 = epi_col(e, g);
+          if (c0 < npad) {
+            float a[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) a[j] = d1[(c0 + j) * TILE_M + row] * __ldg(w_row + c0 + j);
-          store_a32(sm.a_hi, sm.a_lo, row, c0, a);
-        }
-        fence_proxy_async();
-        if (p.training) {
-          epi_bar();
-          if (row == 0) {
-            uint8_t* dst = rec + lay.a + static_cast<size_t>(L - 2) * TILE_MAIN_BYTES;
-            bulk_s2g(dst, sm.a_hi, PLANE_MAIN_BYTES);
-            bulk_s2g(dst + PLANE_MAIN_BYTES, sm.a_lo, PLANE_MAIN_BYTES);
-            bulk_commit();
+            for (int j = 0; j < 16; ++j) a[j] = d1[(c0 + j) * TILE_M + e.row] * __ldg(w_row + c0 + j);
+            store_a16(sm.a_hi, sm.a_lo, e.row, c0, a);
           }
+          epi_publish_group(sm, g);
         }
-        epi_publish_a(sm);
+        if (tr) epi_store_main(e, sm.a_hi, sm.a_lo, rec + lay.a + static_cast<size_t>(L - 2) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);
       }
-      // transposed layers l = L-2 .. 1 : D = v_l (gradient w.r.t. the input of layer l) -> a_{l-1}
+      // ------------------------------------------------------------ transposed layers l = L-2 .. 1: D = v_l -> a_{l-1}
       for (int l = L - 2; l >= 1; --l) {
-        const int step = (L + 1) + (L - 2 - l);
-        const int npad = p.prog.s[step].w.npad;  // width of the input of layer l
+        const Step st = p.prog.s[(L + 1) + (L - 2 - l)];
+        const int npad = st.w.npad;                            // width of the input of layer l
         const float* d1 = d1_base + static_cast<size_t>(l - 1) * (256 * TILE_M);
-        const int n_main = (l == p.skip) ? p.H - p.E : npad;  // columns that feed a_{l-1}
-        epi_wait_d(sm, es);
-        if (row == 0) bulk_wait_read0();
-        epi_bar();
-        for (int c0 = 0; c0 < npad; c0 += 32) {
-          float acc[32];
-          tmem_ld32(tm + c0, acc);
-          tmem_ld_wait();
-          if (l == p.skip) {
+        const int n_main = (l == p.skip) ? p.H - p.E : npad;   // columns that feed a_{l-1}
+        epi_wait_d(sm, e);
+        if (tr) epi_planes_free(e);
+        for (int g = 0; g < N_GROUPS; ++g) {
+          const int c0 = epi_col(e, g);
+          if (c0 < npad) {
+            float s1[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int c = c0 + j;
-              if (c >= n_main) rskip[(c - n_main) * TILE_M + row] = acc[j];
+            for (int j = 0; j < 16; ++j) s1[j] = d1[(c0 + j) * TILE_M + e.row];
+            float acc[16];
+            tmem_ld16(e.tm + st.d_col + c0, acc);
+            tmem_ld_wait();
+            if (l == p.skip) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int c = c0 + j;
+                if (c >= n_main) rskip[(c - n_main) * TILE_M + e.row] = acc[j];
+              }
             }
-          }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] *= d1[(c0 + j) * TILE_M + row];
-          store_a32(sm.a_hi, sm.a_lo, row, c0, acc);
-        }
-        fence_proxy_async();
-        if (p.training) {
-          epi_bar();
-          if (row == 0) {
-            uint8_t* dst = rec + lay.a + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES;
-            bulk_s2g(dst, sm.a_hi, PLANE_MAIN_BYTES);
-            bulk_s2g(dst + PLANE_MAIN_BYTES, sm.a_lo, PLANE_MAIN_BYTES);
-            bulk_commit();
+            for (int j = 0; j < 16; ++j) acc[j] *= s1[j];
+            store_a16(sm.a_hi, sm.a_lo, e.row, c0, acc);
           }
+          epi_publish_group(sm, g);
         }
-        epi_publish_a(sm);
+        if (tr) epi_store_main(e, sm.a_hi, sm.a_lo, rec + lay.a + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);
       }
-      // layer 0: D = v_0 [E]; n = J^T (v_0 + r)
+      // ------------------------------------------------------------ layer 0: D = v_0 [E]; n = J^T (v_0 + r)
       {
-        epi_wait_d(sm, es);
-        float v[64];
-        tmem_ld32(tm, v);
-        tmem_ld32(tm + 32, v + 32);
-        tmem_ld_wait();
-        if (p.skip >= 0) {
-#pragma unroll
-          for (int e = 0; e < A_AUX_COLS; ++e)
-            if (e < p.E) v[e] += rskip[e * TILE_M + row];
+        const Step st = p.prog.s[2 * L - 1];
+        epi_wait_d(sm, e);
+        if (p.skip >= 0) {  // the skip part was written by other warps (last column group): make it visible
+          __threadfence_block();
+          epi_bar();
         }
-        float n[3] = {v[0], v[1], v[2]};
+        if (e.j == 0) {
+          float n[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < 7; ++j) {
-          if (j < p.pts.multires) {
-            const float f = static_cast<float>(1 << j);
+          for (int part = 0; part < 3; ++part) {
+            float v[16];
+            tmem_ld16(e.tm + st.d_col + 16 * part, v);
+            tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              float s, co;
-              sincosf(x[c] * f, &s, &co);
-              n[c] += f * co * v[3 + 6 * j + c] - f * s * v[3 + 6 * j + 3 + c];
+            for (int i = 0; i < 16; ++i) {
+              const int c = 16 * part + i;  // compile-time
+              float val = v[i];
+              if (p.skip >= 0 && c < p.E) val += rskip[c * TILE_M + e.row];
+              if (c < 3) {
+                n[c] += val;
+              } else {
+                const int j = (c - 3) / 6, r6 = (c - 3) % 6, cc = r6 % 3;
+                if (j < p.pts.multires) {
+                  const float f = static_cast<float>(1 << j);
+                  float sn, co;
+                  sincosf(x[cc] * f, &sn, &co);
+                  n[cc] += (r6 < 3 ? f * co : -f * sn) * val;
+                }
+              }
             }
           }
-        }
-        float sdf = s_raw, actv = 1.f;
-        if (p.clamp && p.pts.sphere_r > 0.f) {
-          const float nrm = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
-          const float sph = p.pts.sphere_scale * (p.pts.sphere_r - nrm);
-          if (!(s_raw <= sph)) {  // torch.minimum routes the gradient to `self` on ties
-            actv = 0.f;
-            sdf = sph;
-            const float k = -p.pts.sphere_scale / nrm;
-            n[0] = k * x[0]; n[1] = k * x[1]; n[2] = k * x[2];
+          float sdf = s_raw, actv = 1.f;
+          if (p.clamp && p.pts.sphere_r > 0.f) {
+            const float nrm = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+            const float sph = p.pts.sphere_scale * (p.pts.sphere_r - nrm);
+            if (!(s_raw <= sph)) {  // torch.minimum routes the gradient to `self` on ties
+              actv = 0.f;
+              sdf = sph;
+              const float k = -p.pts.sphere_scale / nrm;
+              n[0] = k * x[0]; n[1] = k * x[1]; n[2] = k * x[2];
+            }
           }
-        }
-        if (valid) {
-          if (p.sdf) p.sdf[pt] = sdf;
-          p.grad[3 * pt + 0] = n[0]; p.grad[3 * pt + 1] = n[1]; p.grad[3 * pt + 2] = n[2];
-          if (p.act) p.act[pt] = actv;
+          if (valid) {
+            if (p.sdf) p.sdf[pt] = sdf;
+            p.grad[3 * pt + 0] = n[0]; p.grad[3 * pt + 1] = n[1]; p.grad[3 * pt + 2] = n[2];
+            if (p.act) p.act[pt] = actv;
+          }
         }
       }
     }
-    if (row == 0) bulk_wait0();
+    if (e.lead) bulk_wait0();
   }
   engine_fini(sm);
 }

@@ -31,6 +31,7 @@ struct WJob {
 constexpr int WG_X_PLANE = 128 / 8 * A_CHUNK_BYTES;  // 32768
 constexpr int WG_Y_PLANE = 256 / 8 * A_CHUNK_BYTES;    // 65536
 constexpr int WG_ONES_BYTES = 2 * A_CHUNK_BYTES;  // 16 columns
+constexpr int WG_THREADS = 192;                   // warps 0-3 flush, warp 4 loads, warp 5 issues MMAs
 
 struct alignas(1024) WgradSmem {
   uint8_t x_hi[WG_X_PLANE], x_lo[WG_X_PLANE];
@@ -40,7 +41,7 @@ struct alignas(1024) WgradSmem {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_kernel(const WJob* __restrict__ jobs) {
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WJob* __restrict__ jobs) {
   extern __shared__ uint8_t smem_raw[];
   WgradSmem& sm = *reinterpret_cast<WgradSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const WJob job = jobs[blockIdx.x];
