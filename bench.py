@@ -142,6 +142,7 @@ def main():
     config = {"workload": "DTU-shaped synthetic batch: %d rays/GPU x 98 samples, 8x256 SDF + 4x256 rendering/attraction "
                           "MLPs, ErrorBoundSampler (<=5 x 128 SDF queries/ray), train step = fwd+loss+bwd+Adam" % args.rays,
               "rays_per_gpu": args.rays, "samples_per_ray": S, "beta": args.beta, "parallelism": "dp%d" % world,
+              "rng": "training draws (stratified jitter, inverse-CDF u, extra columns, eikonal points) made on the device",
               "precision_mode": "bf16x3 (hi/lo split operands, fp32 accumulate) on tcgen05",
               "l2": "no explicit flush: the per-step working set (~5 GB of saved activations at 1024 rays) is >> the 126 MB L2"}
 

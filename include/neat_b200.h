@@ -53,6 +53,19 @@ long neat_param_offset(const neat_ctx* ctx, int net, int layer, int kind);
 /* in/out features of a layer; returns 0 or NEAT_EINVAL */
 int neat_layer_dims(const neat_ctx* ctx, int net, int layer, int* in_features, int* out_features);
 
+/* nn.utils.weight_norm for every layer in one launch (neat_wfr_rend_a.py:71-72): layers in the order of the flat
+ * buffer (implicit, rendering, attraction; layer 0..).  g == NULL: plain Linear (v is the weight).  forward writes
+ * the effective weights + biases into flat; backward reads flat_grad and writes gg / gv / gb.          */
+typedef struct {
+  const float *g, *v, *b; /* weight_g [rows], weight_v [rows, cols], bias [rows] */
+  float *gg, *gv, *gb;    /* their gradients (backward only)                    */
+  int rows, cols;
+  long w_off, b_off;      /* float offsets in the flat buffer (filled by the library) */
+} neat_wn_layer;
+int neat_weight_norm_forward(neat_ctx* ctx, const neat_wn_layer* layers, int n_layers, float* flat, void* stream);
+int neat_weight_norm_backward(neat_ctx* ctx, const neat_wn_layer* layers, int n_layers, const float* flat_grad,
+                              void* stream);
+
 /* Re-pack the flat parameters into tcgen05 operand slabs (bf16 hi/lo planes).  Call once per
  * optimizer step, before any of the entry points below.                                        */
 int neat_pack_weights(neat_ctx* ctx, const float* flat_params, void* stream);
@@ -162,6 +175,24 @@ int neat_line_geometry(int R, const float* pose, const float* K, const float* uv
 size_t neat_dbscan_workspace_bytes(int N);
 int neat_dbscan(const float* points, int N, float eps, void* workspace, float* centroids, int* n_clusters,
                 void* stream);
+
+/* ---- VolSDFLoss (code/model/networks/loss_wfr.py:34-79), forward fused with its own backward ---- */
+/* loss_core = rgb L1 + eikonal_weight * eikonal + line_weight * calibrated line loss.  out[8] = {loss_core, rgb_loss,
+ * eikonal_loss, line_loss, l2d_loss (uncalibrated, statistics only), count}.  g_* = d loss_core / d input.
+ * lines_gt [R,5] = x1 y1 x2 y2 weight; labels [R] or NULL; K3: 3x3 with row stride k_ld; grad_theta may be NULL.
+ * scratch: 8 + R floats.  The Hungarian-matched junction terms (loss_wfr.py:95-131) stay on the host.      */
+typedef struct {
+  int R, n_eik;
+  const float *rgb_values, *rgb_gt, *lines2d, *lines2d_calib, *lines_gt, *labels, *K3;
+  int k_ld;
+  const float* grad_theta;
+  float eikonal_weight, line_weight;
+  float *scratch, *out, *g_rgb, *g_calib, *g_theta;
+} neat_loss_args;
+int neat_loss_forward_backward(const neat_loss_args* a, void* stream);
+/* adjoint of lines2d_calib = project2D(I, R, T, lines3d) (neat_wfr_rend_a.py:442): g_calib [R,2,2] -> g_lines3d [R,2,3] */
+int neat_project_calib_backward(int R, const float* pose_inv, const float* lines3d, const float* g_calib,
+                                float* g_lines3d, void* stream);
 
 /* ---- backward (replaces loss.backward() through the model, code/training/volsdf_train.py:373) ---- */
 /* Adjoint of neat_composite_forward for the outputs the reference losses consume (rgb_values, lines3d;

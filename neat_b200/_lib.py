@@ -29,6 +29,8 @@ SIGNATURES = {
     "neat_param_count": (ctypes.c_size_t, [_P]),
     "neat_param_offset": (ctypes.c_long, [_P, _I, _I, _I]),
     "neat_layer_dims": (_I, [_P, _I, _I, ctypes.POINTER(_I), ctypes.POINTER(_I)]),
+    "neat_weight_norm_forward": (_I, [_P, _P, _I, _P, _P]),
+    "neat_weight_norm_backward": (_I, [_P, _P, _I, _P, _P]),
     "neat_pack_weights": (_I, [_P, _P, _P]),
     "neat_sdf_points": (_I, [_P, _P, _I, _P, _P]),
     "neat_sdf_rays": (_I, [_P, _P, _I, _P, _P, _I, _I, _P, _P]),
@@ -43,6 +45,8 @@ SIGNATURES = {
     "neat_camera_rays": (_I, [_P, _P, _P, _I, _P, _P, _P]),
     "neat_composite_forward": (_I, [_P, _P]),
     "neat_line_geometry": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "neat_loss_forward_backward": (_I, [_P, _P]),
+    "neat_project_calib_backward": (_I, [_I, _P, _P, _P, _P, _P]),
     "neat_dbscan_workspace_bytes": (ctypes.c_size_t, [_I]),
     "neat_dbscan": (_I, [_P, _I, ctypes.c_float, _P, _P, _P, _P]),
     "neat_composite_backward": (_I, [_P, _P]),
@@ -60,6 +64,18 @@ class CompositeBwdArgs(ctypes.Structure):
     _fields_ = [("R", _I), ("S", _I), ("z", _P), ("sdf", _P), ("weights", _P), ("rgb", _P), ("act", _P),
                 ("rgb_values_bar", _P), ("lines3d_bar", _P), ("beta_param", _P), ("beta_min", ctypes.c_float),
                 ("rgb_pre_bar", _P), ("lines_bar", _P), ("sdf_bar", _P), ("beta_bar", _P)]
+
+
+class WnLayer(ctypes.Structure):
+    _fields_ = [("g", _P), ("v", _P), ("b", _P), ("gg", _P), ("gv", _P), ("gb", _P), ("rows", _I), ("cols", _I),
+                ("w_off", ctypes.c_long), ("b_off", ctypes.c_long)]
+
+
+class LossArgs(ctypes.Structure):
+    _fields_ = [("R", _I), ("n_eik", _I), ("rgb_values", _P), ("rgb_gt", _P), ("lines2d", _P), ("lines2d_calib", _P),
+                ("lines_gt", _P), ("labels", _P), ("K3", _P), ("k_ld", _I), ("grad_theta", _P),
+                ("eikonal_weight", ctypes.c_float), ("line_weight", ctypes.c_float), ("scratch", _P), ("out", _P),
+                ("g_rgb", _P), ("g_calib", _P), ("g_theta", _P)]
 
 
 class GradGroup(ctypes.Structure):

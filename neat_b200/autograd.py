@@ -6,7 +6,8 @@ forward : camera rays -> error-bound sampler -> ImplicitNetwork (sdf, analytic n
 backward: compositing adjoint -> head reverse sweeps -> ImplicitNetwork double backward (tangent + reverse
           sweeps) -> weight-gradient GEMMs            (reference: loss.backward())
 
-Differentiable inputs: the flat effective-parameter buffer and density.beta.  Differentiable outputs:
+Differentiable inputs: density.beta and the (weight_g, weight_v, bias) parameters of every MLP layer (weight_norm and
+its adjoint are one kernel launch each).  Differentiable outputs:
 rgb_values [R,3], lines3d [R,2,3], grad_theta [2R,3]; everything else the reference returns is detached
 there as well or does not reach a loss (depth, xyz, points3d, sdf, l3d, lines2d)."""
 import ctypes
@@ -29,11 +30,21 @@ class StepState:
 
 class NeatStepFunction(torch.autograd.Function):
     @staticmethod
-    def forward(fctx, flat, beta_param, renderer, st):
+    def forward(fctx, beta_param, renderer, st, *params):
         ctx = renderer.ctx
         lib = ctx.lib
         dev = ctx.device
-        ctx.pack_weights(flat.detach().contiguous())
+        # params: (weight_g, weight_v, bias) or (weight, bias) per layer, flattened; st.wn_has_g tells which
+        layers, i = [], 0
+        for has_g in st.wn_has_g:
+            if has_g:
+                layers.append((params[i].detach(), params[i + 1].detach(), params[i + 2].detach()))
+                i += 3
+            else:
+                layers.append((None, params[i].detach(), params[i + 1].detach()))
+                i += 2
+        st.wn_layers = layers
+        renderer.effective_weights(layers)
         beta = beta_param.detach().reshape(1).contiguous()
         st.beta = beta
         uv, pose, K = st.uv, st.pose, st.K
@@ -43,24 +54,28 @@ class NeatStepFunction(torch.autograd.Function):
         M = R * S
         st.R, st.S, st.dirs, st.cam, st.z, st.n_iters = R, S, dirs, cam, z, n_it
         pts = renderer.ray_points(cam, dirs, z)
-        st.sdf, st.grad, st.act, st.feat, st.sdf_save = renderer.sdf_outputs(pts, M, clamp=True, training=True)
+        st.sdf, st.grad, st.act, st.feat, st.sdf_save = renderer.sdf_outputs(pts, M, clamp=True, training=True, tag="render")
         st.rgb, st.rend_save = renderer.head_forward(0, pts, M, st.grad, st.feat, training=True)
         st.lines, st.att_save = renderer.head_forward(1, pts, M, st.grad, st.feat, training=True)
         w, rgb_values, lines3d, depth, points3d, _ = renderer.composite(z, st.sdf, st.rgb, st.lines, None, cam, dirs,
                                                                         beta, False)
         st.weights, st.depth, st.points3d = w, depth, points3d
         p3 = renderer.explicit_points(points3d)
-        st.sdf3, st.grad3, _, _, _ = renderer.sdf_outputs(p3, R, clamp=True, want_feat=False)
-        st.lines2d, _, st.l3d, st.pose_inv = renderer.line_geometry(pose, K, st.uv_proj, points3d, st.grad3, lines3d)
+        st.sdf3, st.grad3, _, _, _ = renderer.sdf_outputs(p3, R, clamp=True, want_feat=False, tag="surface")
+        st.lines2d, st.lines2d_calib, st.l3d, st.pose_inv = renderer.line_geometry(pose, K, st.uv_proj, points3d, st.grad3,
+                                                                                   lines3d)
         # eikonal points (neat_wfr_rend_a.py:515-527): R uniform in the bounding cube + R near-surface
         if st.eik_uniform is None:
             r = renderer.scene_bounding_sphere
-            st.eik_uniform = torch.empty(R, 3).uniform_(-r, r).to(dev)
+            if renderer.sampler.rng == "device":
+                st.eik_uniform = torch.empty(R, 3, device=dev).uniform_(-r, r)
+            else:
+                st.eik_uniform = torch.empty(R, 3).uniform_(-r, r).to(dev)  # the reference's CPU-generator draw
         near = cam[None, :] + z_eik * dirs
         st.eik_pts = torch.cat([st.eik_uniform.to(dev, torch.float32), near], 0).contiguous()
         pe = renderer.explicit_points(st.eik_pts)
         _, grad_theta, _, _, st.eik_save = renderer.sdf_outputs(pe, 2 * R, clamp=False, training=True,
-                                                                want_feat=False, want_sdf=False)
+                                                                want_feat=False, want_sdf=False, tag="eik")
         fctx.renderer, fctx.st = renderer, st
         fctx.beta_shape = beta_param.shape
         return rgb_values, lines3d.view(R, 2, 3), grad_theta
@@ -77,30 +92,31 @@ class NeatStepFunction(torch.autograd.Function):
         rvb = rgb_values_bar.contiguous().float() if rgb_values_bar is not None else z(R, 3)
         l3b = lines3d_bar.reshape(R, 6).contiguous().float() if lines3d_bar is not None else z(R, 6)
         gtb = grad_theta_bar.contiguous().float() if grad_theta_bar is not None else z(2 * R, 3)
-        rgb_pre_bar = torch.empty(M, 3, device=dev)
-        lines_bar = torch.empty(M, 6, device=dev)
-        sdf_bar = torch.empty(M, device=dev)
+        pool = renderer.pool
+        rgb_pre_bar = pool.get("bwd.rgb_pre_bar", M * 3).view(M, 3)
+        lines_bar = pool.get("bwd.lines_bar", M * 6).view(M, 6)
+        sdf_bar = pool.get("bwd.sdf_bar", M)
         beta_bar = torch.zeros(1, device=dev)
         a = _lib.CompositeBwdArgs(R, S, _ptr(st.z), _ptr(st.sdf), _ptr(st.weights), _ptr(st.rgb), _ptr(st.act), _ptr(rvb),
                                   _ptr(l3b), _ptr(st.beta), renderer.beta_min, _ptr(rgb_pre_bar), _ptr(lines_bar),
                                   _ptr(sdf_bar), _ptr(beta_bar))
         _lib.check(lib.neat_composite_backward(ctypes.byref(a), stream))
-        feat_bar = torch.empty(int(lib.neat_feat_bar_bytes(M)) // 4, device=dev)
-        n_bar = torch.empty(M, 3, device=dev)
-        hb = [torch.empty(int(lib.neat_head_bwd_save_bytes(ctx._h, M)), dtype=torch.uint8, device=dev) for _ in range(2)]
+        feat_bar = pool.get("bwd.feat_bar", int(lib.neat_feat_bar_bytes(M)) // 4)
+        n_bar = pool.get("bwd.n_bar", M * 3).view(M, 3)
+        hb = [pool.get("bwd.head%d" % h, int(lib.neat_head_bwd_save_bytes(ctx._h, M)), torch.uint8) for h in range(2)]
         with renderer.timed("head_bwd"):
             _lib.check(lib.neat_head_backward(ctx._h, 0, M, _ptr(rgb_pre_bar), _ptr(st.rend_save), _ptr(hb[0]),
                                               _ptr(feat_bar), _ptr(n_bar), 0, stream))
             _lib.check(lib.neat_head_backward(ctx._h, 1, M, _ptr(lines_bar), _ptr(st.att_save), _ptr(hb[1]),
                                               _ptr(feat_bar), _ptr(n_bar), 1, stream))
         pts = renderer.ray_points(st.cam, st.dirs, st.z)
-        sb = torch.empty(int(lib.neat_sdf_bwd_save_bytes(ctx._h, M)), dtype=torch.uint8, device=dev)
-        scratch = torch.empty(int(lib.neat_sdf_bwd_scratch_bytes(ctx._h, M)), dtype=torch.uint8, device=dev)
+        sb = pool.get("bwd.sdf", int(lib.neat_sdf_bwd_save_bytes(ctx._h, M)), torch.uint8)
+        scratch = pool.get("bwd.scratch", int(lib.neat_sdf_bwd_scratch_bytes(ctx._h, M)), torch.uint8)
         with renderer.timed("sdf_bwd_M%d" % M):
             _lib.check(lib.neat_sdf_backward(ctx._h, ctypes.byref(pts), _ptr(n_bar), _ptr(sdf_bar), _ptr(feat_bar),
                                              _ptr(st.act), _ptr(st.sdf_save), _ptr(sb), _ptr(scratch), stream))
         pe = renderer.explicit_points(st.eik_pts)
-        sbe = torch.empty(int(lib.neat_sdf_bwd_save_bytes(ctx._h, 2 * R)), dtype=torch.uint8, device=dev)
+        sbe = pool.get("bwd.sdf_eik", int(lib.neat_sdf_bwd_save_bytes(ctx._h, 2 * R)), torch.uint8)
         _lib.check(lib.neat_sdf_backward(ctx._h, ctypes.byref(pe), _ptr(gtb), None, None, None, _ptr(st.eik_save), _ptr(sbe),
                                          _ptr(scratch), stream))
         flat_grad = torch.zeros(ctx.n_params, device=dev)
@@ -112,4 +128,10 @@ class NeatStepFunction(torch.autograd.Function):
         with renderer.timed("wgrad"):
             _lib.check(lib.neat_weight_gradients(ctx._h, groups, 2, _ptr(flat_grad), stream))
         st.debug = dict(rgb_pre_bar=rgb_pre_bar, lines_bar=lines_bar, sdf_bar=sdf_bar, n_bar=n_bar, feat_bar=feat_bar)
-        return flat_grad, beta_bar.reshape(fctx.beta_shape), None, None
+        grads = renderer.weight_norm_backward(st.wn_layers, flat_grad)
+        flat_out = []
+        for (gg, gv, gb) in grads:
+            if gg is not None:
+                flat_out.append(gg)
+            flat_out += [gv, gb]
+        return (beta_bar.reshape(fctx.beta_shape), None, None) + tuple(flat_out)

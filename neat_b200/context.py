@@ -134,11 +134,13 @@ class ErrorBoundSampler:
         self._ws_R = -1
 
     def workspace(self, R):
-        if self._ws_R < R:
+        if self._ws_R < R:  # persistent: re-allocated only when the ray count grows
             n = int(self.ctx.lib.neat_sampler_workspace_bytes(R))
             self._ws = torch.empty(n, dtype=torch.uint8, device=self.ctx.device)
             self._ws_R = R
         return self._ws
+
+    rng = "reference"  # "reference": replay the reference's CPU-generator stream; "device": draw on the GPU (no sync)
 
     def get_z_vals(self, rays_o, rays_d, beta_param, training=False, randoms=None):
         """rays_o [3] or [R,3], rays_d [R,3], beta_param: 0-dim/1-elem device tensor (density.beta).
@@ -156,8 +158,12 @@ class ErrorBoundSampler:
         z_eik = torch.empty(R, device=dev)
         P = ctypes.c_void_p
         t_rand = u_final = eik = None
+        device_rng = training and randoms is None and self.rng == "device"
         if training:
-            if randoms is None:
+            if device_rng:
+                t_rand = torch.rand(R, c.n_eval, device=dev)
+                u_final = torch.rand(R, c.n_final, device=dev)
+            elif randoms is None:
                 t_rand = torch.rand(R, c.n_eval).to(dev)       # ray_sampler.py:87
                 torch.randint(0, c.n_eval, (R,))               # :91 (drawn and unused by the reference)
                 u_final = torch.rand(R, c.n_final).to(dev)     # :234
@@ -171,7 +177,13 @@ class ErrorBoundSampler:
                 ctx._h, ctypes.byref(c), ctx._chk(rays_o), o_stride, ctx._chk(rays_d, (R, 3)), R,
                 P(beta_param.data_ptr()), P(t_rand.data_ptr()) if training else None,
                 P(u_final.data_ptr()) if training else None, P(ws.data_ptr()), P(n_it.data_ptr()), ctx._stream()))
-        if training:
+        if device_rng:
+            # same distribution as the reference's randperm(128 k)[:n_extra] for whichever k the sampler stops at;
+            # all rows are drawn up front so that no device->host read of k is needed
+            table = torch.stack([torch.randperm(c.n_eval * k, device=dev)[:max(c.n_extra, 1)]
+                                 for k in range(1, c.max_iters + 1)]).contiguous()
+            eik = torch.randint(0, self.n_out, (R,), device=dev)
+        elif training:
             k = int(n_it.item())
             table = torch.zeros(c.max_iters, max(c.n_extra, 1), dtype=torch.int64)
             if randoms is None:

@@ -13,9 +13,11 @@
 #include "composite.cuh"
 #include "dbscan.cuh"
 #include "heads.cuh"
+#include "loss.cuh"
 #include "sampler.cuh"
 #include "sdf_query.cuh"
 #include "sdf_render.cuh"
+#include "weight_norm.cuh"
 #include "wgrad.cuh"
 
 using namespace neat;
@@ -76,6 +78,9 @@ struct neat_ctx {
   uint8_t* ones_tile = nullptr;  // X operand with column 0 = 1 (aux-plane sized, hi then lo)
   WJob* jobs_dev = nullptr;
   int jobs_cap = 0;
+  WnTable* wn_dev = nullptr;
+  WnTable wn_host{};
+  bool wn_valid = false;
 };
 
 // ---------------------------------------------------------------- packing kernels
@@ -201,6 +206,7 @@ void neat_destroy(neat_ctx* c) {
   cudaFree(c->g_fdst);
   cudaFree(c->ones_tile);
   cudaFree(c->jobs_dev);
+  cudaFree(c->wn_dev);
   delete c;
 }
 
@@ -220,6 +226,60 @@ int neat_layer_dims(const neat_ctx* c, int net, int layer, int* in_f, int* out_f
   if (!v || layer < 0 || layer >= static_cast<int>(v->size())) return fail(NEAT_EINVAL, "bad net/layer");
   if (in_f) *in_f = (*v)[layer].in;
   if (out_f) *out_f = (*v)[layer].out;
+  return NEAT_OK;
+}
+
+namespace {
+int upload_wn_table(neat_ctx* c, const neat_wn_layer* layers, int n, cudaStream_t st) {
+  const Plan& P = c->plan;
+  const int expect = static_cast<int>(P.sdf.size() + P.rend.size() + P.att.size());
+  if (!layers || n != expect || n > WN_MAX_LAYERS) return fail(NEAT_EINVAL, "weight_norm: wrong number of layers");
+  WnTable t{};
+  t.n = n;
+  int rows = 0, i = 0;
+  for (const std::vector<LinearDims>* net : {&P.sdf, &P.rend, &P.att})
+    for (const LinearDims& d : *net) {
+      neat_wn_layer L = layers[i];
+      if (L.rows != d.out || L.cols != d.in || !L.v || !L.b) return fail(NEAT_EINVAL, "weight_norm: layer shape mismatch");
+      L.w_off = static_cast<long>(d.w_off);
+      L.b_off = static_cast<long>(d.b_off);
+      t.l[i] = L;
+      t.row_start[i] = rows;
+      rows += d.out;
+      ++i;
+    }
+  t.row_start[n] = rows;
+  if (!c->wn_dev) CK(cudaMalloc(&c->wn_dev, sizeof(WnTable)));
+  if (!c->wn_valid || std::memcmp(&t, &c->wn_host, sizeof(WnTable)) != 0) {
+    c->wn_host = t;
+    c->wn_valid = true;
+    CK(cudaMemcpyAsync(c->wn_dev, &c->wn_host, sizeof(WnTable), cudaMemcpyHostToDevice, st));
+  }
+  return NEAT_OK;
+}
+}  // namespace
+
+int neat_weight_norm_forward(neat_ctx* c, const neat_wn_layer* layers, int n_layers, float* flat, void* stream) {
+  if (!c || !flat) return fail(NEAT_EINVAL, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int e = upload_wn_table(c, layers, n_layers, st)) return e;
+  const int rows = c->wn_host.row_start[c->wn_host.n];
+  weight_norm_fwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(c->wn_dev, flat);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+int neat_weight_norm_backward(neat_ctx* c, const neat_wn_layer* layers, int n_layers, const float* flat_grad, void* stream) {
+  if (!c || !flat_grad) return fail(NEAT_EINVAL, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int e = upload_wn_table(c, layers, n_layers, st)) return e;
+  for (int i = 0; i < n_layers; ++i)
+    if (!layers[i].gv || !layers[i].gb || (layers[i].g && !layers[i].gg)) return fail(NEAT_EINVAL, "weight_norm: null gradient pointer");
+  const int rows = c->wn_host.row_start[c->wn_host.n];
+  weight_norm_bwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(c->wn_dev, flat_grad);
+  ++g_launches;
+  CK(cudaGetLastError());
   return NEAT_OK;
 }
 
@@ -498,6 +558,41 @@ int neat_line_geometry(int R, const float* pose, const float* K, const float* uv
   p.R = R; p.pose = pose; p.K = K; p.uv_proj = uv_proj; p.points3d = points3d; p.grad3d = grad3d;
   p.lines3d = lines3d; p.lines2d = lines2d; p.lines2d_calib = lines2d_calib; p.l3d = l3d; p.pose_inv = pose_inv;
   line_geometry_kernel<<<(R + 127) / 128, 128, 0, st>>>(p);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+// ---------------------------------------------------------------- loss
+int neat_loss_forward_backward(const neat_loss_args* a, void* stream) {
+  if (!a || a->R <= 0 || !a->rgb_values || !a->rgb_gt || !a->lines2d || !a->lines2d_calib || !a->lines_gt || !a->K3 ||
+      !a->scratch || !a->out || !a->g_rgb || !a->g_calib || (a->grad_theta && (!a->g_theta || a->n_eik <= 0)))
+    return fail(NEAT_EINVAL, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LossParams p{};
+  p.R = a->R; p.n_eik = a->grad_theta ? a->n_eik : 0;
+  p.rgb_values = a->rgb_values; p.rgb_gt = a->rgb_gt; p.lines2d = a->lines2d; p.lines2d_calib = a->lines2d_calib;
+  p.lines_gt = a->lines_gt; p.labels = a->labels; p.K3 = a->K3; p.k_ld = a->k_ld; p.grad_theta = a->grad_theta;
+  p.eikonal_weight = a->eikonal_weight; p.line_weight = a->line_weight;
+  p.sums = a->scratch; p.per_uncal = a->scratch + 8;
+  p.out = a->out; p.g_rgb = a->g_rgb; p.g_calib = a->g_calib; p.g_theta = a->g_theta;
+  CK(cudaMemsetAsync(p.sums, 0, 8 * sizeof(float), st));
+  const int n = std::max(p.R, p.n_eik);
+  loss_terms_kernel<<<(n + 255) / 256, 256, 0, st>>>(p);
+  ++g_launches;
+  loss_calib_kernel<<<(p.R + 255) / 256, 256, 0, st>>>(p);
+  ++g_launches;
+  loss_grads_kernel<<<(n + 255) / 256, 256, 0, st>>>(p);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+int neat_project_calib_backward(int R, const float* pose_inv, const float* lines3d, const float* g_calib,
+                                float* g_lines3d, void* stream) {
+  if (R <= 0 || !pose_inv || !lines3d || !g_calib || !g_lines3d) return fail(NEAT_EINVAL, "bad argument");
+  project_calib_bwd_kernel<<<(R + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(R, pose_inv, lines3d, g_calib,
+                                                                                         g_lines3d);
   ++g_launches;
   CK(cudaGetLastError());
   return NEAT_OK;

@@ -29,6 +29,29 @@ def _embed_dim(multires, d=3):
     return d + 2 * d * multires if multires > 0 else d
 
 
+class _ProjectCalib(torch.autograd.Function):
+    """lines2d_calib = project2D(I, R, T, lines3d) (neat_wfr_rend_a.py:442): the forward value comes from the geometry
+    kernel of the step; the backward is project_calib_bwd_kernel."""
+
+    @staticmethod
+    def forward(ctx, lines3d, lines2d_calib, pose_inv):
+        ctx.save_for_backward(lines3d.detach(), pose_inv)
+        return lines2d_calib.view_as(lines2d_calib).clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        import ctypes
+        lines3d, pose_inv = ctx.saved_tensors
+        lib = _lib.load()
+        R = lines3d.shape[0]
+        out = torch.empty(R, 2, 3, device=lines3d.device)
+        P = ctypes.c_void_p
+        _lib.check(lib.neat_project_calib_backward(R, P(pose_inv.data_ptr()), P(lines3d.contiguous().data_ptr()),
+                                                   P(g.contiguous().float().data_ptr()), P(out.data_ptr()),
+                                                   P(torch.cuda.current_stream(lines3d.device).cuda_stream)))
+        return out, None, None
+
+
 class _WeightNormMLP(nn.Module):
     """lin0..lin{n-1} with nn.utils.weight_norm, parameters only: the math runs in the kernels."""
 
@@ -129,6 +152,7 @@ class _Head(_WeightNormMLP):
         feat = rn.pack_features(feature_vectors.detach().float())
         out, _ = rn.head_forward(self._head, rn.explicit_points(x, view_dirs.detach().float().contiguous()), M,
                                  normals.detach().float().contiguous(), feat)
+        out = out.clone()  # the kernel output lives in the renderer's reusable workspace
         return out if self._head == 0 else out.view(M, 2, 3)
 
 
@@ -196,6 +220,10 @@ class VolSDFNetwork(nn.Module):
         self._renderer = None
         self._packed_version = None
         self.replay = None  # tests: dict(sampler=..., eik_uniform=...) recorded draws to replay
+        # "reference": the training-mode random draws replay the reference's CPU-generator calls in order (same seed =>
+        # same samples; costs pageable H2D copies and one device->host read of the sampler's iteration count);
+        # "device": the same distributions drawn on the GPU, fully asynchronous.
+        self.rng = "reference"
 
     # ------------------------------------------------------------------ kernel context plumbing
     def _get_renderer(self):
@@ -212,20 +240,17 @@ class VolSDFNetwork(nn.Module):
     def _param_version(self):
         return tuple(p._version for p in self.parameters()) + tuple(id(p) for p in self.parameters())
 
-    def _flat_params(self):
-        rn = self._get_renderer()
-        sd = {}
-        for name, mod in (("implicit_network", self.implicit_network), ("rendering_network", self.rendering_network),
-                          ("attraction_network", self.attraction_network)):
+    def _wn_layers(self):
+        """[(weight_g | None, weight_v | weight, bias)] of every MLP layer, in flat-buffer order."""
+        out = []
+        for mod in (self.implicit_network, self.rendering_network, self.attraction_network):
             for l in range(mod.num_layers - 1):
                 lin = getattr(mod, "lin%d" % l)
-                pre = "%s.lin%d" % (name, l)
                 if hasattr(lin, "weight_g"):
-                    sd[pre + ".weight_g"], sd[pre + ".weight_v"] = lin.weight_g, lin.weight_v
+                    out.append((lin.weight_g, lin.weight_v, lin.bias))
                 else:
-                    sd[pre + ".weight"] = lin.weight
-                sd[pre + ".bias"] = lin.bias
-        return rn.ctx.flatten_state_dict(sd)
+                    out.append((None, lin.weight, lin.bias))
+        return out
 
     def _sync_weights(self):
         """(inference entry points) re-pack the weight slabs if any parameter changed."""
@@ -233,7 +258,8 @@ class VolSDFNetwork(nn.Module):
         v = self._param_version()
         if v != self._packed_version:
             with torch.no_grad():
-                rn.ctx.pack_weights(self._flat_params().detach())
+                rn.effective_weights([(None if g is None else g.detach(), w.detach(), b.detach())
+                                      for g, w, b in self._wn_layers()])
             self._packed_version = v
         return rn
 
@@ -248,10 +274,15 @@ class VolSDFNetwork(nn.Module):
         return (x / (den + eps * sign)).reshape(*shape)[..., :2]
 
     def cluster_dbscan(self, points, eps=0.01, min_samples=2):
-        from sklearn.cluster import DBSCAN
-        labels = DBSCAN(eps=eps, min_samples=min_samples).fit(points).labels_
-        cl = [points[labels == i].mean(axis=0) for i in range(labels.max() + 1)]
-        return torch.tensor(np.array(cl).reshape(-1, 3)).float().to(self.latents.device)
+        """points: [N,3] device tensor (or numpy array, as the reference passes) -> cluster centroids [C,3].
+        min_samples must be 2 (the only value the reference uses): DBSCAN is then the connected components of the
+        eps-graph, computed on the GPU (dbscan.cuh)."""
+        if min_samples != 2:
+            raise _lib.NeatError("cluster_dbscan: only min_samples=2 is supported")
+        rn = self._get_renderer()
+        if not torch.is_tensor(points):
+            points = torch.as_tensor(np.asarray(points), dtype=torch.float32)
+        return rn.dbscan(points.detach().to(rn.ctx.device, torch.float32).reshape(-1, 3).contiguous(), eps)
 
     def volume_rendering(self, z_vals, sdf):
         sigma = self.density(sdf.reshape(-1, z_vals.shape[1]))
@@ -283,13 +314,16 @@ class VolSDFNetwork(nn.Module):
 
         st = StepState()
         st.uv, st.pose, st.K, st.uv_proj = uv, pose, K4, uv_proj
+        rn.sampler.rng = self.rng
         st.sampler_randoms = self.replay["sampler"] if self.replay else None
         st.eik_uniform = self.replay["eik_uniform"] if self.replay else None
-        flat = self._flat_params()
+        layers = self._wn_layers()
+        st.wn_has_g = [g is not None for g, _, _ in layers]
+        params = [t for lay in layers for t in lay if t is not None]
         self._packed_version = None  # the step packs its own copy
         # the eikonal draw follows the junction block in the reference's RNG order; it is made lazily inside the
         # step when not replayed, so do the (host-side) junction block on the detached outputs afterwards.
-        rgb_values, lines3d, grad_theta = NeatStepFunction.apply(flat, self.density.beta, rn, st)
+        rgb_values, lines3d, grad_theta = NeatStepFunction.apply(self.density.beta, rn, st, *params)
         self.last_step = st
         pinv = st.pose_inv[:3]
         Rm, T = pinv[:, :3], pinv[:, 3:]
@@ -297,12 +331,13 @@ class VolSDFNetwork(nn.Module):
         I3 = torch.eye(3, device=dev)
         out.update(points=st.cam[None, None, :] + st.z[:, :, None] * st.dirs[:, None, :], rgb_values=rgb_values,
                    depth=st.depth, xyz=st.points3d, points3d=st.points3d, lines3d=lines3d, l3d=st.l3d,
-                   lines2d=st.lines2d, lines2d_calib=self.project2D(I3, Rm, T, lines3d), sdf=st.sdf3,
+                   lines2d=st.lines2d, lines2d_calib=_ProjectCalib.apply(lines3d, st.lines2d_calib, st.pose_inv.reshape(-1)),
+                   sdf=st.sdf3,
                    K=K3, grad_theta=grad_theta)
         out["wireframe-gt"] = input.get("wireframe")
         # ---- junction block (neat_wfr_rend_a.py:457-496): DBSCAN + Hungarian on the host, as the reference
         from scipy.optimize import linear_sum_assignment
-        j3d = self.cluster_dbscan(lines3d.detach().cpu().numpy().reshape(-1, 3), eps=0.01, min_samples=2)
+        j3d = self.cluster_dbscan(lines3d.detach().reshape(-1, 3), eps=0.01, min_samples=2)
         j2d = self.project2D(K3, Rm, T, j3d)
         j2d_cal = self.project2D(I3, Rm, T, j3d)
         gt = input["wireframe"][0].vertices.to(dev, torch.float32)

@@ -30,6 +30,31 @@ class _Timed:
             self.rn.timers.setdefault(self.name, []).append((self.e0, e1))
 
 
+class WorkspacePool:
+    """Named, persistent device buffers.  The per-step save records are GB-sized; asking the caching allocator for
+    them every step ends in cudaMalloc/cudaFree.  One step is in flight at a time, so each named buffer is simply
+    reused (it is only re-allocated when a larger size is requested)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+
+    def get(self, name, numel, dtype=torch.float32):
+        key = (name, dtype)
+        t = self.bufs.get(key)
+        if t is None or t.numel() < numel:
+            self.bufs[key] = t = torch.empty(max(int(numel), 1), dtype=dtype, device=self.device)
+        return t[:numel]
+
+    def zeros(self, name, numel, dtype=torch.float32):
+        t = self.get(name, numel, dtype)
+        t.zero_()
+        return t
+
+    def total_bytes(self):
+        return sum(t.numel() * t.element_size() for t in self.bufs.values())
+
+
 class Renderer:
     def __init__(self, ctx: Context, conf):
         self.ctx = ctx
@@ -38,6 +63,7 @@ class Renderer:
         self.sampler.renderer = self
         self.beta_min = float(conf["density"].get("beta_min", 1e-4))
         self.scene_bounding_sphere = float(conf.get("scene_bounding_sphere", 1.0))
+        self.pool = WorkspacePool(ctx.device)
         self.timers = None  # bench.py: dict name -> [(start, end) CUDA events] on the launching stream
 
     def timed(self, name):
@@ -46,6 +72,37 @@ class Renderer:
     def timer_ms(self):
         """name -> (launch groups, total ms); call after a synchronize."""
         return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (self.timers or {}).items()}
+
+    # ---- weight_norm + packing of all layers (two launches) --------------------------------------------
+    def _wn_table(self, layers, grads=None):
+        """layers: [(weight_g | None, weight_v, bias)] in flat-buffer order; grads: same structure (backward)."""
+        arr = (_lib.WnLayer * len(layers))()
+        for i, (g, v, b) in enumerate(layers):
+            gg = gv = gb = None
+            if grads is not None:
+                gg, gv, gb = grads[i]
+            arr[i] = _lib.WnLayer(_ptr(g), _ptr(v), _ptr(b), _ptr(gg), _ptr(gv), _ptr(gb), v.shape[0], v.shape[1], 0, 0)
+        return arr
+
+    def effective_weights(self, layers):
+        """nn.utils.weight_norm of every layer into the flat parameter buffer, then the tcgen05 operand slabs."""
+        ctx = self.ctx
+        for g, v, b in layers:
+            for t in (g, v, b):
+                if t is not None and not (t.is_contiguous() and t.dtype == torch.float32 and t.device == ctx.device):
+                    raise _lib.NeatError("parameters must be contiguous fp32 tensors on %s" % ctx.device)
+        flat = self.pool.get("params.flat", ctx.n_params)
+        arr = self._wn_table(layers)
+        _lib.check(ctx.lib.neat_weight_norm_forward(ctx._h, arr, len(layers), _ptr(flat), ctx._stream()))
+        ctx.pack_weights(flat)
+        return flat
+
+    def weight_norm_backward(self, layers, flat_grad):
+        ctx = self.ctx
+        grads = [(None if g is None else torch.empty_like(g), torch.empty_like(v), torch.empty_like(b)) for g, v, b in layers]
+        arr = self._wn_table(layers, grads)
+        _lib.check(ctx.lib.neat_weight_norm_backward(ctx._h, arr, len(layers), _ptr(flat_grad), ctx._stream()))
+        return grads
 
     # ---- small helpers over the C entry points ------------------------------------------------
     def camera_rays(self, uv, pose, K):
@@ -64,14 +121,17 @@ class Renderer:
     def explicit_points(self, x, dirs=None):
         return _lib.Points(_ptr(x), _ptr(dirs), None, None, None, 0, 0, 0, x.shape[0])
 
-    def sdf_outputs(self, pts, M, clamp=True, training=False, want_feat=True, want_sdf=True):
+    def sdf_outputs(self, pts, M, clamp=True, training=False, want_feat=True, want_sdf=True, tag="sdf"):
+        """`tag` names the persistent workspace buffers of this call site (they stay valid until the same tag is
+        used again, i.e. through the backward pass of the step)."""
         ctx = self.ctx
         dev = ctx.device
+        pool = self.pool
         sdf = torch.empty(M, device=dev) if want_sdf else None
         grad = torch.empty(M, 3, device=dev)
-        act = torch.empty(M, device=dev) if training else None
-        feat = torch.empty(int(ctx.lib.neat_feat_tiles_bytes(M)), dtype=torch.uint8, device=dev) if want_feat else None
-        save = torch.empty(int(ctx.lib.neat_sdf_save_bytes(ctx._h, M, int(training))), dtype=torch.uint8, device=dev)
+        act = pool.get(tag + ".act", M) if training else None
+        feat = pool.get(tag + ".feat", int(ctx.lib.neat_feat_tiles_bytes(M)), torch.uint8) if want_feat else None
+        save = pool.get(tag + ".save", int(ctx.lib.neat_sdf_save_bytes(ctx._h, M, int(training))), torch.uint8)
         with self.timed("sdf_render_M%d" % M):
             _lib.check(ctx.lib.neat_sdf_outputs(ctx._h, ctypes.byref(pts), int(clamp), int(training), _ptr(sdf), _ptr(grad),
                                                 _ptr(act), _ptr(feat), _ptr(save), ctx._stream()))
@@ -79,8 +139,8 @@ class Renderer:
 
     def head_forward(self, head, pts, M, normals, feat, training=False):
         ctx = self.ctx
-        out = torch.empty(M, 3 if head == 0 else 6, device=ctx.device)
-        save = (torch.empty(int(ctx.lib.neat_head_save_bytes(ctx._h, M)), dtype=torch.uint8, device=ctx.device)
+        out = self.pool.get("head%d.out" % head, M * (3 if head == 0 else 6)).view(M, 3 if head == 0 else 6)
+        save = (self.pool.get("head%d.save" % head, int(ctx.lib.neat_head_save_bytes(ctx._h, M)), torch.uint8)
                 if training else None)
         with self.timed("head_fwd"):
             _lib.check(ctx.lib.neat_head_forward(ctx._h, head, ctypes.byref(pts), _ptr(normals), _ptr(feat), int(training),
@@ -91,7 +151,7 @@ class Renderer:
         ctx = self.ctx
         dev = ctx.device
         R, S = z.shape
-        w = torch.empty(R, S, device=dev)
+        w = self.pool.get("composite.w", R * S).view(R, S)
         rgb_values = torch.empty(R, 3, device=dev)
         lines3d = torch.empty(R, 6, device=dev)
         depth = torch.empty(R, device=dev)
@@ -115,6 +175,18 @@ class Renderer:
                                               _ptr(lines3d), _ptr(pose_inv), _ptr(l2d), _ptr(l2dc), _ptr(l3d),
                                               ctx._stream()))
         return l2d, l2dc, l3d, pose_inv.view(4, 4)
+
+    def dbscan(self, points, eps=0.01):
+        """cluster_dbscan (neat_wfr_rend_a.py:333-342) on device: centroids [C,3] of the eps-connected components
+        with >= 2 points, ordered like sklearn's labels.  One 4-byte device->host read (C)."""
+        ctx = self.ctx
+        N = points.shape[0]
+        ws = self.pool.get("dbscan.ws", int(ctx.lib.neat_dbscan_workspace_bytes(N)), torch.uint8)
+        cent = torch.empty(N // 2 + 1, 3, device=ctx.device)
+        n = torch.zeros(1, dtype=torch.int32, device=ctx.device)
+        _lib.check(ctx.lib.neat_dbscan(ctx._chk(points, (N, 3)), N, ctypes.c_float(eps), _ptr(ws), _ptr(cent), _ptr(n),
+                                       ctx._stream()))
+        return cent[:int(n.item())]
 
     # ---- feature tiles <-> [M, F] (standalone ImplicitNetwork / head entry points only) ------------
     def unpack_features(self, tiles, M):
@@ -143,13 +215,15 @@ class Renderer:
         R, S = z.shape
         M = R * S
         pts = self.ray_points(cam, dirs, z)
-        sdf, grad, _, feat, _ = self.sdf_outputs(pts, M, clamp=True)
+        sdf, grad, _, feat, _ = self.sdf_outputs(pts, M, clamp=True, tag="render")
         rgb, _ = self.head_forward(0, pts, M, grad, feat)
         lines, _ = self.head_forward(1, pts, M, grad, feat)
         w, rgb_values, lines3d, depth, points3d, nmap = self.composite(z, sdf, rgb, lines, grad, cam, dirs, beta_param, True)
         p3 = self.explicit_points(points3d)
-        sdf3, grad3, _, _, _ = self.sdf_outputs(p3, R, clamp=True, want_feat=False)
+        sdf3, grad3, _, _, _ = self.sdf_outputs(p3, R, clamp=True, want_feat=False, tag="surface")
         l2d, l2dc, l3d, _ = self.line_geometry(pose, K, uv_proj, points3d, grad3, lines3d)
+        # rgb / lines / weights live in the reusable pool: hand out copies of what the caller may keep
+        rgb, lines, w = rgb.clone(), lines.clone(), w.clone()
         return dict(points=cam[None, None, :] + z[:, :, None] * dirs[:, None, :], rgb_values=rgb_values, depth=depth,
                     xyz=points3d, points3d=points3d, lines3d=lines3d.view(R, 2, 3), lines2d=l2d, lines2d_calib=l2dc,
                     l3d=l3d, sdf=sdf3, normal_map=nmap, K=K[:3, :3], z_vals=z, weights=w, n_sampler_iters=n_it,

@@ -40,7 +40,7 @@ def h2d_bytes(hb):
 
 
 class TrainStep:
-    def __init__(self, conf=None, device="cuda:0", seed=42, beta=None, lr=5.0e-4):
+    def __init__(self, conf=None, device="cuda:0", seed=42, beta=None, lr=5.0e-4, rng="device"):
         conf = conf or synth.dtu_conf()
         torch.manual_seed(seed)
         self.model = VolSDFNetwork(conf)
@@ -48,9 +48,11 @@ class TrainStep:
             with torch.no_grad():
                 self.model.density.beta.fill_(beta)
         self.model = self.model.to(device).train()
+        self.model.rng = rng
         self.loss_fn = VolSDFLoss(**synth.loss_conf())
         self.bucket = GradBucket(self.model.parameters())
-        self.opt = torch.optim.Adam(self.model.parameters(), lr=lr)
+        # same update rule as the reference's torch.optim.Adam(lr) (volsdf_train.py:178); fused = one kernel, step on device
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=lr, fused=True)
 
     def step(self, inp, gt):
         out = self.model(inp)

@@ -180,6 +180,28 @@ def test_backward_vs_oracle_same_samples(name):
     assert checked >= 50
 
 
+@pytest.mark.parametrize("N,seed", [(64, 0), (2048, 1), (16384, 2)])
+def test_dbscan_vs_sklearn(N, seed):
+    """GPU connected-components DBSCAN == sklearn DBSCAN(eps=0.01, min_samples=2) + per-cluster means: same
+    number of clusters, same order, same centroids (also with empty result and with chains of points)."""
+    from sklearn.cluster import DBSCAN
+    g, conf, sd_np, sd, ctx, rn, P = setup_case("toy_beta0.1")
+    rs = np.random.RandomState(seed)
+    centers = rs.uniform(-1, 1, size=(max(N // 6, 1), 3))
+    pts = centers[rs.randint(0, len(centers), N)] + rs.normal(scale=0.004, size=(N, 3))
+    pts[: N // 8] = rs.uniform(-1, 1, size=(N // 8, 3))                       # isolated noise points
+    chain = np.arange(N // 16)[:, None] * np.array([[0.008, 0.0, 0.0]]) + 1.5   # a long chain: one cluster
+    pts[N // 8: N // 8 + len(chain)] = chain
+    pts = pts.astype(np.float32)
+    labels = DBSCAN(eps=0.01, min_samples=2).fit(pts).labels_
+    ref = np.array([pts[labels == i].mean(axis=0) for i in range(labels.max() + 1)]).reshape(-1, 3)
+    got = rn.dbscan(torch.from_numpy(pts).cuda(), 0.01).cpu().numpy()
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() < 1e-5
+    far = torch.from_numpy(rs.uniform(-1, 1, size=(50, 3)).astype(np.float32) * 100).cuda()
+    assert rn.dbscan(far, 0.01).shape == (0, 3)
+
+
 def test_full_size_properties():
     """BASELINE configs[1] size (1024 rays x 98 samples, 8x256 / 4x256 nets): size-independent properties."""
     from neat_b200.context import Context
