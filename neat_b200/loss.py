@@ -146,17 +146,22 @@ class VolSDFLoss(nn.Module):
             j3l, j3g = mo["j3d_local"], mo["j3d_global"]
             j2l, j2g = mo["j2d_local"].detach(), mo["j2d_global"].detach()
             j2lc, j2gc = mo["j2d_local_calib"], mo["j2d_global_calib"]
-            with torch.no_grad():
-                cost = torch.cdist(j3l, j3g, p=1) + 0.1 * torch.cdist(j2lc, j2gc, p=1)
-            a0, a1 = linear_sum_assignment(cost.cpu().numpy())
-            a0 = torch.as_tensor(a0, device=dev)
-            a1 = torch.as_tensor(a1, device=dev)
+            if "_junction_assignment" in mo:  # computed by neat_b200.model in its single host round trip
+                a0, a1, jcount = mo["_junction_assignment"]
+                jcount = torch.tensor(jcount, device=dev)
+            else:
+                with torch.no_grad():
+                    cost = torch.cdist(j3l, j3g, p=1) + 0.1 * torch.cdist(j2lc, j2gc, p=1)
+                a0, a1 = linear_sum_assignment(cost.cpu().numpy())
+                a0 = torch.as_tensor(a0, device=dev)
+                a1 = torch.as_tensor(a1, device=dev)
+                jcount = (cost[a0, a1] < 10).sum()
             l3 = (j3l[a0] - j3g[a1]).abs().sum(-1).mean()
             l2 = (j2lc[a0] - j2gc[a1]).abs().sum(-1).mean()
             with torch.no_grad():
                 l2u = (j2l[a0] - j2g[a1]).abs().sum(-1).mean()
             loss = loss + self.junction_3d_weight * l3 + self.junction_2d_weight * l2
-            out.update(j3d_loss=l3, j2d_loss=l2, j2d_stat=l2u, jcount=(cost[a0, a1] < 10).sum())
+            out.update(j3d_loss=l3, j2d_loss=l2, j2d_stat=l2u, jcount=jcount)
         out["loss"] = loss
         if "median" in mo:
             out["median"] = mo["median"]

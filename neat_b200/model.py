@@ -335,25 +335,50 @@ class VolSDFNetwork(nn.Module):
                    sdf=st.sdf3,
                    K=K3, grad_theta=grad_theta)
         out["wireframe-gt"] = input.get("wireframe")
-        # ---- junction block (neat_wfr_rend_a.py:457-496): DBSCAN + Hungarian on the host, as the reference
+        # ---- junction block (neat_wfr_rend_a.py:457-496).  DBSCAN runs on the GPU; the two Hungarian assignments (here and
+        # in the loss, loss_wfr.py:104-108) stay on the host as in the reference, but behind ONE device->host transfer:
+        # everything they need (cluster centroids, their count, the global junctions) is fetched together, and the
+        # loss' assignment is handed over in the output dict so that it need not synchronise again.
         from scipy.optimize import linear_sum_assignment
-        j3d = self.cluster_dbscan(lines3d.detach().reshape(-1, 3), eps=0.01, min_samples=2)
-        j2d = self.project2D(K3, Rm, T, j3d)
-        j2d_cal = self.project2D(I3, Rm, T, j3d)
-        gt = input["wireframe"][0].vertices.to(dev, torch.float32)
-        jcost = torch.sum((j2d[None] - gt[:, None]) ** 2, dim=-1).sqrt()
-        a0, a1 = linear_sum_assignment(jcost.detach().cpu().numpy())
+        glob = self.ffn(self.latents)
+        j2d_global = self.project2D(K3, Rm, T, glob)
+        j2d_global_calib = self.project2D(I3, Rm, T, glob)
+        cent_d, n_d = rn.dbscan_async(lines3d.detach().reshape(-1, 3).contiguous(), 0.01)
+        n_h, cent_h, glob_h, pinv_h, K_h = rn.to_host([n_d, cent_d, glob.detach(), st.pose_inv, K4])
+        C = int(n_h[0])
+        cent = cent_h[:C].astype(np.float32)
+        RT = pinv_h.reshape(4, 4)[:3].astype(np.float32)
+
+        def proj(Km, X):  # project2D on the host (float32, same guards)
+            x = (Km @ (RT[:, :3] @ X.T + RT[:, 3:])).T
+            den = x[:, 2:3]
+            sign = np.where(den >= 0, 1.0, -1.0).astype(np.float32)
+            eps = np.where(np.abs(den) < 1e-8, 1e-8, 0.0).astype(np.float32)
+            return (x / (den + eps * sign))[:, :2]
+
+        K3h, I3h = K_h[:3, :3].astype(np.float32), np.eye(3, dtype=np.float32)
+        gt = input["wireframe"][0].vertices.detach().cpu().numpy().astype(np.float32)
+        j2d = proj(K3h, cent) if C else np.zeros((0, 2), np.float32)
+        j2d_cal = proj(I3h, cent) if C else np.zeros((0, 2), np.float32)
+        jcost = np.sqrt(((j2d[None] - gt[:, None]) ** 2).sum(-1))
+        a0, a1 = linear_sum_assignment(jcost)
         sel = jcost[a0, a1]
         if self.use_median:
-            med = sel.detach().median()
-            if torch.isnan(med):
-                med = torch.tensor(10.0, device=dev)
+            med = np.median(sel) if len(sel) else np.nan
+            if np.isnan(med):
+                med = 10.0
             ok = sel < med
-            out["median"] = med
+            out["median"] = torch.tensor(float(med), device=dev)
         else:
             ok = sel < 10
-        glob = self.ffn(self.latents)
-        out.update(j2d_local=j2d[a1][ok], j3d_local=j3d[a1][ok], j3d_global=glob,
-                   j2d_global=self.project2D(K3, Rm, T, glob), j2d_local_calib=j2d_cal[a1][ok],
-                   j2d_global_calib=self.project2D(I3, Rm, T, glob))
+        j3l, j2l, j2lc = cent[a1][ok], j2d[a1][ok], j2d_cal[a1][ok]
+        if len(j3l):
+            gcal = proj(I3h, glob_h.astype(np.float32))
+            cost = np.abs(j3l[:, None] - glob_h[None]).sum(-1) + 0.1 * np.abs(j2lc[:, None] - gcal[None]).sum(-1)
+            b0, b1 = linear_sum_assignment(cost)
+            out["_junction_assignment"] = (torch.as_tensor(b0, device=dev), torch.as_tensor(b1, device=dev),
+                                           int((cost[b0, b1] < 10).sum()))
+        packed = torch.from_numpy(np.concatenate([j3l, j2l, j2lc], axis=1).astype(np.float32)).to(dev)
+        out.update(j2d_local=packed[:, 3:5], j3d_local=packed[:, 0:3], j3d_global=glob, j2d_global=j2d_global,
+                   j2d_local_calib=packed[:, 5:7], j2d_global_calib=j2d_global_calib)
         return out

@@ -64,6 +64,7 @@ class Renderer:
         self.beta_min = float(conf["density"].get("beta_min", 1e-4))
         self.scene_bounding_sphere = float(conf.get("scene_bounding_sphere", 1.0))
         self.pool = WorkspacePool(ctx.device)
+        self._pinned = {}
         self.timers = None  # bench.py: dict name -> [(start, end) CUDA events] on the launching stream
 
     def timed(self, name):
@@ -175,6 +176,31 @@ class Renderer:
                                               _ptr(lines3d), _ptr(pose_inv), _ptr(l2d), _ptr(l2dc), _ptr(l3d),
                                               ctx._stream()))
         return l2d, l2dc, l3d, pose_inv.view(4, 4)
+
+    def dbscan_async(self, points, eps=0.01):
+        """Like dbscan() but without the device->host read: returns (centroid buffer [N/2+1,3], device count [1])."""
+        ctx = self.ctx
+        N = points.shape[0]
+        ws = self.pool.get("dbscan.ws", int(ctx.lib.neat_dbscan_workspace_bytes(N)), torch.uint8)
+        cent = self.pool.get("dbscan.cent", (N // 2 + 1) * 3).view(-1, 3)
+        n = self.pool.get("dbscan.n", 1, torch.int32)
+        _lib.check(ctx.lib.neat_dbscan(ctx._chk(points, (N, 3)), N, ctypes.c_float(eps), _ptr(ws), _ptr(cent), _ptr(n),
+                                       ctx._stream()))
+        return cent, n
+
+    def to_host(self, tensors):
+        """One synchronisation for several small device tensors: async copies into pinned buffers, then one wait."""
+        outs = []
+        for i, t in enumerate(tensors):
+            key = ("host%d" % i, t.dtype)
+            h = self._pinned.get(key)
+            if h is None or h.numel() < t.numel():
+                self._pinned[key] = h = torch.empty(max(t.numel(), 1), dtype=t.dtype, pin_memory=True)
+            hv = h[:t.numel()].view(t.shape)
+            hv.copy_(t, non_blocking=True)
+            outs.append(hv)
+        torch.cuda.current_stream(self.ctx.device).synchronize()
+        return [o.numpy() for o in outs]
 
     def dbscan(self, points, eps=0.01):
         """cluster_dbscan (neat_wfr_rend_a.py:333-342) on device: centroids [C,3] of the eps-connected components
