@@ -128,7 +128,7 @@ def cpu_baseline(R_cpu, beta, steps, threads):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--rays", type=int, default=1024, help="rays per GPU per step (weak scaling)")
     ap.add_argument("--beta", type=float, default=0.1, help="density.beta (0.1 = init, k~2; 0.01 = trained-like, k=5)")
@@ -252,7 +252,8 @@ def main():
                                      "issues 3 bf16 MMAs per algorithmic MAC (hi*hi + hi*lo + lo*hi) to meet the 1e-4 "
                                      "parity bound, so the tensor pipe does 3x this"},
                 "kernel_time_share": {k: round(v, 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1])},
-                "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in timers.items()}}
+                "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in timers.items()},
+                "host_junction_block": getattr(ts.model, "last_host_ms", None)}
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             val, sec, kc = cpu_baseline(args.cpu_rays, args.beta, 1, threads)

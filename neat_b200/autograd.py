@@ -60,6 +60,11 @@ class NeatStepFunction(torch.autograd.Function):
         w, rgb_values, lines3d, depth, points3d, _ = renderer.composite(z, st.sdf, st.rgb, st.lines, None, cam, dirs,
                                                                         beta, False)
         st.weights, st.depth, st.points3d = w, depth, points3d
+        # junction clustering needs only lines3d: launch it now and start the (single) device->host transfer of the step,
+        # so that the host-side Hungarian overlaps the remaining forward kernels (surface point, geometry, eikonal points)
+        if st.junction_inputs is not None:
+            cent_d, n_d = renderer.dbscan_async(lines3d.view(-1, 3), 0.01)
+            st.junction_event, st.junction_host = renderer.to_host_async([n_d, cent_d] + list(st.junction_inputs))
         p3 = renderer.explicit_points(points3d)
         st.sdf3, st.grad3, _, _, _ = renderer.sdf_outputs(p3, R, clamp=True, want_feat=False, tag="surface")
         st.lines2d, st.lines2d_calib, st.l3d, st.pose_inv = renderer.line_geometry(pose, K, st.uv_proj, points3d, st.grad3,

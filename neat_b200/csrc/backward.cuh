@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_bwd_kernel(const __grid_c
       const uint8_t* frec = p.fwd_save + static_cast<size_t>(tile) * fl.total;
       uint8_t* brec = p.bwd_save + static_cast<size_t>(tile) * bl.total;
       // ---- stage 0: dL/d(out) -> aux columns 0..15
-      epi_planes_free(e);
+      epi_planes_free(sm, e);
       if (e.j == 0) {
         float a[A_AUX_COLS];
 #pragma unroll
@@ -102,13 +102,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_bwd_kernel(const __grid_c
         epi_publish_aux(sm);
       }
       epi_publish_all(sm);
-      epi_store_main(e, sm.a_hi + PLANE_MAIN_BYTES, sm.a_lo + PLANE_MAIN_BYTES, brec + bl.zb_aux, PLANE_AUX_BYTES);
+      epi_store_main(sm, e, sm.a_hi + PLANE_MAIN_BYTES, sm.a_lo + PLANE_MAIN_BYTES, brec + bl.zb_aux, PLANE_AUX_BYTES);
       // ---- layers HL-1 .. 1: D = dL/d(u_l);  z_bar_{l-1} = D * [u_l > 0]
       for (int l = p.HL - 1; l >= 1; --l) {
         const Step st = p.prog.s[p.HL - 1 - l];
         const uint8_t* __restrict__ u_hi = frec + fl.u + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES;
         epi_wait_d(sm, e);
-        epi_planes_free(e);
+        epi_planes_free(sm, e);
         for (int g = 0; g < N_GROUPS; ++g) {
           const int c0 = epi_col(e, g);
           if (c0 < st.w.npad) {
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_bwd_kernel(const __grid_c
           }
           epi_publish_group(sm, g);
         }
-        epi_store_main(e, sm.a_hi, sm.a_lo, brec + bl.zb + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);
+        epi_store_main(sm, e, sm.a_hi, sm.a_lo, brec + bl.zb + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);
       }
       // ---- first layer: dL/d(feature) (step HL-1) and dL/d(normal) (step HL)
       {
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
       uint8_t* brec = p.bwd_save + static_cast<size_t>(tile) * bl.total;
       const float* __restrict__ d1_base = reinterpret_cast<const float*>(frec + fl.d1);
       // ---------------------------------------------------------------- stage 0: tangent seed p_0 = J (act * n_bar)
-      epi_planes_free(e);
+      epi_planes_free(sm, e);
       if (e.j == 0) {
         float x[3] = {0.f, 0.f, 0.f}, nb[3] = {0.f, 0.f, 0.f};
         if (valid) {
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
         epi_publish_aux(sm);
       }
       epi_publish_all(sm);
-      epi_store_main(e, sm.a_hi + PLANE_MAIN_BYTES, sm.a_lo + PLANE_MAIN_BYTES, brec + bl.p_aux, PLANE_AUX_BYTES);
+      epi_store_main(sm, e, sm.a_hi + PLANE_MAIN_BYTES, sm.a_lo + PLANE_MAIN_BYTES, brec + bl.p_aux, PLANE_AUX_BYTES);
       // ---------------------------------------------------------------- tangent sweep, layers 0 .. L-2
       for (int l = 0; l < L - 1; ++l) {
         const Step st = p.prog.s[l];
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
         const uint8_t* __restrict__ a_lo = a_hi + PLANE_MAIN_BYTES;
         float* __restrict__ zh = zhat_base + static_cast<size_t>(l) * (256 * TILE_M);
         epi_wait_d(sm, e);  // D = q_l = W_l p_l
-        epi_planes_free(e);
+        epi_planes_free(sm, e);
         for (int g = 0; g < N_GROUPS; ++g) {
           const int c0 = epi_col(e, g);
           if (c0 < st.w.npad) {
@@ -288,10 +288,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
           if (l < L - 2) epi_publish_group(sm, g);  // -> F_{l+1}
         }
         if (l == L - 2) fence_proxy_async();
-        epi_store_main(e, sm.a_hi, sm.a_lo, brec + bl.p + static_cast<size_t>(l) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);  // p_{l+1}
+        epi_store_main(sm, e, sm.a_hi, sm.a_lo, brec + bl.p + static_cast<size_t>(l) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);  // p_{l+1}
       }
       // ---------------------------------------------------------------- z_bar_{L-1} = o_bar = [s_bar | feat_bar]
-      epi_planes_free(e);
+      epi_planes_free(sm, e);
       {
         const int npadF = p.prog.s[L - 1].w.nk_main * 16;  // feature columns read by T_{L-1}
         const float* __restrict__ fb = p.feat_bar ? p.feat_bar + static_cast<size_t>(tile) * (256 * TILE_M) : nullptr;
@@ -314,8 +314,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
         }
       }
       epi_publish_all(sm);  // -> T_{L-1}
-      epi_bar();
+      mbar_arrive(&sm.wr_done);
       if (e.lead) {
+        mbar_wait(&sm.wr_done, e.wr_phase);
         uint8_t* dst = brec + bl.zb + static_cast<size_t>(L - 1) * TILE_MAIN_BYTES;
         bulk_s2g(dst, sm.a_hi, PLANE_MAIN_BYTES);
         bulk_s2g(dst + PLANE_MAIN_BYTES, sm.a_lo, PLANE_MAIN_BYTES);
@@ -323,6 +324,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
         bulk_s2g(brec + bl.zb_aux + PLANE_AUX_BYTES, sm.a_lo + PLANE_MAIN_BYTES, PLANE_AUX_BYTES);
         bulk_commit();
       }
+      e.wr_phase ^= 1;
       // ---------------------------------------------------------------- reverse sweep: layers L-1 .. 1
       for (int l = L - 1; l >= 1; --l) {
         const Step st = p.prog.s[(L - 1) + (L - 1 - l)];
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
         const float* __restrict__ d1 = d1_base + static_cast<size_t>(l - 1) * (256 * TILE_M);
         const float* __restrict__ zh = zhat_base + static_cast<size_t>(l - 1) * (256 * TILE_M);
         epi_wait_d(sm, e);  // D = W_l^T z_bar_l  (gradient w.r.t. the input of layer l)
-        epi_planes_free(e);
+        epi_planes_free(sm, e);
         for (int g = 0; g < N_GROUPS; ++g) {
           const int c0 = epi_col(e, g);
           if (c0 < ncols) {
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
           if (l >= 2) epi_publish_group(sm, g);  // -> T_{l-1}
         }
         if (l < 2) fence_proxy_async();
-        epi_store_main(e, sm.a_hi, sm.a_lo, brec + bl.zb + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);  // z_bar_{l-1}
+        epi_store_main(sm, e, sm.a_hi, sm.a_lo, brec + bl.zb + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);  // z_bar_{l-1}
       }
     }
     if (e.lead) bulk_wait0();

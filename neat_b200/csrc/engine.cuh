@@ -42,6 +42,8 @@ struct alignas(1024) EngineSmem {
   uint64_t aux_ready;          // 128 arrivals: the group-0 warps
   uint64_t d_ready;
   uint64_t in_ready;           // bulk loads of input operand tiles (heads / backward kernels)
+  uint64_t wr_done;            // 512 arrivals: every epilogue thread wrote (and fenced) its part of the A planes
+  uint64_t rd_done;            // 1 arrival: the lead thread's bulk store finished reading the A planes
   uint32_t tmem_base;
 };
 
@@ -57,6 +59,8 @@ __device__ __forceinline__ void engine_init(EngineSmem<STAGES>& sm) {
     mbar_init(&sm.aux_ready, 128);
     mbar_init(&sm.d_ready, 1);
     mbar_init(&sm.in_ready, 1);
+    mbar_init(&sm.wr_done, EPI_THREADS);
+    mbar_init(&sm.rd_done, 1);
     fence_mbar_init();
   }
   if (warp == EPI_WARPS) tmem_alloc(&sm.tmem_base, TMEM_COLS);
@@ -147,7 +151,7 @@ __device__ __forceinline__ void mma_loop(EngineSmem<STAGES>& sm, const Program& 
 struct Epi {
   int q, j, lane, row;  // row quadrant, 16-column slice inside a group, lane, tile row
   uint32_t tm;          // TMEM address of this warp's lanes, column 0
-  uint32_t d_phase;
+  uint32_t d_phase, wr_phase, rd_phase;
   bool lead;            // thread 0: issues bulk stores
 };
 template <int STAGES>
@@ -160,6 +164,8 @@ __device__ __forceinline__ Epi epi_make(const EngineSmem<STAGES>& sm) {
   e.row = e.q * 32 + e.lane;
   e.tm = sm.tmem_base + (static_cast<uint32_t>(e.q * 32) << 16);
   e.d_phase = 0;
+  e.wr_phase = 0;
+  e.rd_phase = 0;
   e.lead = threadIdx.x == 0;
   return e;
 }
@@ -193,20 +199,31 @@ __device__ __forceinline__ void epi_publish_aux(EngineSmem<STAGES>& sm) {  // sl
   mbar_arrive(&sm.aux_ready);
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
-// the previous bulk store out of the A planes must have finished reading before the planes are overwritten
-__device__ __forceinline__ void epi_planes_free(const Epi& e) {
-  if (e.lead) bulk_wait_read0();
-  epi_bar();
-}
-// all epilogue threads: after everyone wrote (and fenced) its columns, store both main planes to global
-__device__ __forceinline__ void epi_store_main(const Epi& e, const uint8_t* a_hi, const uint8_t* a_lo, uint8_t* dst,
-                                               int plane_bytes) {
-  epi_bar();
+// The A planes may be overwritten only after the previous bulk store out of them finished READING shared memory.
+// Only the lead thread can know (bulk_group completion is per thread); it tells the others through an mbarrier,
+// so nobody sits in a CTA-wide barrier.  Must alternate with epi_store_* (one arrival per call).
+template <int STAGES>
+__device__ __forceinline__ void epi_planes_free(EngineSmem<STAGES>& sm, Epi& e) {
   if (e.lead) {
+    bulk_wait_read0();
+    mbar_arrive(&sm.rd_done);
+  }
+  mbar_wait(&sm.rd_done, e.rd_phase);
+  e.rd_phase ^= 1;
+}
+// every epilogue thread calls this after writing + fencing its part; the lead thread waits for all 512 and then
+// stores `plane_bytes` of both planes (starting at a_hi / a_lo) to dst / dst + plane_bytes.  Nobody else waits.
+template <int STAGES>
+__device__ __forceinline__ void epi_store_main(EngineSmem<STAGES>& sm, Epi& e, const uint8_t* a_hi, const uint8_t* a_lo,
+                                               uint8_t* dst, int plane_bytes) {
+  mbar_arrive(&sm.wr_done);
+  if (e.lead) {
+    mbar_wait(&sm.wr_done, e.wr_phase);
     bulk_s2g(dst, a_hi, plane_bytes);
     bulk_s2g(dst + plane_bytes, a_lo, plane_bytes);
     bulk_commit();
   }
+  e.wr_phase ^= 1;
 }
 
 // write 32 consecutive columns [c0, c0+32) of row `row` (c0 % 8 == 0) into the A tile

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_fwd_kernel(const __grid_c
       uint8_t* rec = tr ? p.save + static_cast<size_t>(tile) * lay.total : nullptr;
       float x[3] = {0.f, 0.f, 0.f};
       // ---- stage 0: feature tile by bulk copy into the main planes, [x, view, normal] into the aux columns
-      epi_planes_free(e);
+      epi_planes_free(sm, e);
       if (e.lead) {
         const uint8_t* src = p.feat_tiles + static_cast<size_t>(tile) * TILE_MAIN_BYTES;
         mbar_arrive_expect_tx(&sm.in_ready, TILE_MAIN_BYTES);
@@ -106,17 +106,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_fwd_kernel(const __grid_c
         for (int i = 0; i < A_AUX_COLS / 8; ++i) store_a8(sm.a_hi, sm.a_lo, e.row, A_MAIN_COLS + 8 * i, a + 8 * i);
         epi_publish_aux(sm);
       }
-      if (e.lead) mbar_wait(&sm.in_ready, in_phase);  // the feature planes have landed
+      mbar_wait(&sm.in_ready, in_phase);  // the feature planes have landed (every thread observes the TMA completion)
       in_phase ^= 1;
-      epi_bar();
       epi_publish_all(sm);
-      if (tr) epi_store_main(e, sm.a_hi + PLANE_MAIN_BYTES, sm.a_lo + PLANE_MAIN_BYTES, rec + lay.aux, PLANE_AUX_BYTES);
+      if (tr) epi_store_main(sm, e, sm.a_hi + PLANE_MAIN_BYTES, sm.a_lo + PLANE_MAIN_BYTES, rec + lay.aux, PLANE_AUX_BYTES);
 
       for (int l = 0; l < p.HL - 1; ++l) {
         const Step st = p.prog.s[l];
         const float4* bias = reinterpret_cast<const float4*>(p.packed + st.w.bias_off);
         epi_wait_d(sm, e);
-        if (tr) epi_planes_free(e);
+        if (tr) epi_planes_free(sm, e);
         for (int g = 0; g < N_GROUPS; ++g) {
           const int c0 = epi_col(e, g);
           if (c0 < st.w.npad) {
@@ -135,7 +134,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_fwd_kernel(const __grid_c
           }
           epi_publish_group(sm, g);
         }
-        if (tr) epi_store_main(e, sm.a_hi, sm.a_lo, rec + lay.u + static_cast<size_t>(l) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);
+        if (tr) epi_store_main(sm, e, sm.a_hi, sm.a_lo, rec + lay.u + static_cast<size_t>(l) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);
       }
       {
         const Step st = p.prog.s[p.HL - 1];

@@ -86,13 +86,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
       if (e.j == 0 && valid) load_point(p.pts, pt, x);
 
       // ------------------------------------------------------------ stage 0: positional encoding
-      epi_planes_free(e);
+      epi_planes_free(sm, e);
       if (e.j == 0) {
         pe_to_aux(sm.a_hi, sm.a_lo, e.row, x, p.pts.multires);
         epi_publish_aux(sm);
       }
       epi_publish_all(sm);
-      if (tr) epi_store_main(e, sm.a_hi + PLANE_MAIN_BYTES, sm.a_lo + PLANE_MAIN_BYTES, rec + lay.pe, PLANE_AUX_BYTES);
+      if (tr) epi_store_main(sm, e, sm.a_hi + PLANE_MAIN_BYTES, sm.a_lo + PLANE_MAIN_BYTES, rec + lay.pe, PLANE_AUX_BYTES);
 
       // ------------------------------------------------------------ forward pass, hidden layers
       for (int l = 0; l < L - 1; ++l) {
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
         const float4* bias = reinterpret_cast<const float4*>(p.packed + st.w.bias_off);
         float* d1 = d1_base + static_cast<size_t>(l) * (256 * TILE_M);
         epi_wait_d(sm, e);
-        if (tr) epi_planes_free(e);
+        if (tr) epi_planes_free(sm, e);
         for (int g = 0; g < N_GROUPS; ++g) {
           const int c0 = epi_col(e, g);
           if (c0 < st.w.npad) {
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
           }
           epi_publish_group(sm, g);
         }
-        if (tr) epi_store_main(e, sm.a_hi, sm.a_lo, rec + lay.u + static_cast<size_t>(l) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);
+        if (tr) epi_store_main(sm, e, sm.a_hi, sm.a_lo, rec + lay.u + static_cast<size_t>(l) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);
       }
 
       // ------------------------------------------------------------ last layer: sdf (step L-1) + features (step L)
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
         const Step ss = p.prog.s[L - 1], sf = p.prog.s[L];
         const float4* bias = reinterpret_cast<const float4*>(p.packed + sf.w.bias_off);
         epi_wait_d(sm, e);
-        if (tr) epi_planes_free(e);
+        if (tr) epi_planes_free(sm, e);
         if (e.j == 0) {
           float acc[16];
           tmem_ld16(e.tm + ss.d_col, acc);
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
           }
           epi_publish_group(sm, g);
         }
-        if (tr) epi_store_main(e, sm.a_hi, sm.a_lo, rec + lay.a + static_cast<size_t>(L - 2) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);
+        if (tr) epi_store_main(sm, e, sm.a_hi, sm.a_lo, rec + lay.a + static_cast<size_t>(L - 2) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);
       }
       // ------------------------------------------------------------ transposed layers l = L-2 .. 1: D = v_l -> a_{l-1}
       for (int l = L - 2; l >= 1; --l) {
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
         const float* d1 = d1_base + static_cast<size_t>(l - 1) * (256 * TILE_M);
         const int n_main = (l == p.skip) ? p.H - p.E : npad;   // columns that feed a_{l-1}
         epi_wait_d(sm, e);
-        if (tr) epi_planes_free(e);
+        if (tr) epi_planes_free(sm, e);
         for (int g = 0; g < N_GROUPS; ++g) {
           const int c0 = epi_col(e, g);
           if (c0 < npad) {
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
           }
           epi_publish_group(sm, g);
         }
-        if (tr) epi_store_main(e, sm.a_hi, sm.a_lo, rec + lay.a + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);
+        if (tr) epi_store_main(sm, e, sm.a_hi, sm.a_lo, rec + lay.a + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);
       }
       // ------------------------------------------------------------ layer 0: D = v_0 [E]; n = J^T (v_0 + r)
       {

@@ -317,6 +317,10 @@ class VolSDFNetwork(nn.Module):
         rn.sampler.rng = self.rng
         st.sampler_randoms = self.replay["sampler"] if self.replay else None
         st.eik_uniform = self.replay["eik_uniform"] if self.replay else None
+        # global junctions (independent of the render step): enqueue first so that their host copy rides in the step's
+        # single device->host transfer
+        glob = self.ffn(self.latents)
+        st.junction_inputs = (glob.detach(), pose, K4)
         layers = self._wn_layers()
         st.wn_has_g = [g is not None for g, _, _ in layers]
         params = [t for lay in layers for t in lay if t is not None]
@@ -340,14 +344,16 @@ class VolSDFNetwork(nn.Module):
         # everything they need (cluster centroids, their count, the global junctions) is fetched together, and the
         # loss' assignment is handed over in the output dict so that it need not synchronise again.
         from scipy.optimize import linear_sum_assignment
-        glob = self.ffn(self.latents)
         j2d_global = self.project2D(K3, Rm, T, glob)
         j2d_global_calib = self.project2D(I3, Rm, T, glob)
-        cent_d, n_d = rn.dbscan_async(lines3d.detach().reshape(-1, 3).contiguous(), 0.01)
-        n_h, cent_h, glob_h, pinv_h, K_h = rn.to_host([n_d, cent_d, glob.detach(), st.pose_inv, K4])
+        import time as _time
+        _t0 = _time.perf_counter()
+        st.junction_event.synchronize()
+        _t1 = _time.perf_counter()
+        n_h, cent_h, glob_h, pose_h, K_h = st.junction_host
         C = int(n_h[0])
         cent = cent_h[:C].astype(np.float32)
-        RT = pinv_h.reshape(4, 4)[:3].astype(np.float32)
+        RT = np.linalg.inv(pose_h.reshape(4, 4).astype(np.float32))[:3].astype(np.float32)
 
         def proj(Km, X):  # project2D on the host (float32, same guards)
             x = (Km @ (RT[:, :3] @ X.T + RT[:, 3:])).T
@@ -378,6 +384,8 @@ class VolSDFNetwork(nn.Module):
             b0, b1 = linear_sum_assignment(cost)
             out["_junction_assignment"] = (torch.as_tensor(b0, device=dev), torch.as_tensor(b1, device=dev),
                                            int((cost[b0, b1] < 10).sum()))
+        self.last_host_ms = {"wait_for_gpu": (_t1 - _t0) * 1e3, "junction_host": (_time.perf_counter() - _t1) * 1e3,
+                             "clusters": C, "gt_junctions": int(gt.shape[0]), "matched": int(len(j3l))}
         packed = torch.from_numpy(np.concatenate([j3l, j2l, j2lc], axis=1).astype(np.float32)).to(dev)
         out.update(j2d_local=packed[:, 3:5], j3d_local=packed[:, 0:3], j3d_global=glob, j2d_global=j2d_global,
                    j2d_local_calib=packed[:, 5:7], j2d_global_calib=j2d_global_calib)

@@ -188,6 +188,22 @@ class Renderer:
                                        ctx._stream()))
         return cent, n
 
+    def to_host_async(self, tensors):
+        """Enqueue copies of several small device tensors into pinned host buffers; returns (event, numpy views).
+        The views are valid after event.synchronize() and until the next call."""
+        outs = []
+        for i, t in enumerate(tensors):
+            key = ("host%d" % i, t.dtype)
+            h = self._pinned.get(key)
+            if h is None or h.numel() < t.numel():
+                self._pinned[key] = h = torch.empty(max(t.numel(), 1), dtype=t.dtype, pin_memory=True)
+            hv = h[:t.numel()].view(t.shape)
+            hv.copy_(t, non_blocking=True)
+            outs.append(hv)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.ctx.device))
+        return ev, [o.numpy() for o in outs]
+
     def to_host(self, tensors):
         """One synchronisation for several small device tensors: async copies into pinned buffers, then one wait."""
         outs = []
