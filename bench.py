@@ -205,7 +205,11 @@ def main():
     rn.timers = None
     k_iters = int(ts.model.last_step.n_iters.item())
 
-    # ---- end to end from host buffers --------------------------------------------------------------
+    # ---- end to end from host buffers (same initial state and trajectory as the loop above) ----------------
+    del ts
+    ts = TR.TrainStep(synth.dtu_conf(), device=dev, seed=42, beta=args.beta)
+    for _ in range(max(args.warmup, 3)):
+        ts.step(inp, gt)
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
