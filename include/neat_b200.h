@@ -66,6 +66,11 @@ int neat_weight_norm_forward(neat_ctx* ctx, const neat_wn_layer* layers, int n_l
 int neat_weight_norm_backward(neat_ctx* ctx, const neat_wn_layer* layers, int n_layers, const float* flat_grad,
                               void* stream);
 
+/* Arithmetic of the layer GEMMs: 0 (default) = bf16x3, operands split hi + lo, three MMAs per k-step, fp32
+ * accumulation (meets the 1e-4 parity bound); 1 = plain bf16 operands, one MMA per k-step (~1e-2 on the SDF;
+ * an explicitly opt-in fast mode, never used by the tests or the headline benchmark).             */
+int neat_set_precision(neat_ctx* ctx, int fast);
+
 /* Re-pack the flat parameters into tcgen05 operand slabs (bf16 hi/lo planes).  Call once per
  * optimizer step, before any of the entry points below.                                        */
 int neat_pack_weights(neat_ctx* ctx, const float* flat_params, void* stream);
@@ -193,6 +198,16 @@ int neat_loss_forward_backward(const neat_loss_args* a, void* stream);
 /* adjoint of lines2d_calib = project2D(I, R, T, lines3d) (neat_wfr_rend_a.py:442): g_calib [R,2,2] -> g_lines3d [R,2,3] */
 int neat_project_calib_backward(int R, const float* pose_inv, const float* lines3d, const float* g_calib,
                                 float* g_lines3d, void* stream);
+
+/* ---- dataset-side attraction precompute (once per image) ------------------------ */
+/* hawp.base._C.encodels (third-party/hawp/hawp/base/csrc/linesegment.cu:23-139): lines [num,4] (x1,y1,x2,y2) ->
+ * map [6,H,W] f32, label [num,H,W] bool (bytes; zero-initialised here), tmap [1,H,W] f32.            */
+int neat_encodels(const float* lines, int input_height, int input_width, int height, int width, int num_lines,
+                  float* map, uint8_t* label, float* tmap, void* stream);
+/* SceneDataset.compute_point_line_attraction (code/datasets/scene_hawp_dataset.py:92-146), fused:
+ * mask [H*W] bool, labels [H*W] int64, proj_points [H*W,2] f32.                                   */
+int neat_point_line_attraction(const float* lines, int num_lines, int height, int width, float distance,
+                               uint8_t* mask, long long* labels, float* proj_points, void* stream);
 
 /* ---- backward (replaces loss.backward() through the model, code/training/volsdf_train.py:373) ---- */
 /* Adjoint of neat_composite_forward for the outputs the reference losses consume (rgb_values, lines3d;

@@ -31,6 +31,7 @@ SIGNATURES = {
     "neat_layer_dims": (_I, [_P, _I, _I, ctypes.POINTER(_I), ctypes.POINTER(_I)]),
     "neat_weight_norm_forward": (_I, [_P, _P, _I, _P, _P]),
     "neat_weight_norm_backward": (_I, [_P, _P, _I, _P, _P]),
+    "neat_set_precision": (_I, [_P, _I]),
     "neat_pack_weights": (_I, [_P, _P, _P]),
     "neat_sdf_points": (_I, [_P, _P, _I, _P, _P]),
     "neat_sdf_rays": (_I, [_P, _P, _I, _P, _P, _I, _I, _P, _P]),
@@ -45,6 +46,8 @@ SIGNATURES = {
     "neat_camera_rays": (_I, [_P, _P, _P, _I, _P, _P, _P]),
     "neat_composite_forward": (_I, [_P, _P]),
     "neat_line_geometry": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "neat_encodels": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "neat_point_line_attraction": (_I, [_P, _I, _I, _I, ctypes.c_float, _P, _P, _P, _P]),
     "neat_loss_forward_backward": (_I, [_P, _P]),
     "neat_project_calib_backward": (_I, [_I, _P, _P, _P, _P, _P]),
     "neat_dbscan_workspace_bytes": (ctypes.c_size_t, [_I]),

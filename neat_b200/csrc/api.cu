@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "plan.h"
+#include "attraction.cuh"
 #include "backward.cuh"
 #include "composite.cuh"
 #include "dbscan.cuh"
@@ -563,6 +564,35 @@ int neat_line_geometry(int R, const float* pose, const float* K, const float* uv
   return NEAT_OK;
 }
 
+// ---------------------------------------------------------------- dataset-side attraction precompute
+int neat_encodels(const float* lines, int input_height, int input_width, int height, int width, int num_lines, float* map,
+                  uint8_t* label, float* tmap, void* stream) {
+  if (!lines || !map || !label || !tmap || height <= 0 || width <= 0 || num_lines < 0 || input_height <= 0 || input_width <= 0)
+    return fail(NEAT_EINVAL, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t hw = static_cast<size_t>(height) * width;
+  CK(cudaMemsetAsync(map, 0, 6 * hw * sizeof(float), st));
+  CK(cudaMemsetAsync(tmap, 0, hw * sizeof(float), st));
+  CK(cudaMemsetAsync(label, 0, hw * static_cast<size_t>(num_lines), st));
+  encodels_kernel<<<static_cast<int>((hw + 255) / 256), 256, 0, st>>>(lines, input_height, input_width, num_lines, height,
+                                                                    width, map, label, tmap);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+int neat_point_line_attraction(const float* lines, int num_lines, int height, int width, float distance, uint8_t* mask,
+                               long long* labels, float* proj_points, void* stream) {
+  if (!lines || !mask || !labels || !proj_points || height <= 0 || width <= 0 || num_lines < 0)
+    return fail(NEAT_EINVAL, "bad argument");
+  const size_t hw = static_cast<size_t>(height) * width;
+  point_line_attraction_kernel<<<static_cast<int>((hw + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      lines, num_lines, height, width, distance, mask, labels, proj_points);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
 // ---------------------------------------------------------------- loss
 int neat_loss_forward_backward(const neat_loss_args* a, void* stream) {
   if (!a || a->R <= 0 || !a->rgb_values || !a->rgb_gt || !a->lines2d || !a->lines2d_calib || !a->lines_gt || !a->K3 ||
@@ -862,6 +892,14 @@ int neat_weight_gradients(neat_ctx* c, const neat_grad_group* groups, int n_grou
 }
 
 long long neat_launch_count(void) { return g_launches.load(); }
+
+int neat_set_precision(neat_ctx* c, int fast) {
+  if (!c) return fail(NEAT_EINVAL, "null context");
+  for (Program* p : {&c->prog_query, &c->prog_render, &c->prog_head[0], &c->prog_head[1], &c->prog_head_bwd[0],
+                     &c->prog_head_bwd[1], &c->prog_sdf_bwd})
+    p->fast = fast ? 1 : 0;
+  return NEAT_OK;
+}
 
 // ---------------------------------------------------------------- debug / bring-up
 int neat_debug_set_desc_swap(int swap) {

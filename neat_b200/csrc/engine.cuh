@@ -85,12 +85,13 @@ __device__ __forceinline__ void producer_loop(EngineSmem<STAGES>& sm, const Prog
     for (int i = 0; i < prog.n; ++i) {
       const PLayer w = prog.s[i].w;
       const uint32_t slab = static_cast<uint32_t>(w.npad) * 64u;
+      const uint32_t bytes = prog.fast ? slab / 2 : slab;  // the hi plane is the first half of a slab
       const int nk = w.nk_main + w.nk_aux;
       const uint8_t* src = packed + w.off;
       for (int ks = 0; ks < nk; ++ks) {
         mbar_wait(&sm.empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&sm.full[stage], slab);
-        bulk_g2s(sm.w[stage], src + static_cast<size_t>(ks) * slab, slab, &sm.full[stage]);
+        mbar_arrive_expect_tx(&sm.full[stage], bytes);
+        bulk_g2s(sm.w[stage], src + static_cast<size_t>(ks) * slab, bytes, &sm.full[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -120,8 +121,10 @@ __device__ __forceinline__ void mma_loop(EngineSmem<STAGES>& sm, const Program& 
         const uint64_t db_hi = make_desc_k(wb, npad * 16, 128);
         const uint64_t db_lo = make_desc_k(wb + npad * 32, npad * 16, 128);
         umma_bf16(d, da_hi, db_hi, idesc, acc);
-        umma_bf16(d, da_hi, db_lo, idesc, 1u);
-        umma_bf16(d, da_lo, db_hi, idesc, 1u);
+        if (!prog.fast) {
+          umma_bf16(d, da_hi, db_lo, idesc, 1u);
+          umma_bf16(d, da_lo, db_hi, idesc, 1u);
+        }
         umma_commit(&sm.empty[stage]);
         acc = 1u;
         if (++stage == STAGES) { stage = 0; phase ^= 1; }

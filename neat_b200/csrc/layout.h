@@ -36,6 +36,7 @@ struct Step {          // one GEMM of a kernel's program
 
 struct Program {
   int n;
+  int fast;  // 0: bf16x3 (hi*hi + hi*lo + lo*hi, the parity mode); 1: plain bf16 (hi*hi only; ~1e-2 accuracy)
   Step s[MAX_STEPS];
 };
 

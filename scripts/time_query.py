@@ -10,6 +10,8 @@ sd = {k: torch.from_numpy(v).cuda() for k, v in synth.make_state_dict(conf, seed
 ctx.pack_weights(ctx.flatten_state_dict(sd))
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+fast = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+ctx.lib.neat_set_precision(ctx._h, fast)
 x = (torch.rand(R * 128, 3, device="cuda") - 0.5) * 3
 for _ in range(3): ctx.sdf_points(x)
 torch.cuda.synchronize()
@@ -18,4 +20,4 @@ e0.record()
 for _ in range(n): ctx.sdf_points(x)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
-print("query R=%d: %.3f ms, %.1f Mpts/s, %.1f TFLOP/s algorithmic" % (R, ms, R * 128 / ms / 1e3, R * 128 * 1049088.0 / ms / 1e9))
+print("fast=%d" % fast, "query R=%d: %.3f ms, %.1f Mpts/s, %.1f TFLOP/s algorithmic" % (R, ms, R * 128 / ms / 1e3, R * 128 * 1049088.0 / ms / 1e9))
