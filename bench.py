@@ -223,7 +223,14 @@ def main():
     clk = clocks.stop() if rank == 0 else None
 
     t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+    per_rank = None
     if world > 1:
+        mine = torch.tensor([ms_total / args.steps, float(k_iters), sum(v[1] for v in timers.values()) / args.steps],
+                            device=dev, dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{"ms_per_step": round(float(a[0]), 3), "sampler_k": int(a[1]), "mlp_kernel_ms": round(float(a[2]), 3)}
+                    for a in allr]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e = float(t[0]), float(t[1])
     if rank == 0:
@@ -257,7 +264,7 @@ def main():
                                      "parity bound, so the tensor pipe does 3x this"},
                 "kernel_time_share": {k: round(v, 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1])},
                 "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in timers.items()},
-                "host_junction_block": getattr(ts.model, "last_host_ms", None)}
+                "host_junction_block": getattr(ts.model, "last_host_ms", None), "per_rank": per_rank}
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             val, sec, kc = cpu_baseline(args.cpu_rays, args.beta, 1, threads)

@@ -17,10 +17,14 @@ class Wireframe:
         self.weights = None if weights is None else torch.as_tensor(weights, dtype=torch.float32)
 
 
-def host_batch(R, seed, pinned=True):
+def host_batch(R, seed, pinned=True, camera_seed=1):
     """A synthetic DTU-shaped batch as HOST tensors, shaped like the reference's
-    dataloader output (scene_hawp_dataset.py:148-194)."""
-    b = synth.make_batch(R, seed=seed)
+    dataloader output (scene_hawp_dataset.py:148-194).  `seed` draws the pixels / colours / wireframe; the camera
+    is the one of `camera_seed` so that every data-parallel rank sees statistically identical work."""
+    import math
+    a = 0.3 + 0.7 * camera_seed
+    pose = synth.look_at_pose((2.5 * math.cos(a) * 0.9, 2.5 * math.sin(a) * 0.9, 2.5 * 0.436))
+    b = synth.make_batch(R, seed=seed, pose=pose)
     t = {k: torch.from_numpy(b[k]) for k in ("intrinsics", "pose", "uv", "uv_proj", "rgb", "lines2d")}
     if pinned and torch.cuda.is_available():
         t = {k: v.pin_memory() for k, v in t.items()}
