@@ -258,7 +258,11 @@ def main():
                         "ms_per_step": ms_e2e / args.steps, "last_loss": loss_host},
                 "gpu_launches": int(launches), "clocks": clk,
                 "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                             "frac": achieved / peak, "traffic": None, "peak_kind": pk_kind + " sustained bf16 (cuBLAS)",
+                             "frac": achieved / peak,
+                             # dram__bytes_read.sum + dram__bytes_write.sum of one wgrad launch at 1024 rays, from the
+                             # ncu --set full capture in profiles/r01_wgrad_ncu_full.txt
+                             "traffic": 6.527e9 if (dom == "wgrad" and args.rays == 1024) else None,
+                             "peak_kind": pk_kind + " sustained bf16 (cuBLAS)",
                              "note": "achieved = ALGORITHMIC fp32-equivalent FLOPs (2*MAC) / CUDA-event time; the kernel "
                                      "issues 3 bf16 MMAs per algorithmic MAC (hi*hi + hi*lo + lo*hi) to meet the 1e-4 "
                                      "parity bound, so the tensor pipe does 3x this"},
