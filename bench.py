@@ -239,8 +239,9 @@ def main():
         value = world * args.rays * args.steps / (ms_total * 1e-3)
         e2e = world * args.rays * args.steps / (ms_e2e * 1e-3)
         M = args.rays * S
-        # dominant kernel: the ImplicitNetwork double backward over the render points (4 F_sdf per point)
-        flops = {"sdf_bwd_M%d" % M: 4 * F_SDF * M, "sdf_render_M%d" % M: 2 * F_SDF * M,
+        # per point: forward F, normal pass F (sdf_render); tangent F + reverse F (sdf_bwd); the two outer-product
+        # accumulations 2 F plus the heads' (wgrad) -- SURVEY.md Appendix A, 6 F_sdf per render point in total
+        flops = {"sdf_bwd_M%d" % M: 2 * F_SDF * M, "sdf_render_M%d" % M: 2 * F_SDF * M,
                  "sampler": 128.0 * k_iters * args.rays * F_SDF,
                  "head_fwd": (F_REND + F_ATT) * M, "head_bwd": (F_REND + F_ATT) * M,
                  "wgrad": (2 * F_SDF + F_REND + F_ATT) * M + 2 * F_SDF * 2 * args.rays}

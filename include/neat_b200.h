@@ -181,6 +181,28 @@ size_t neat_dbscan_workspace_bytes(int N);
 int neat_dbscan(const float* points, int N, float eps, void* workspace, float* centroids, int* n_clusters,
                 void* stream);
 
+/* ---- junction matching, HOST functions (no device work, no stream) -------------------------------------
+ * The reference moves the clustered junctions to the CPU and solves two assignment problems with
+ * scipy.optimize.linear_sum_assignment (neat_wfr_rend_a.py:466-484, loss_wfr.py:104-108).  These two entry
+ * points are that host step in native code; all pointers are HOST pointers.
+ *
+ * neat_linear_sum_assignment: min-cost assignment of an n_rows x n_cols row-major cost matrix (shortest
+ * augmenting paths, float64).  Writes min(n_rows, n_cols) pairs sorted by row (scipy's convention) and returns
+ * their number, or a negative error code (NaN / -inf entries, infeasible problem).                          */
+int neat_linear_sum_assignment(const double* cost, int n_rows, int n_cols, int* row_ind, int* col_ind);
+
+/* neat_junction_match: centroids [C,3] (neat_dbscan output), gt_vertices [J,2] (WireframeGraph.vertices, pixels),
+ * pose [16] (camera-to-world), intrinsics [16] (4x4), global_junctions [G,3] (ffn(latents)).
+ *   1. project the centroids (pixel and calibrated coordinates), cost[j,c] = ||proj_c - gt_j||_2, assignment,
+ *      keep pairs with cost < 10 px (use_median: < the median of the matched costs, 10 if there are none);
+ *      local_out [min(J,C),7] rows = (x y z | u v | u_calib v_calib) in ground-truth order, *n_local rows valid
+ *   2. the loss' assignment of the kept junctions to the global ones: cost = L1(3D) + 0.1 L1(calibrated 2D);
+ *      global_rows / global_cols [n_local]; *n_close = pairs with cost < 10 (the loss' "jcount")            */
+int neat_junction_match(const float* centroids, int n_centroids, const float* gt_vertices, int n_gt,
+                        const float* pose, const float* intrinsics, const float* global_junctions, int n_global,
+                        int use_median, float* local_out, int* n_local, int* global_rows, int* global_cols,
+                        int* n_close, float* median_out);
+
 /* ---- VolSDFLoss (code/model/networks/loss_wfr.py:34-79), forward fused with its own backward ---- */
 /* loss_core = rgb L1 + eikonal_weight * eikonal + line_weight * calibrated line loss.  out[8] = {loss_core, rgb_loss,
  * eikonal_loss, line_loss, l2d_loss (uncalibrated, statistics only), count}.  g_* = d loss_core / d input.

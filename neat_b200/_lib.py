@@ -48,6 +48,8 @@ SIGNATURES = {
     "neat_line_geometry": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "neat_encodels": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "neat_point_line_attraction": (_I, [_P, _I, _I, _I, ctypes.c_float, _P, _P, _P, _P]),
+    "neat_linear_sum_assignment": (_I, [_P, _I, _I, _P, _P]),
+    "neat_junction_match": (_I, [_P, _I, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "neat_loss_forward_backward": (_I, [_P, _P]),
     "neat_project_calib_backward": (_I, [_I, _P, _P, _P, _P, _P]),
     "neat_dbscan_workspace_bytes": (ctypes.c_size_t, [_I]),
@@ -119,8 +121,8 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    lib.neat_debug_set_desc_swap.restype = _I
-    lib.neat_debug_set_desc_swap.argtypes = [_I]
+    lib.neat_debug_set_l2_prefetch.restype = _I
+    lib.neat_debug_set_l2_prefetch.argtypes = [_I]
     _lib = lib
     return lib
 

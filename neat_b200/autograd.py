@@ -55,6 +55,28 @@ class NeatStepFunction(torch.autograd.Function):
         st.R, st.S, st.dirs, st.cam, st.z, st.n_iters = R, S, dirs, cam, z, n_it
         pts = renderer.ray_points(cam, dirs, z)
         st.sdf, st.grad, st.act, st.feat, st.sdf_save = renderer.sdf_outputs(pts, M, clamp=True, training=True, tag="render")
+        # eikonal points (neat_wfr_rend_a.py:515-527): R uniform in the bounding cube + R near-surface.  They only need
+        # the sampler's output, and their 2R/128 tiles fit into the tail of the render launch (148 persistent CTAs, the
+        # last round of tiles leaves most SMs idle): launched on a side stream right behind it.
+        if st.eik_uniform is None:
+            r = renderer.scene_bounding_sphere
+            if renderer.sampler.rng == "device":
+                st.eik_uniform = torch.empty(R, 3, device=dev).uniform_(-r, r)
+            else:
+                st.eik_uniform = torch.empty(R, 3).uniform_(-r, r).to(dev)  # the reference's CPU-generator draw
+        near = cam[None, :] + z_eik * dirs
+        st.eik_pts = torch.cat([st.eik_uniform.to(dev, torch.float32), near], 0).contiguous()
+        pe = renderer.explicit_points(st.eik_pts)
+        main, side = torch.cuda.current_stream(dev), renderer.side_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(fork)
+            _, grad_theta, _, _, st.eik_save = renderer.sdf_outputs(pe, 2 * R, clamp=False, training=True,
+                                                                    want_feat=False, want_sdf=False, tag="eik")
+            eik_done = torch.cuda.Event()
+            eik_done.record(side)
+        grad_theta.record_stream(main)
         st.rgb, st.rend_save = renderer.head_forward(0, pts, M, st.grad, st.feat, training=True)
         st.lines, st.att_save = renderer.head_forward(1, pts, M, st.grad, st.feat, training=True)
         w, rgb_values, lines3d, depth, points3d, _ = renderer.composite(z, st.sdf, st.rgb, st.lines, None, cam, dirs,
@@ -69,18 +91,7 @@ class NeatStepFunction(torch.autograd.Function):
         st.sdf3, st.grad3, _, _, _ = renderer.sdf_outputs(p3, R, clamp=True, want_feat=False, tag="surface")
         st.lines2d, st.lines2d_calib, st.l3d, st.pose_inv = renderer.line_geometry(pose, K, st.uv_proj, points3d, st.grad3,
                                                                                    lines3d)
-        # eikonal points (neat_wfr_rend_a.py:515-527): R uniform in the bounding cube + R near-surface
-        if st.eik_uniform is None:
-            r = renderer.scene_bounding_sphere
-            if renderer.sampler.rng == "device":
-                st.eik_uniform = torch.empty(R, 3, device=dev).uniform_(-r, r)
-            else:
-                st.eik_uniform = torch.empty(R, 3).uniform_(-r, r).to(dev)  # the reference's CPU-generator draw
-        near = cam[None, :] + z_eik * dirs
-        st.eik_pts = torch.cat([st.eik_uniform.to(dev, torch.float32), near], 0).contiguous()
-        pe = renderer.explicit_points(st.eik_pts)
-        _, grad_theta, _, _, st.eik_save = renderer.sdf_outputs(pe, 2 * R, clamp=False, training=True,
-                                                                want_feat=False, want_sdf=False, tag="eik")
+        main.wait_event(eik_done)
         fctx.renderer, fctx.st = renderer, st
         fctx.beta_shape = beta_param.shape
         return rgb_values, lines3d.view(R, 2, 3), grad_theta
@@ -120,10 +131,21 @@ class NeatStepFunction(torch.autograd.Function):
         with renderer.timed("sdf_bwd_M%d" % M):
             _lib.check(lib.neat_sdf_backward(ctx._h, ctypes.byref(pts), _ptr(n_bar), _ptr(sdf_bar), _ptr(feat_bar),
                                              _ptr(st.act), _ptr(st.sdf_save), _ptr(sb), _ptr(scratch), stream))
+        # the eikonal points' double backward rides in the tail of the launch above (side stream, own scratch)
         pe = renderer.explicit_points(st.eik_pts)
         sbe = pool.get("bwd.sdf_eik", int(lib.neat_sdf_bwd_save_bytes(ctx._h, 2 * R)), torch.uint8)
-        _lib.check(lib.neat_sdf_backward(ctx._h, ctypes.byref(pe), _ptr(gtb), None, None, None, _ptr(st.eik_save), _ptr(sbe),
-                                         _ptr(scratch), stream))
+        scratch_e = pool.get("bwd.scratch_eik", int(lib.neat_sdf_bwd_scratch_bytes(ctx._h, 2 * R)), torch.uint8)
+        main, side = torch.cuda.current_stream(dev), renderer.side_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(fork)
+            _lib.check(lib.neat_sdf_backward(ctx._h, ctypes.byref(pe), _ptr(gtb), None, None, None, _ptr(st.eik_save),
+                                             _ptr(sbe), _ptr(scratch_e), ctx._stream()))
+            eik_done = torch.cuda.Event()
+            eik_done.record(side)
+        gtb.record_stream(side)
+        main.wait_event(eik_done)
         flat_grad = torch.zeros(ctx.n_params, device=dev)
         groups = (_lib.GradGroup * 2)()
         groups[0] = _lib.GradGroup(M, _ptr(st.sdf_save), _ptr(sb), _ptr(st.feat),

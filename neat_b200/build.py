@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libneat_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-SOURCES = ["api.cu", "plan.cpp"]
+SOURCES = ["api.cu", "plan.cpp", "junction.cpp"]
 
 
 def _newer_than(target, deps):

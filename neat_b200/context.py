@@ -2,6 +2,7 @@
 effective-parameter buffer, and typed wrappers over the C entry points.  torch is used only for
 device memory and the current stream."""
 import ctypes
+import os
 
 import torch
 
@@ -42,6 +43,8 @@ class Context:
         self._h = ctypes.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.neat_create(ctypes.byref(self.cfg), ctypes.byref(self._h)))
+            if os.environ.get("NEAT_L2_PREFETCH") is not None:  # A/B knob for profiling only
+                _lib.check(self.lib.neat_debug_set_l2_prefetch(int(os.environ["NEAT_L2_PREFETCH"])))
         self.n_params = int(self.lib.neat_param_count(self._h))
         self.layers = []  # (net index, layer, in, out, w_off, b_off)
         for net, n_l in ((0, self.cfg.sdf_layers), (1, self.cfg.head_layers), (2, self.cfg.head_layers)):

@@ -902,8 +902,9 @@ int neat_set_precision(neat_ctx* c, int fast) {
 }
 
 // ---------------------------------------------------------------- debug / bring-up
-int neat_debug_set_desc_swap(int swap) {
-  CK(cudaMemcpyToSymbol(g_desc_swap, &swap, sizeof(int)));
+
+int neat_debug_set_l2_prefetch(int on) {
+  CK(cudaMemcpyToSymbol(g_l2_prefetch, &on, sizeof(int)));
   return NEAT_OK;
 }
 

@@ -25,8 +25,7 @@ __device__ __forceinline__ void load_tile8(const uint8_t* hi_plane, const uint8_
   }
 }
 // ReLU mask of 8 columns from the hi plane of the saved ReLU output (bf16(u) != 0  <=>  u > 0)
-__device__ __forceinline__ uint32_t load_mask8(const uint8_t* hi_plane, int chunk, int row) {
-  const uint4 h = *reinterpret_cast<const uint4*>(hi_plane + chunk * A_CHUNK_BYTES + row * 16);
+__device__ __forceinline__ uint32_t mask8(const uint4& h) {
   const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
   uint32_t m = 0;
 #pragma unroll
@@ -70,12 +69,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_bwd_kernel(const __grid_c
   engine_init(sm);
   const int n_tiles = (p.M + TILE_M - 1) / TILE_M;
   const int my_tiles = (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform();
 
   if (warp == EPI_WARPS) {
-    if (lane == 0) producer_loop(sm, p.prog, p.packed, my_tiles);
+    producer_loop(sm, p.prog, p.packed, my_tiles);
   } else if (warp == EPI_WARPS + 1) {
-    if (lane == 0) mma_loop(sm, p.prog, my_tiles);
+    mma_loop(sm, p.prog, my_tiles);
   } else {
     Epi e = epi_make(sm);
     const HeadSaveLayout fl = head_save_layout(p.HL);
@@ -107,22 +106,39 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_bwd_kernel(const __grid_c
       for (int l = p.HL - 1; l >= 1; --l) {
         const Step st = p.prog.s[p.HL - 1 - l];
         const uint8_t* __restrict__ u_hi = frec + fl.u + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES;
-        epi_wait_d(sm, e);
-        epi_planes_free(sm, e);
+        // the saved ReLU outputs (masks) of all four groups are requested before waiting for the accumulator
+        uint4 mraw[N_GROUPS][2];
+#pragma unroll
         for (int g = 0; g < N_GROUPS; ++g) {
           const int c0 = epi_col(e, g);
           if (c0 < st.w.npad) {
-            uint32_t m[2];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) m[j] = load_mask8(u_hi, (c0 >> 3) + j, e.row);
-            float acc[16];
-            tmem_ld16(e.tm + st.d_col + c0, acc);
-            tmem_ld_wait();
+            for (int j = 0; j < 2; ++j) mraw[g][j] = ldg128(u_hi + ((c0 >> 3) + j) * A_CHUNK_BYTES + e.row * 16);
+          }
+        }
+        epi_wait_d(sm, e);
+        epi_planes_free(sm, e);
+        uint32_t mbits[2] = {0u, 0u};  // 16 mask bits per group (the raw vectors are dead before the accumulator loads)
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
+        for (int g = 0; g < N_GROUPS; ++g) {
+          if (epi_col(e, g) < st.w.npad)
+            mbits[g >> 1] |= (mask8(mraw[g][0]) | (mask8(mraw[g][1]) << 8)) << (16 * (g & 1));
+        }
+        float nxt[16];
+        tmem_ld16(e.tm + st.d_col + epi_col(e, 0), nxt);
 #pragma unroll
-              for (int k = 0; k < 8; ++k)
-                if (!((m[j] >> k) & 1u)) acc[8 * j + k] = 0.f;
+        for (int g = 0; g < N_GROUPS; ++g) {
+          const int c0 = epi_col(e, g);
+          float acc[16];
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = nxt[j];
+          if (g + 1 < N_GROUPS) tmem_ld16(e.tm + st.d_col + epi_col(e, g + 1), nxt);
+          if (c0 < st.w.npad) {
+            const uint32_t m = mbits[g >> 1] >> (16 * (g & 1));
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+              if (!((m >> k) & 1u)) acc[k] = 0.f;
             store_a16(sm.a_hi, sm.a_lo, e.row, c0, acc);
           }
           epi_publish_group(sm, g);
@@ -207,13 +223,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
   engine_init(sm);
   const int n_tiles = (p.pts.M + TILE_M - 1) / TILE_M;
   const int my_tiles = (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform();
   const int L = p.L;
 
   if (warp == EPI_WARPS) {
-    if (lane == 0) producer_loop(sm, p.prog, p.packed, my_tiles);
+    producer_loop(sm, p.prog, p.packed, my_tiles);
   } else if (warp == EPI_WARPS + 1) {
-    if (lane == 0) mma_loop(sm, p.prog, my_tiles);
+    mma_loop(sm, p.prog, my_tiles);
   } else {
     Epi e = epi_make(sm);
     const SdfSaveLayout fl = sdf_save_layout(L, true);
@@ -265,27 +281,42 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
         const uint8_t* __restrict__ a_hi = frec + fl.a + static_cast<size_t>(l) * TILE_MAIN_BYTES;
         const uint8_t* __restrict__ a_lo = a_hi + PLANE_MAIN_BYTES;
         float* __restrict__ zh = zhat_base + static_cast<size_t>(l) * (256 * TILE_M);
+        const int npad = st.w.npad;
+        float s1n[8];
+        uint4 ahn, aln;
+        auto issue = [&](int u) {
+          const int c = epi_unit_col(e, u);
+          if (c < npad) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s1n[j] = __ldg(d1 + (c + j) * TILE_M + e.row);
+            ahn = ldg128(a_hi + (c >> 3) * A_CHUNK_BYTES + e.row * 16);
+            aln = ldg128(a_lo + (c >> 3) * A_CHUNK_BYTES + e.row * 16);
+          }
+        };
+        issue(0);
         epi_wait_d(sm, e);  // D = q_l = W_l p_l
         epi_planes_free(sm, e);
-        for (int g = 0; g < N_GROUPS; ++g) {
-          const int c0 = epi_col(e, g);
-          if (c0 < st.w.npad) {
-            float s1[16], a[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) s1[j] = __ldg(d1 + (c0 + j) * TILE_M + e.row);
-            load_tile8(a_hi, a_lo, (c0 >> 3), e.row, a);
-            load_tile8(a_hi, a_lo, (c0 >> 3) + 1, e.row, a + 8);
-            float q[16];
-            tmem_ld16(e.tm + st.d_col + c0, q);
+        for (int u = 0; u < N_UNITS; ++u) {
+          const int c = epi_unit_col(e, u);
+          float s1[8];
+          const uint4 ah = ahn, al = aln;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s1[j] = s1n[j];
+          if (u + 1 < N_UNITS) issue(u + 1);
+          if (c < npad) {
+            float a[8], q[8];
+            tmem_ld8(e.tm + st.d_col + c, q);
+            unpack_hilo8(ah, al, a);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              zh[(c0 + i) * TILE_M + e.row] = SP_BETA * (1.0f - s1[i]) * a[i] * q[i];  // sigma'' g_{l+1} q_l
+            for (int i = 0; i < 8; ++i) {
+              zh[(c + i) * TILE_M + e.row] = SP_BETA * (1.0f - s1[i]) * a[i] * q[i];  // sigma'' g_{l+1} q_l
               q[i] *= s1[i];                                                            // p_{l+1}
             }
-            store_a16(sm.a_hi, sm.a_lo, e.row, c0, q);
+            store_a8(sm.a_hi, sm.a_lo, e.row, c, q);
           }
-          if (l < L - 2) epi_publish_group(sm, g);  // -> F_{l+1}
+          if ((u & 1) && l < L - 2) epi_publish_group(sm, u >> 1);  // -> F_{l+1}
         }
         if (l == L - 2) fence_proxy_async();
         epi_store_main(sm, e, sm.a_hi, sm.a_lo, brec + bl.p + static_cast<size_t>(l) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);  // p_{l+1}
@@ -314,7 +345,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
         }
       }
       epi_publish_all(sm);  // -> T_{L-1}
-      mbar_arrive(&sm.wr_done);
+      epi_wrote(sm);
       if (e.lead) {
         mbar_wait(&sm.wr_done, e.wr_phase);
         uint8_t* dst = brec + bl.zb + static_cast<size_t>(L - 1) * TILE_MAIN_BYTES;
@@ -330,26 +361,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
         const Step st = p.prog.s[(L - 1) + (L - 1 - l)];
         const int ncols = p.prog.s[l - 1].w.npad;  // width of z_bar_{l-1}
         const float* __restrict__ d1 = d1_base + static_cast<size_t>(l - 1) * (256 * TILE_M);
-        const float* __restrict__ zh = zhat_base + static_cast<size_t>(l - 1) * (256 * TILE_M);
+        const float* zh = zhat_base + static_cast<size_t>(l - 1) * (256 * TILE_M);
+        float s1n[8], zzn[8];
+        auto issue = [&](int u) {
+          const int c = epi_unit_col(e, u);
+          if (c < ncols) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              s1n[j] = __ldg(d1 + (c + j) * TILE_M + e.row);
+              zzn[j] = zh[(c + j) * TILE_M + e.row];  // written by this very thread in the tangent sweep
+            }
+          }
+        };
+        issue(0);
         epi_wait_d(sm, e);  // D = W_l^T z_bar_l  (gradient w.r.t. the input of layer l)
         epi_planes_free(sm, e);
-        for (int g = 0; g < N_GROUPS; ++g) {
-          const int c0 = epi_col(e, g);
-          if (c0 < ncols) {
-            float s1[16], zz[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              s1[j] = __ldg(d1 + (c0 + j) * TILE_M + e.row);
-              zz[j] = zh[(c0 + j) * TILE_M + e.row];
-            }
-            float gq[16];
-            tmem_ld16(e.tm + st.d_col + c0, gq);
+        for (int u = 0; u < N_UNITS; ++u) {
+          const int c = epi_unit_col(e, u);
+          float s1[8], zz[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { s1[j] = s1n[j]; zz[j] = zzn[j]; }
+          if (u + 1 < N_UNITS) issue(u + 1);
+          if (c < ncols) {
+            float gq[8];
+            tmem_ld8(e.tm + st.d_col + c, gq);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) gq[j] = s1[j] * gq[j] + zz[j];
-            store_a16(sm.a_hi, sm.a_lo, e.row, c0, gq);
+            for (int j = 0; j < 8; ++j) gq[j] = s1[j] * gq[j] + zz[j];
+            store_a8(sm.a_hi, sm.a_lo, e.row, c, gq);
           }
-          if (l >= 2) epi_publish_group(sm, g);  // -> T_{l-1}
+          if ((u & 1) && l >= 2) epi_publish_group(sm, u >> 1);  // -> T_{l-1}
         }
         if (l < 2) fence_proxy_async();
         epi_store_main(sm, e, sm.a_hi, sm.a_lo, brec + bl.zb + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);  // z_bar_{l-1}

@@ -24,12 +24,12 @@
 
 namespace neat {
 
-// Debug knob (neat_debug_set_desc_swap): exchanges the LBO / SBO fields of every matrix descriptor.
-__constant__ int g_desc_swap = 0;
 // k_stride: bytes between core matrices adjacent along K; mn_stride: along M/N
 __device__ __forceinline__ uint64_t make_desc_k(uint32_t saddr, uint32_t k_stride, uint32_t mn_stride) {
-  return g_desc_swap ? make_desc(saddr, mn_stride, k_stride) : make_desc(saddr, k_stride, mn_stride);
+  return make_desc(saddr, k_stride, mn_stride);
 }
+// a descriptor whose start address is `bytes` further (the 14-bit address field cannot carry: smem < 256 KB)
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (bytes >> 4); }
 
 template <int STAGES>
 struct alignas(1024) EngineSmem {
@@ -38,28 +38,28 @@ struct alignas(1024) EngineSmem {
   uint8_t w[STAGES][W_STAGE_BYTES];
   uint64_t full[STAGES];
   uint64_t empty[STAGES];
-  uint64_t a_ready[N_GROUPS];  // 512 arrivals each: every epilogue thread, once per column group and stage
-  uint64_t aux_ready;          // 128 arrivals: the group-0 warps
+  uint64_t a_ready[N_GROUPS];  // 16 arrivals each: lane 0 of every epilogue warp, once per column group and stage
+  uint64_t aux_ready;          // 4 arrivals: lane 0 of the slice-0 warps
   uint64_t d_ready;
   uint64_t in_ready;           // bulk loads of input operand tiles (heads / backward kernels)
-  uint64_t wr_done;            // 512 arrivals: every epilogue thread wrote (and fenced) its part of the A planes
+  uint64_t wr_done;            // 16 arrivals: every epilogue warp wrote (and fenced) its part of the A planes
   uint64_t rd_done;            // 1 arrival: the lead thread's bulk store finished reading the A planes
   uint32_t tmem_base;
 };
 
 template <int STAGES>
 __device__ __forceinline__ void engine_init(EngineSmem<STAGES>& sm) {
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_uniform();
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&sm.full[i], 1);
       mbar_init(&sm.empty[i], 1);
     }
-    for (int g = 0; g < N_GROUPS; ++g) mbar_init(&sm.a_ready[g], EPI_THREADS);
-    mbar_init(&sm.aux_ready, 128);
+    for (int g = 0; g < N_GROUPS; ++g) mbar_init(&sm.a_ready[g], EPI_WARPS);
+    mbar_init(&sm.aux_ready, 4);
     mbar_init(&sm.d_ready, 1);
     mbar_init(&sm.in_ready, 1);
-    mbar_init(&sm.wr_done, EPI_THREADS);
+    mbar_init(&sm.wr_done, EPI_WARPS);
     mbar_init(&sm.rd_done, 1);
     fence_mbar_init();
   }
@@ -73,10 +73,10 @@ template <int STAGES>
 __device__ __forceinline__ void engine_fini(EngineSmem<STAGES>& sm) {
   tc_fence_before();
   __syncthreads();
-  if ((threadIdx.x >> 5) == EPI_WARPS) tmem_dealloc(sm.tmem_base, TMEM_COLS);
+  if (warp_idx_uniform() == EPI_WARPS) tmem_dealloc(sm.tmem_base, TMEM_COLS);
 }
 
-// producer warp, lane 0: stream every slab of every step, for every tile this CTA owns
+// producer warp (all lanes, converged; one elected lane issues): stream every slab of every step, for every tile
 template <int STAGES>
 __device__ __forceinline__ void producer_loop(EngineSmem<STAGES>& sm, const Program& prog, const uint8_t* packed,
                                               int n_tiles) {
@@ -90,42 +90,51 @@ __device__ __forceinline__ void producer_loop(EngineSmem<STAGES>& sm, const Prog
       const uint8_t* src = packed + w.off;
       for (int ks = 0; ks < nk; ++ks) {
         mbar_wait(&sm.empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&sm.full[stage], bytes);
-        bulk_g2s(sm.w[stage], src + static_cast<size_t>(ks) * slab, bytes, &sm.full[stage]);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&sm.full[stage], bytes);
+          bulk_g2s(sm.w[stage], src + static_cast<size_t>(ks) * slab, bytes, &sm.full[stage]);
+        }
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   }
 }
 
-// MMA warp, lane 0
+// MMA warp (all lanes, converged; one elected lane issues the tcgen05 instructions)
 template <int STAGES>
 __device__ __forceinline__ void mma_loop(EngineSmem<STAGES>& sm, const Program& prog, int n_tiles) {
   uint32_t stage = 0, phase = 0, a_phase = 0, aux_phase = 0;
-  const uint32_t tmem = sm.tmem_base;
-  const uint32_t a_hi = smem_u32(sm.a_hi), a_lo = smem_u32(sm.a_lo);
+  const uint32_t tmem = __shfl_sync(0xffffffffu, sm.tmem_base, 0);
+  // descriptor templates, advanced by plain additions in the k-step loop
+  const uint64_t da_hi0 = make_desc_k(smem_u32(sm.a_hi), A_CHUNK_BYTES, 128);
+  const uint64_t da_lo0 = make_desc_k(smem_u32(sm.a_lo), A_CHUNK_BYTES, 128);
+  const uint32_t w0 = smem_u32(sm.w[0]);
+  const bool fast = prog.fast != 0;
   for (int t = 0; t < n_tiles; ++t) {
     for (int i = 0; i < prog.n; ++i) {
       const Step st = prog.s[i];
       const uint32_t npad = st.w.npad;
       const uint32_t idesc = make_idesc(TILE_M, npad, 0, 0);
       const uint32_t d = tmem + st.d_col;
+      const uint64_t db0 = make_desc_k(w0, npad * 16, 128);  // stage 0, hi plane; lo plane = + npad * 32 bytes
       uint32_t acc = 0;
       auto kstep = [&](uint32_t col0) {
         mbar_wait(&sm.full[stage], phase);
         tc_fence_after();
-        const uint32_t a_off = (col0 >> 3) * A_CHUNK_BYTES;
-        const uint64_t da_hi = make_desc_k(a_hi + a_off, A_CHUNK_BYTES, 128);
-        const uint64_t da_lo = make_desc_k(a_lo + a_off, A_CHUNK_BYTES, 128);
-        const uint32_t wb = smem_u32(sm.w[stage]);
-        const uint64_t db_hi = make_desc_k(wb, npad * 16, 128);
-        const uint64_t db_lo = make_desc_k(wb + npad * 32, npad * 16, 128);
-        umma_bf16(d, da_hi, db_hi, idesc, acc);
-        if (!prog.fast) {
-          umma_bf16(d, da_hi, db_lo, idesc, 1u);
-          umma_bf16(d, da_lo, db_hi, idesc, 1u);
+        const uint64_t da_hi = desc_advance(da_hi0, col0 * (A_CHUNK_BYTES / 8));
+        const uint64_t da_lo = desc_advance(da_lo0, col0 * (A_CHUNK_BYTES / 8));
+        const uint64_t db_hi = desc_advance(db0, stage * W_STAGE_BYTES);
+        const uint64_t db_lo = desc_advance(db_hi, npad * 32);
+        if (elect_one()) {
+          umma_bf16(d, da_hi, db_hi, idesc, acc);
+          if (!fast) {
+            umma_bf16(d, da_hi, db_lo, idesc, 1u);
+            umma_bf16(d, da_lo, db_hi, idesc, 1u);
+          }
+          umma_commit(&sm.empty[stage]);
         }
-        umma_commit(&sm.empty[stage]);
+        __syncwarp();
         acc = 1u;
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       };
@@ -145,7 +154,10 @@ __device__ __forceinline__ void mma_loop(EngineSmem<STAGES>& sm, const Program& 
       }
       if (st.wait_a) a_phase ^= 1;
       for (int ks = 0; ks < st.w.nk_aux; ++ks) kstep(A_MAIN_COLS + 16u * ks);
-      if (st.commit_d) umma_commit(&sm.d_ready);
+      if (st.commit_d) {
+        if (elect_one()) umma_commit(&sm.d_ready);
+        __syncwarp();
+      }
     }
   }
 }
@@ -160,12 +172,12 @@ struct Epi {
 template <int STAGES>
 __device__ __forceinline__ Epi epi_make(const EngineSmem<STAGES>& sm) {
   Epi e;
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_uniform();
   e.lane = threadIdx.x & 31;
   e.q = warp & 3;
   e.j = warp >> 2;
   e.row = e.q * 32 + e.lane;
-  e.tm = sm.tmem_base + (static_cast<uint32_t>(e.q * 32) << 16);
+  e.tm = __shfl_sync(0xffffffffu, sm.tmem_base, 0) + (static_cast<uint32_t>(e.q * 32) << 16);
   e.d_phase = 0;
   e.wr_phase = 0;
   e.rd_phase = 0;
@@ -180,26 +192,49 @@ __device__ __forceinline__ void epi_wait_d(EngineSmem<STAGES>& sm, Epi& e) {
 }
 // column offset of this warp's 16-column slice in group g
 __device__ __forceinline__ int epi_col(const Epi& e, int g) { return g * GROUP_COLS + 16 * e.j; }
-// after this thread finished writing its slice of group g of the A tile (and reading that part of the accumulator)
+// The kernels whose epilogue also reads saved tensors from global memory walk their 64 columns per layer as 8
+// "units" of 8 columns (unit u = group u/2, half u%2) and keep the loads of unit u+1 in flight while unit u is
+// computed; the loads of unit 0 are issued BEFORE waiting for the accumulator, under the tail of the MMAs.
+constexpr int N_UNITS = 2 * N_GROUPS;
+__device__ __forceinline__ int epi_unit_col(const Epi& e, int u) { return (u >> 1) * GROUP_COLS + 16 * e.j + 8 * (u & 1); }
+__device__ __forceinline__ uint4 ldg128(const uint8_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+// fp32 values of 8 columns from the raw hi / lo vectors of an operand tile row
+__device__ __forceinline__ void unpack_hilo8(const uint4& h, const uint4& l, float* v) {
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
+    v[2 * i + 1] = __uint_as_float(hw[i] & 0xFFFF0000u) + __uint_as_float(lw[i] & 0xFFFF0000u);
+  }
+}
+// after this thread finished writing its slice of group g of the A tile (and reading that part of the accumulator).
+// Every lane fences its own writes, the warp converges, ONE lane arrives: 16 arrivals per barrier phase instead of
+// 512 serialized shared-memory atomics on one word.  All publish / store helpers must be called warp-uniformly.
+__device__ __forceinline__ bool epi_elect() {
+  __syncwarp();
+  return (threadIdx.x & 31) == 0;
+}
 template <int STAGES>
 __device__ __forceinline__ void epi_publish_group(EngineSmem<STAGES>& sm, int g) {
   fence_proxy_async();
   tc_fence_before();
-  mbar_arrive(&sm.a_ready[g]);
+  if (epi_elect()) mbar_arrive(&sm.a_ready[g]);
 }
 // a stage that wrote no main columns still has to arrive on every group (the MMA issuer waits on all of them)
 template <int STAGES>
 __device__ __forceinline__ void epi_publish_all(EngineSmem<STAGES>& sm) {
   fence_proxy_async();
   tc_fence_before();
+  if (epi_elect()) {
 #pragma unroll
-  for (int g = 0; g < N_GROUPS; ++g) mbar_arrive(&sm.a_ready[g]);
+    for (int g = 0; g < N_GROUPS; ++g) mbar_arrive(&sm.a_ready[g]);
+  }
 }
 template <int STAGES>
 __device__ __forceinline__ void epi_publish_aux(EngineSmem<STAGES>& sm) {  // slice-0 warps (j == 0) only
   fence_proxy_async();
   tc_fence_before();
-  mbar_arrive(&sm.aux_ready);
+  if (epi_elect()) mbar_arrive(&sm.aux_ready);
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 // The A planes may be overwritten only after the previous bulk store out of them finished READING shared memory.
@@ -214,12 +249,16 @@ __device__ __forceinline__ void epi_planes_free(EngineSmem<STAGES>& sm, Epi& e) 
   mbar_wait(&sm.rd_done, e.rd_phase);
   e.rd_phase ^= 1;
 }
-// every epilogue thread calls this after writing + fencing its part; the lead thread waits for all 512 and then
+// every epilogue thread calls this after writing + fencing its part; the lead thread waits for all 16 warps and then
 // stores `plane_bytes` of both planes (starting at a_hi / a_lo) to dst / dst + plane_bytes.  Nobody else waits.
+template <int STAGES>
+__device__ __forceinline__ void epi_wrote(EngineSmem<STAGES>& sm) {
+  if (epi_elect()) mbar_arrive(&sm.wr_done);
+}
 template <int STAGES>
 __device__ __forceinline__ void epi_store_main(EngineSmem<STAGES>& sm, Epi& e, const uint8_t* a_hi, const uint8_t* a_lo,
                                                uint8_t* dst, int plane_bytes) {
-  mbar_arrive(&sm.wr_done);
+  epi_wrote(sm);
   if (e.lead) {
     mbar_wait(&sm.wr_done, e.wr_phase);
     bulk_s2g(dst, a_hi, plane_bytes);
@@ -229,33 +268,28 @@ __device__ __forceinline__ void epi_store_main(EngineSmem<STAGES>& sm, Epi& e, c
   e.wr_phase ^= 1;
 }
 
-// write 32 consecutive columns [c0, c0+32) of row `row` (c0 % 8 == 0) into the A tile
-__device__ __forceinline__ void store_a32(uint8_t* a_hi, uint8_t* a_lo, int row, int c0, const float* v) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint4 hi, lo;
-    split8(v + 8 * j, hi, lo);
-    const int off = ((c0 >> 3) + j) * A_CHUNK_BYTES + row * 16;
-    *reinterpret_cast<uint4*>(a_hi + off) = hi;
-    *reinterpret_cast<uint4*>(a_lo + off) = lo;
-  }
+// 16-byte store through the shared window (STS.128; a generic ST.E.128 pays the address translation)
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// write 16 / 8 consecutive columns [c0, ...) of row `row` (c0 % 8 == 0) into the A tile
 __device__ __forceinline__ void store_a16(uint8_t* a_hi, uint8_t* a_lo, int row, int c0, const float* v) {
+  const uint32_t off = (c0 >> 3) * A_CHUNK_BYTES + row * 16;
+  const uint32_t s_hi = smem_u32(a_hi) + off, s_lo = smem_u32(a_lo) + off;
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     uint4 hi, lo;
     split8(v + 8 * j, hi, lo);
-    const int off = ((c0 >> 3) + j) * A_CHUNK_BYTES + row * 16;
-    *reinterpret_cast<uint4*>(a_hi + off) = hi;
-    *reinterpret_cast<uint4*>(a_lo + off) = lo;
+    sts128(s_hi + j * A_CHUNK_BYTES, hi);
+    sts128(s_lo + j * A_CHUNK_BYTES, lo);
   }
 }
 __device__ __forceinline__ void store_a8(uint8_t* a_hi, uint8_t* a_lo, int row, int c0, const float* v) {
   uint4 hi, lo;
   split8(v, hi, lo);
-  const int off = (c0 >> 3) * A_CHUNK_BYTES + row * 16;
-  *reinterpret_cast<uint4*>(a_hi + off) = hi;
-  *reinterpret_cast<uint4*>(a_lo + off) = lo;
+  const uint32_t off = (c0 >> 3) * A_CHUNK_BYTES + row * 16;
+  sts128(smem_u32(a_hi) + off, hi);
+  sts128(smem_u32(a_lo) + off, lo);
 }
 
 // ---------------------------------------------------------------- activations
@@ -264,21 +298,33 @@ constexpr float SP_THRESH = 20.0f;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 
+// bare MUFU.EX2 / MUFU.LG2: exp2f() wraps the MUFU in a denormal-range rescue (FSETP + 2 predicated FMUL per
+// element); here an argument below -126 flushes to 0, i.e. softplus(z) = 0 for 100 z < -87 (true value < 1e-40)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // nn.Softplus(beta=100, threshold=20):  z if 100 z > 20 else log1p(exp(100 z)) / 100
 __device__ __forceinline__ float softplus100(float z) {
-  const float bz = z * SP_BETA;
-  const float e = exp2f(fminf(bz, SP_THRESH) * LOG2E);
-  const float sp = __log2f(1.0f + e) * (LN2 / SP_BETA);
-  return bz > SP_THRESH ? z : sp;
+  const float t = z * (SP_BETA * LOG2E);  // log2(e^(100 z))
+  const float e = ex2_approx(fminf(t, SP_THRESH * LOG2E));
+  const float sp = lg2_approx(1.0f + e) * (LN2 / SP_BETA);
+  return t > SP_THRESH * LOG2E ? z : sp;
 }
 // softplus and its derivative sigmoid(100 z) (1 above the threshold, as autograd computes it)
 __device__ __forceinline__ void softplus100_d1(float z, float& h, float& d1) {
-  const float bz = z * SP_BETA;
-  const float e = exp2f(fminf(bz, SP_THRESH) * LOG2E);
+  const float t = z * (SP_BETA * LOG2E);
+  const float e = ex2_approx(fminf(t, SP_THRESH * LOG2E));
   const float ope = 1.0f + e;
-  const float sp = __log2f(ope) * (LN2 / SP_BETA);
+  const float sp = lg2_approx(ope) * (LN2 / SP_BETA);
   const float sg = __fdividef(e, ope);
-  const bool lin = bz > SP_THRESH;
+  const bool lin = t > SP_THRESH * LOG2E;
   h = lin ? z : sp;
   d1 = lin ? 1.0f : sg;
 }

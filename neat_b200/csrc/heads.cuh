@@ -42,12 +42,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_fwd_kernel(const __grid_c
   engine_init(sm);
   const int n_tiles = (p.pts.M + TILE_M - 1) / TILE_M;
   const int my_tiles = (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform();
 
   if (warp == EPI_WARPS) {
-    if (lane == 0) producer_loop(sm, p.prog, p.packed, my_tiles);
+    producer_loop(sm, p.prog, p.packed, my_tiles);
   } else if (warp == EPI_WARPS + 1) {
-    if (lane == 0) mma_loop(sm, p.prog, my_tiles);
+    mma_loop(sm, p.prog, my_tiles);
   } else {
     Epi e = epi_make(sm);
     const HeadSaveLayout lay = head_save_layout(p.HL);
@@ -116,12 +116,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_fwd_kernel(const __grid_c
         const float4* bias = reinterpret_cast<const float4*>(p.packed + st.w.bias_off);
         epi_wait_d(sm, e);
         if (tr) epi_planes_free(sm, e);
+        // (TMEM columns past npad are allocated but hold stale data: loaded unconditionally, never used)
+        float nxt[16];
+        tmem_ld16(e.tm + st.d_col + epi_col(e, 0), nxt);
+#pragma unroll
         for (int g = 0; g < N_GROUPS; ++g) {
           const int c0 = epi_col(e, g);
+          float acc[16];
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = nxt[j];
+          if (g + 1 < N_GROUPS) tmem_ld16(e.tm + st.d_col + epi_col(e, g + 1), nxt);
           if (c0 < st.w.npad) {
-            float acc[16];
-            tmem_ld16(e.tm + st.d_col + c0, acc);
-            tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float4 b = __ldg(bias + (c0 >> 2) + j);

@@ -63,13 +63,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
   engine_init(sm);
   const int n_tiles = (p.pts.M + TILE_M - 1) / TILE_M;
   const int my_tiles = (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform();
   const int L = p.L;
 
   if (warp == EPI_WARPS) {
-    if (lane == 0) producer_loop(sm, p.prog, p.packed, my_tiles);
+    producer_loop(sm, p.prog, p.packed, my_tiles);
   } else if (warp == EPI_WARPS + 1) {
-    if (lane == 0) mma_loop(sm, p.prog, my_tiles);
+    mma_loop(sm, p.prog, my_tiles);
   } else {
     Epi e = epi_make(sm);
     const SdfSaveLayout lay = sdf_save_layout(L, p.training != 0);
@@ -101,12 +101,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
         float* d1 = d1_base + static_cast<size_t>(l) * (256 * TILE_M);
         epi_wait_d(sm, e);
         if (tr) epi_planes_free(sm, e);
+        // (TMEM columns past npad are allocated but hold stale data: loaded unconditionally, never used)
+        float nxt[16];
+        tmem_ld16(e.tm + st.d_col + epi_col(e, 0), nxt);
+#pragma unroll
         for (int g = 0; g < N_GROUPS; ++g) {
           const int c0 = epi_col(e, g);
+          float acc[16];
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = nxt[j];
+          if (g + 1 < N_GROUPS) tmem_ld16(e.tm + st.d_col + epi_col(e, g + 1), nxt);
           if (c0 < st.w.npad) {
-            float acc[16];
-            tmem_ld16(e.tm + st.d_col + c0, acc);
-            tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float4 b = __ldg(bias + (c0 >> 2) + j);
@@ -189,29 +195,40 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
         const int npad = st.w.npad;                            // width of the input of layer l
         const float* d1 = d1_base + static_cast<size_t>(l - 1) * (256 * TILE_M);
         const int n_main = (l == p.skip) ? p.H - p.E : npad;   // columns that feed a_{l-1}
+        float s1n[8];
+        auto issue = [&](int u) {
+          const int c = epi_unit_col(e, u);
+          if (c < npad) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s1n[j] = d1[(c + j) * TILE_M + e.row];  // written by this very thread
+          }
+        };
+        issue(0);
         epi_wait_d(sm, e);
         if (tr) epi_planes_free(sm, e);
-        for (int g = 0; g < N_GROUPS; ++g) {
-          const int c0 = epi_col(e, g);
-          if (c0 < npad) {
-            float s1[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) s1[j] = d1[(c0 + j) * TILE_M + e.row];
-            float acc[16];
-            tmem_ld16(e.tm + st.d_col + c0, acc);
+        for (int u = 0; u < N_UNITS; ++u) {
+          const int c = epi_unit_col(e, u);
+          float s1[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s1[j] = s1n[j];
+          if (u + 1 < N_UNITS) issue(u + 1);
+          if (c < npad) {
+            float acc[8];
+            tmem_ld8(e.tm + st.d_col + c, acc);
             tmem_ld_wait();
             if (l == p.skip) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int c = c0 + j;
-                if (c >= n_main) rskip[(c - n_main) * TILE_M + e.row] = acc[j];
+              for (int j = 0; j < 8; ++j) {
+                const int cc = c + j;
+                if (cc >= n_main) rskip[(cc - n_main) * TILE_M + e.row] = acc[j];
               }
             }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] *= s1[j];
-            store_a16(sm.a_hi, sm.a_lo, e.row, c0, acc);
+            for (int j = 0; j < 8; ++j) acc[j] *= s1[j];
+            store_a8(sm.a_hi, sm.a_lo, e.row, c, acc);
           }
-          epi_publish_group(sm, g);
+          if (u & 1) epi_publish_group(sm, u >> 1);
         }
         if (tr) epi_store_main(sm, e, sm.a_hi, sm.a_lo, rec + lay.a + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);
       }

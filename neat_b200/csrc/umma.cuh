@@ -12,6 +12,18 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Warp index the compiler can prove to be warp-uniform (a shuffle from lane 0): branches on it are uniform branches,
+// so the role loops below run converged and their addresses / descriptors live in uniform registers.  With a plain
+// `threadIdx.x >> 5` (or an `if (lane == 0)` around the loop) every tcgen05 / TMA instruction was wrapped in an
+// ELECT + R2UR + BRA.U.ANY serialisation loop: ~95 SASS instructions per k-step on the MMA issuer's critical path.
+__device__ __forceinline__ int warp_idx_uniform() { return __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0); }
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -57,6 +69,15 @@ __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, u
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
                "r"(bytes)
                : "memory");
+}
+// ask the L2 to fetch [gmem, gmem + bytes) (16-byte aligned, size % 16 == 0); no completion tracking.
+// Used by wgrad for its next tile (measured 1.60 -> 1.43 ms).  The same hint in front of the backward / normal-pass
+// epilogues' global loads made those kernels SLOWER (sdf_bwd 1.37 -> 1.57 ms) and was removed.
+// g_l2_prefetch (neat_debug_set_l2_prefetch) switches the hints off for A/B measurements.
+__constant__ int g_l2_prefetch = 1;
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem, uint32_t bytes) {
+  if (g_l2_prefetch)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -143,6 +164,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
       : "r"(taddr)
       : "memory");
 }

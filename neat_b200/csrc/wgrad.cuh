@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WJob* __rest
   extern __shared__ uint8_t smem_raw[];
   WgradSmem& sm = *reinterpret_cast<WgradSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const WJob job = jobs[blockIdx.x];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform();
   const int my_tiles = job.n_tiles > job.split ? (job.n_tiles - job.split + job.n_split - 1) / job.n_split : 0;
 
   if (threadIdx.x == 0) {
@@ -76,46 +76,64 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WJob* __rest
 
   const uint32_t xb = static_cast<uint32_t>(job.x_cols / 8) * A_CHUNK_BYTES;
   const uint32_t yb = static_cast<uint32_t>(job.n_cols / 8) * A_CHUNK_BYTES;
-  if (warp == 4 && lane == 0) {
+  if (warp == 4) {  // load warp (converged; one elected lane issues the bulk copies)
     for (int t = 0; t < my_tiles; ++t) {
       const uint64_t tile = static_cast<uint64_t>(job.split) + static_cast<uint64_t>(t) * job.n_split;
       const uint8_t* xs = job.x_base + tile * job.x_stride + static_cast<uint64_t>(job.m0 / 8) * A_CHUNK_BYTES;
       const uint8_t* ys = job.y_base + tile * job.y_stride;
       mbar_wait(&sm.empty, (t & 1) ^ 1);
-      mbar_arrive_expect_tx(&sm.full, 2 * xb + 2 * yb);
-      bulk_g2s(sm.x_hi, xs + job.x_hi, xb, &sm.full);
-      bulk_g2s(sm.x_lo, xs + job.x_lo, xb, &sm.full);
-      bulk_g2s(sm.y_hi, ys + job.y_hi, yb, &sm.full);
-      bulk_g2s(sm.y_lo, ys + job.y_lo, yb, &sm.full);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&sm.full, 2 * xb + 2 * yb);
+        bulk_g2s(sm.x_hi, xs + job.x_hi, xb, &sm.full);
+        bulk_g2s(sm.x_lo, xs + job.x_lo, xb, &sm.full);
+        bulk_g2s(sm.y_hi, ys + job.y_hi, yb, &sm.full);
+        bulk_g2s(sm.y_lo, ys + job.y_lo, yb, &sm.full);
+        if (t + 1 < my_tiles) {  // the next tile streams from HBM into the L2 while this one is multiplied
+          const uint8_t* xn = xs + static_cast<uint64_t>(job.n_split) * job.x_stride;
+          const uint8_t* yn = ys + static_cast<uint64_t>(job.n_split) * job.y_stride;
+          bulk_prefetch_l2(xn + job.x_hi, xb);
+          bulk_prefetch_l2(xn + job.x_lo, xb);
+          bulk_prefetch_l2(yn + job.y_hi, yb);
+          bulk_prefetch_l2(yn + job.y_lo, yb);
+        }
+      }
+      __syncwarp();
     }
-  } else if (warp == 5 && lane == 0) {
+  } else if (warp == 5) {  // MMA warp (converged; one elected lane issues)
     // MN-major operands: core matrix = 8 points (K) x 8 columns (16 B); K-direction stride 128 B,
     // MN-direction stride = one chunk (2048 B)
     const uint32_t idesc = make_idesc(128, job.n_cols, 1, 1);
     const uint32_t idesc1 = make_idesc(128, 16, 1, 1);
-    const uint32_t d = sm.tmem_base, d1 = sm.tmem_base + 256;
-    const uint32_t xh = smem_u32(sm.x_hi), xl = smem_u32(sm.x_lo), yh = smem_u32(sm.y_hi), yl = smem_u32(sm.y_lo);
-    const uint32_t on = smem_u32(sm.ones);
+    const uint32_t d = __shfl_sync(0xffffffffu, sm.tmem_base, 0), d1 = d + 256;
+    const uint64_t dxh0 = make_desc_k(smem_u32(sm.x_hi), 128, A_CHUNK_BYTES), dxl0 = make_desc_k(smem_u32(sm.x_lo), 128, A_CHUNK_BYTES);
+    const uint64_t dyh0 = make_desc_k(smem_u32(sm.y_hi), 128, A_CHUNK_BYTES), dyl0 = make_desc_k(smem_u32(sm.y_lo), 128, A_CHUNK_BYTES);
+    const uint64_t don0 = make_desc_k(smem_u32(sm.ones), 128, A_CHUNK_BYTES);
+    const bool has_bias = job.bias != nullptr;
     for (int t = 0; t < my_tiles; ++t) {
       mbar_wait(&sm.full, t & 1);
       tc_fence_after();
-      for (int ks = 0; ks < TILE_M / 16; ++ks) {
-        const uint32_t ko = ks * 256;  // 16 points = 2 core matrices of 128 B
-        const uint64_t dxh = make_desc_k(xh + ko, 128, A_CHUNK_BYTES), dxl = make_desc_k(xl + ko, 128, A_CHUNK_BYTES);
-        const uint64_t dyh = make_desc_k(yh + ko, 128, A_CHUNK_BYTES), dyl = make_desc_k(yl + ko, 128, A_CHUNK_BYTES);
-        const uint32_t acc = (t | ks) ? 1u : 0u;
-        umma_bf16(d, dxh, dyh, idesc, acc);
-        umma_bf16(d, dxh, dyl, idesc, 1u);
-        umma_bf16(d, dxl, dyh, idesc, 1u);
-        if (job.bias) {
-          const uint64_t don = make_desc_k(on + ko, 128, A_CHUNK_BYTES);
-          umma_bf16(d1, dxh, don, idesc1, acc);
-          umma_bf16(d1, dxl, don, idesc1, 1u);
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < TILE_M / 16; ++ks) {
+          const uint32_t ko = ks * 256;  // 16 points = 2 core matrices of 128 B
+          const uint64_t dxh = desc_advance(dxh0, ko), dxl = desc_advance(dxl0, ko);
+          const uint64_t dyh = desc_advance(dyh0, ko), dyl = desc_advance(dyl0, ko);
+          const uint32_t acc = (t | ks) ? 1u : 0u;
+          umma_bf16(d, dxh, dyh, idesc, acc);
+          umma_bf16(d, dxh, dyl, idesc, 1u);
+          umma_bf16(d, dxl, dyh, idesc, 1u);
+          if (has_bias) {
+            const uint64_t don = desc_advance(don0, ko);
+            umma_bf16(d1, dxh, don, idesc1, acc);
+            umma_bf16(d1, dxl, don, idesc1, 1u);
+          }
         }
+        umma_commit(&sm.empty);
       }
-      umma_commit(&sm.empty);
+      __syncwarp();
     }
-    umma_commit(&sm.d_ready);
+    if (elect_one()) umma_commit(&sm.d_ready);
+    __syncwarp();
   } else if (warp < 4) {
     if (my_tiles > 0) {
       mbar_wait(&sm.d_ready, 0);

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from . import _lib
+from . import _lib, junction
 from .autograd import NeatStepFunction, StepState
 from .context import Context
 from .render import Renderer
@@ -343,7 +343,6 @@ class VolSDFNetwork(nn.Module):
         # in the loss, loss_wfr.py:104-108) stay on the host as in the reference, but behind ONE device->host transfer:
         # everything they need (cluster centroids, their count, the global junctions) is fetched together, and the
         # loss' assignment is handed over in the output dict so that it need not synchronise again.
-        from scipy.optimize import linear_sum_assignment
         j2d_global = self.project2D(K3, Rm, T, glob)
         j2d_global_calib = self.project2D(I3, Rm, T, glob)
         import time as _time
@@ -352,41 +351,25 @@ class VolSDFNetwork(nn.Module):
         _t1 = _time.perf_counter()
         n_h, cent_h, glob_h, pose_h, K_h = st.junction_host
         C = int(n_h[0])
-        cent = cent_h[:C].astype(np.float32)
-        RT = np.linalg.inv(pose_h.reshape(4, 4).astype(np.float32))[:3].astype(np.float32)
-
-        def proj(Km, X):  # project2D on the host (float32, same guards)
-            x = (Km @ (RT[:, :3] @ X.T + RT[:, 3:])).T
-            den = x[:, 2:3]
-            sign = np.where(den >= 0, 1.0, -1.0).astype(np.float32)
-            eps = np.where(np.abs(den) < 1e-8, 1e-8, 0.0).astype(np.float32)
-            return (x / (den + eps * sign))[:, :2]
-
-        K3h, I3h = K_h[:3, :3].astype(np.float32), np.eye(3, dtype=np.float32)
-        gt = input["wireframe"][0].vertices.detach().cpu().numpy().astype(np.float32)
-        j2d = proj(K3h, cent) if C else np.zeros((0, 2), np.float32)
-        j2d_cal = proj(I3h, cent) if C else np.zeros((0, 2), np.float32)
-        jcost = np.sqrt(((j2d[None] - gt[:, None]) ** 2).sum(-1))
-        a0, a1 = linear_sum_assignment(jcost)
-        sel = jcost[a0, a1]
+        gt = input["wireframe"][0].vertices.detach().cpu().numpy()
+        # projections, both assignments and the < 10 px filter in native host code (csrc/junction.cpp)
+        local, b0, b1, n_close, med = junction.junction_match(cent_h[:C], gt, pose_h, K_h, glob_h, self.use_median)
         if self.use_median:
-            med = np.median(sel) if len(sel) else np.nan
-            if np.isnan(med):
-                med = 10.0
-            ok = sel < med
             out["median"] = torch.tensor(float(med), device=dev)
-        else:
-            ok = sel < 10
-        j3l, j2l, j2lc = cent[a1][ok], j2d[a1][ok], j2d_cal[a1][ok]
-        if len(j3l):
-            gcal = proj(I3h, glob_h.astype(np.float32))
-            cost = np.abs(j3l[:, None] - glob_h[None]).sum(-1) + 0.1 * np.abs(j2lc[:, None] - gcal[None]).sum(-1)
-            b0, b1 = linear_sum_assignment(cost)
-            out["_junction_assignment"] = (torch.as_tensor(b0, device=dev), torch.as_tensor(b1, device=dev),
-                                           int((cost[b0, b1] < 10).sum()))
+        n = local.shape[0]
+        # one pinned staging buffer, one host->device copy: [n,7] floats, then the n + n assignment indices
+        stage = rn.pinned("junction.stage", 9 * max(n, 1), torch.float32)
+        stage[:7 * n].copy_(torch.from_numpy(local.reshape(-1)))
+        idx = stage[7 * n:9 * n].view(torch.int32)
+        idx[:n].copy_(torch.from_numpy(b0.astype(np.int32)))
+        idx[n:].copy_(torch.from_numpy(b1.astype(np.int32)))
+        on_dev = stage[:9 * n].to(dev, non_blocking=True)
+        packed = on_dev[:7 * n].view(n, 7)
+        if n:
+            di = on_dev[7 * n:].view(torch.int32)
+            out["_junction_assignment"] = (di[:n], di[n:], int(n_close))
         self.last_host_ms = {"wait_for_gpu": (_t1 - _t0) * 1e3, "junction_host": (_time.perf_counter() - _t1) * 1e3,
-                             "clusters": C, "gt_junctions": int(gt.shape[0]), "matched": int(len(j3l))}
-        packed = torch.from_numpy(np.concatenate([j3l, j2l, j2lc], axis=1).astype(np.float32)).to(dev)
+                             "clusters": C, "gt_junctions": int(gt.shape[0]), "matched": int(n)}
         out.update(j2d_local=packed[:, 3:5], j3d_local=packed[:, 0:3], j3d_global=glob, j2d_global=j2d_global,
                    j2d_local_calib=packed[:, 5:7], j2d_global_calib=j2d_global_calib)
         return out

@@ -188,6 +188,20 @@ class Renderer:
                                        ctx._stream()))
         return cent, n
 
+    def side_stream(self):
+        """Second stream for the small launches that fit into the tail of a big persistent one."""
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(self.ctx.device)
+        return self._side
+
+    def pinned(self, name, numel, dtype=torch.float32):
+        """A named, persistent pinned host buffer (staging for small host->device hand-overs)."""
+        key = (name, dtype)
+        h = self._pinned.get(key)
+        if h is None or h.numel() < numel:
+            self._pinned[key] = h = torch.empty(max(int(numel), 1), dtype=dtype, pin_memory=True)
+        return h
+
     def to_host_async(self, tensors):
         """Enqueue copies of several small device tensors into pinned host buffers; returns (event, numpy views).
         The views are valid after event.synchronize() and until the next call."""
