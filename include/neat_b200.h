@@ -63,8 +63,10 @@ typedef struct {
   long w_off, b_off;      /* float offsets in the flat buffer (filled by the library) */
 } neat_wn_layer;
 int neat_weight_norm_forward(neat_ctx* ctx, const neat_wn_layer* layers, int n_layers, float* flat, void* stream);
+/* accumulate != 0: ADD into gg / gv / gb (a second backward before zero_grad, or gradient buffers that are
+ * views of a zeroed data-parallel bucket); 0: overwrite.                                              */
 int neat_weight_norm_backward(neat_ctx* ctx, const neat_wn_layer* layers, int n_layers, const float* flat_grad,
-                              void* stream);
+                              int accumulate, void* stream);
 
 /* Arithmetic of the layer GEMMs: 0 (default) = bf16x3, operands split hi + lo, three MMAs per k-step, fp32
  * accumulation (meets the 1e-4 parity bound); 1 = plain bf16 operands, one MMA per k-step (~1e-2 on the SDF;
@@ -202,6 +204,26 @@ int neat_junction_match(const float* centroids, int n_centroids, const float* gt
                         const float* pose, const float* intrinsics, const float* global_junctions, int n_global,
                         int use_median, float* local_out, int* n_local, int* global_rows, int* global_cols,
                         int* n_close, float* median_out);
+
+/* ---- junction terms on the device ------------------------------------------------------------------------
+ * neat_project_points: out_pix = project2D(K, R, T, X) and out_calib = project2D(I, R, T, X) of N points
+ * (the global junctions, neat_wfr_rend_a.py:484-486); pose_inv [16] = world-to-camera (neat_line_geometry's output),
+ * K: 3x3 with row stride k_ld.  Either output may be NULL.  _backward: g_X [N,3] = adjoint of both (either g NULL). */
+int neat_project_points(int N, const float* pose_inv, const float* K, int k_ld, const float* X, float* out_pix,
+                        float* out_calib, void* stream);
+int neat_project_points_backward(int N, const float* pose_inv, const float* K, int k_ld, const float* X,
+                                 const float* g_pix, const float* g_calib, float* g_X, void* stream);
+/* neat_junction_terms (loss_wfr.py:110-121): for the n matched pairs (rows[i] -> local junction, cols[i] -> global
+ * junction): out[0] = mean L1 3D distance (j3d_loss), out[1] = mean L1 calibrated 2D distance (j2d_loss), out[2] = the
+ * same in pixels (statistics).  _backward: g_out [2] (device) -> gradients w.r.t. the GLOBAL junctions [n_global,3] /
+ * their calibrated projections [n_global,2] (zero for unmatched rows).                                        */
+int neat_junction_terms(int n, const float* j3d_local, const float* j3d_global, const float* j2d_local_calib,
+                        const float* j2d_global_calib, const float* j2d_local, const float* j2d_global, const int* rows,
+                        const int* cols, float* out, void* stream);
+int neat_junction_terms_backward(int n, int n_global, const float* j3d_local, const float* j3d_global,
+                                 const float* j2d_local_calib, const float* j2d_global_calib, const int* rows,
+                                 const int* cols, const float* g_out, float* g_j3d_global, float* g_j2d_global_calib,
+                                 void* stream);
 
 /* ---- VolSDFLoss (code/model/networks/loss_wfr.py:34-79), forward fused with its own backward ---- */
 /* loss_core = rgb L1 + eikonal_weight * eikonal + line_weight * calibrated line loss.  out[8] = {loss_core, rgb_loss,

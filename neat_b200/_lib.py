@@ -30,7 +30,7 @@ SIGNATURES = {
     "neat_param_offset": (ctypes.c_long, [_P, _I, _I, _I]),
     "neat_layer_dims": (_I, [_P, _I, _I, ctypes.POINTER(_I), ctypes.POINTER(_I)]),
     "neat_weight_norm_forward": (_I, [_P, _P, _I, _P, _P]),
-    "neat_weight_norm_backward": (_I, [_P, _P, _I, _P, _P]),
+    "neat_weight_norm_backward": (_I, [_P, _P, _I, _P, _I, _P]),
     "neat_set_precision": (_I, [_P, _I]),
     "neat_pack_weights": (_I, [_P, _P, _P]),
     "neat_sdf_points": (_I, [_P, _P, _I, _P, _P]),
@@ -50,6 +50,10 @@ SIGNATURES = {
     "neat_point_line_attraction": (_I, [_P, _I, _I, _I, ctypes.c_float, _P, _P, _P, _P]),
     "neat_linear_sum_assignment": (_I, [_P, _I, _I, _P, _P]),
     "neat_junction_match": (_I, [_P, _I, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "neat_project_points": (_I, [_I, _P, _P, _I, _P, _P, _P, _P]),
+    "neat_project_points_backward": (_I, [_I, _P, _P, _I, _P, _P, _P, _P, _P]),
+    "neat_junction_terms": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "neat_junction_terms_backward": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "neat_loss_forward_backward": (_I, [_P, _P]),
     "neat_project_calib_backward": (_I, [_I, _P, _P, _P, _P, _P]),
     "neat_dbscan_workspace_bytes": (ctypes.c_size_t, [_I]),

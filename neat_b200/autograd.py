@@ -30,19 +30,14 @@ class StepState:
 
 class NeatStepFunction(torch.autograd.Function):
     @staticmethod
-    def forward(fctx, beta_param, renderer, st, *params):
+    def forward(fctx, beta_param, renderer, st):
+        """The MLP parameters are NOT autograd inputs: st.param_layers = [(weight_g | None, weight_v | weight, bias)]
+        holds the nn.Parameters, and backward() writes (or adds to) their .grad itself in ONE kernel launch, instead of
+        handing 57 tensors to 57 AccumulateGrad nodes (one elementwise launch each).  density.beta is the graph anchor."""
         ctx = renderer.ctx
         lib = ctx.lib
         dev = ctx.device
-        # params: (weight_g, weight_v, bias) or (weight, bias) per layer, flattened; st.wn_has_g tells which
-        layers, i = [], 0
-        for has_g in st.wn_has_g:
-            if has_g:
-                layers.append((params[i].detach(), params[i + 1].detach(), params[i + 2].detach()))
-                i += 3
-            else:
-                layers.append((None, params[i].detach(), params[i + 1].detach()))
-                i += 2
+        layers = [tuple(None if t is None else t.detach() for t in lay) for lay in st.param_layers]
         st.wn_layers = layers
         renderer.effective_weights(layers)
         beta = beta_param.detach().reshape(1).contiguous()
@@ -155,10 +150,24 @@ class NeatStepFunction(torch.autograd.Function):
         with renderer.timed("wgrad"):
             _lib.check(lib.neat_weight_gradients(ctx._h, groups, 2, _ptr(flat_grad), stream))
         st.debug = dict(rgb_pre_bar=rgb_pre_bar, lines_bar=lines_bar, sdf_bar=sdf_bar, n_bar=n_bar, feat_bar=feat_bar)
-        grads = renderer.weight_norm_backward(st.wn_layers, flat_grad)
-        flat_out = []
-        for (gg, gv, gb) in grads:
-            if gg is not None:
-                flat_out.append(gg)
-            flat_out += [gv, gb]
-        return (beta_bar.reshape(fctx.beta_shape), None, None) + tuple(flat_out)
+        # parameter gradients: straight into p.grad (allocated here if the caller cleared it, added to otherwise)
+        with torch.no_grad():
+            have = [p.grad is not None for lay in st.param_layers for p in lay if p is not None and p.requires_grad]
+            accumulate = bool(have) and all(have)
+            targets = []
+            for lay in st.param_layers:
+                tg = []
+                for p in lay:
+                    if p is None:
+                        tg.append(None)
+                    elif not p.requires_grad:
+                        tg.append(torch.empty_like(p))  # frozen parameter: computed and dropped
+                    else:
+                        if p.grad is None:
+                            p.grad = torch.zeros_like(p) if (have and any(have)) else torch.empty_like(p)
+                        elif not (p.grad.is_contiguous() and p.grad.dtype == torch.float32):
+                            raise _lib.NeatError("parameter gradients must be contiguous fp32 tensors")
+                        tg.append(p.grad)
+                targets.append(tuple(tg))
+            renderer.weight_norm_backward(st.wn_layers, flat_grad, targets, accumulate or (bool(have) and any(have)))
+        return beta_bar.reshape(fctx.beta_shape), None, None

@@ -136,6 +136,15 @@ class ErrorBoundSampler:
         self._ws = None
         self._ws_R = -1
 
+    def _perm_mask(self):
+        """[max_iters, n_eval * max_iters]: 0 where column < n_eval * (row + 1), +inf elsewhere."""
+        if getattr(self, "_mask", None) is None:
+            c = self.cfg
+            col = torch.arange(c.n_eval * c.max_iters, device=self.ctx.device)[None, :]
+            lim = (torch.arange(1, c.max_iters + 1, device=self.ctx.device) * c.n_eval)[:, None]
+            self._mask = torch.where(col < lim, 0.0, float("inf")).float()
+        return self._mask
+
     def workspace(self, R):
         if self._ws_R < R:  # persistent: re-allocated only when the ray count grows
             n = int(self.ctx.lib.neat_sampler_workspace_bytes(R))
@@ -183,8 +192,10 @@ class ErrorBoundSampler:
         if device_rng:
             # same distribution as the reference's randperm(128 k)[:n_extra] for whichever k the sampler stops at;
             # all rows are drawn up front so that no device->host read of k is needed
-            table = torch.stack([torch.randperm(c.n_eval * k, device=dev)[:max(c.n_extra, 1)]
-                                 for k in range(1, c.max_iters + 1)]).contiguous()
+            # (the first n_extra entries of a uniform random permutation of [0, L) = the positions of the n_extra
+            # smallest of L i.i.d. uniform keys: one rand + one top-k for all candidate L instead of 5 randperms)
+            keys = torch.rand(c.max_iters, c.n_eval * c.max_iters, device=dev) + self._perm_mask()
+            table = keys.topk(max(c.n_extra, 1), dim=1, largest=False, sorted=False).indices.contiguous()
             eik = torch.randint(0, self.n_out, (R,), device=dev)
         elif training:
             k = int(n_it.item())

@@ -20,6 +20,7 @@
 #include "sdf_render.cuh"
 #include "weight_norm.cuh"
 #include "wgrad.cuh"
+#include "junction.cuh"
 
 using namespace neat;
 
@@ -271,14 +272,15 @@ int neat_weight_norm_forward(neat_ctx* c, const neat_wn_layer* layers, int n_lay
   return NEAT_OK;
 }
 
-int neat_weight_norm_backward(neat_ctx* c, const neat_wn_layer* layers, int n_layers, const float* flat_grad, void* stream) {
+int neat_weight_norm_backward(neat_ctx* c, const neat_wn_layer* layers, int n_layers, const float* flat_grad, int accumulate,
+                              void* stream) {
   if (!c || !flat_grad) return fail(NEAT_EINVAL, "null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (int e = upload_wn_table(c, layers, n_layers, st)) return e;
   for (int i = 0; i < n_layers; ++i)
     if (!layers[i].gv || !layers[i].gb || (layers[i].g && !layers[i].gg)) return fail(NEAT_EINVAL, "weight_norm: null gradient pointer");
   const int rows = c->wn_host.row_start[c->wn_host.n];
-  weight_norm_bwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(c->wn_dev, flat_grad);
+  weight_norm_bwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(c->wn_dev, flat_grad, accumulate);
   ++g_launches;
   CK(cudaGetLastError());
   return NEAT_OK;
@@ -623,6 +625,59 @@ int neat_project_calib_backward(int R, const float* pose_inv, const float* lines
   if (R <= 0 || !pose_inv || !lines3d || !g_calib || !g_lines3d) return fail(NEAT_EINVAL, "bad argument");
   project_calib_bwd_kernel<<<(R + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(R, pose_inv, lines3d, g_calib,
                                                                                          g_lines3d);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+int neat_project_points(int N, const float* pose_inv, const float* K, int k_ld, const float* X, float* out_pix,
+                        float* out_calib, void* stream) {
+  if (N < 0 || !pose_inv || !X || (out_pix && !K)) return fail(NEAT_EINVAL, "bad argument");
+  if (N == 0) return NEAT_OK;
+  project_points_kernel<<<(N + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(N, pose_inv, K, k_ld, X, out_pix,
+                                                                                      out_calib);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+int neat_project_points_backward(int N, const float* pose_inv, const float* K, int k_ld, const float* X,
+                                 const float* g_pix, const float* g_calib, float* g_X, void* stream) {
+  if (N < 0 || !pose_inv || !X || !g_X || (g_pix && !K)) return fail(NEAT_EINVAL, "bad argument");
+  if (N == 0) return NEAT_OK;
+  project_points_bwd_kernel<<<(N + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(N, pose_inv, K, k_ld, X, g_pix,
+                                                                                          g_calib, g_X);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+int neat_junction_terms(int n, const float* j3d_local, const float* j3d_global, const float* j2d_local_calib,
+                        const float* j2d_global_calib, const float* j2d_local, const float* j2d_global, const int* rows,
+                        const int* cols, float* out, void* stream) {
+  if (n <= 0 || !j3d_local || !j3d_global || !j2d_local_calib || !j2d_global_calib || !j2d_local || !j2d_global || !rows ||
+      !cols || !out)
+    return fail(NEAT_EINVAL, "bad argument");
+  junction_terms_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(n, j3d_local, j3d_global, j2d_local_calib,
+                                                                        j2d_global_calib, j2d_local, j2d_global, rows, cols,
+                                                                        out);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+int neat_junction_terms_backward(int n, int n_global, const float* j3d_local, const float* j3d_global,
+                                 const float* j2d_local_calib, const float* j2d_global_calib, const int* rows,
+                                 const int* cols, const float* g_out, float* g_j3d_global, float* g_j2d_global_calib,
+                                 void* stream) {
+  if (n <= 0 || n_global <= 0 || !j3d_local || !j3d_global || !j2d_local_calib || !j2d_global_calib || !rows || !cols ||
+      !g_out || !g_j3d_global || !g_j2d_global_calib)
+    return fail(NEAT_EINVAL, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CK(cudaMemsetAsync(g_j3d_global, 0, sizeof(float) * 3 * n_global, st));
+  CK(cudaMemsetAsync(g_j2d_global_calib, 0, sizeof(float) * 2 * n_global, st));
+  junction_terms_bwd_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, j3d_local, j3d_global, j2d_local_calib, j2d_global_calib,
+                                                             rows, cols, g_out, g_j3d_global, g_j2d_global_calib);
   ++g_launches;
   CK(cudaGetLastError());
   return NEAT_OK;

@@ -44,7 +44,8 @@ __global__ void __launch_bounds__(256) weight_norm_fwd_kernel(const WnTable* __r
   if (lane == 0) flat[L.b_off + r] = L.b[r];
 }
 
-__global__ void __launch_bounds__(256) weight_norm_bwd_kernel(const WnTable* __restrict__ tp, const float* __restrict__ flat_grad) {
+__global__ void __launch_bounds__(256) weight_norm_bwd_kernel(const WnTable* __restrict__ tp, const float* __restrict__ flat_grad,
+                                                              int accumulate) {
   const WnTable& t = *tp;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -64,12 +65,12 @@ __global__ void __launch_bounds__(256) weight_norm_bwd_kernel(const WnTable* __r
     const float inv = rsqrtf(ss);
     const float gi = L.g[r] * inv;
     const float c = dot / ss;
-    for (int k = lane; k < L.cols; k += 32) gv[k] = gi * (wb[k] - c * v[k]);
-    if (lane == 0) L.gg[r] = dot * inv;
+    for (int k = lane; k < L.cols; k += 32) gv[k] = (accumulate ? gv[k] : 0.f) + gi * (wb[k] - c * v[k]);
+    if (lane == 0) L.gg[r] = (accumulate ? L.gg[r] : 0.f) + dot * inv;
   } else {
-    for (int k = lane; k < L.cols; k += 32) gv[k] = wb[k];
+    for (int k = lane; k < L.cols; k += 32) gv[k] = (accumulate ? gv[k] : 0.f) + wb[k];
   }
-  if (lane == 0) L.gb[r] = flat_grad[L.b_off + r];
+  if (lane == 0) L.gb[r] = (accumulate ? L.gb[r] : 0.f) + flat_grad[L.b_off + r];
 }
 
 }  // namespace neat

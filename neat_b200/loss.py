@@ -61,6 +61,41 @@ def _get_class(path):
     return getattr(importlib.import_module(mod), name)
 
 
+class _JunctionTerms(torch.autograd.Function):
+    """The Hungarian-matched junction terms (loss_wfr.py:110-121) as one kernel each way (csrc/junction.cuh):
+    returns out[3] = (j3d_loss, j2d_loss, j2d_stat); gradients flow to the GLOBAL junctions and their calibrated
+    projections only (the local junctions are detached DBSCAN centroids, in the reference too)."""
+
+    @staticmethod
+    def forward(ctx, j3g, j2gc, j3l, j2lc, j2l, j2g, rows, cols):
+        lib = _lib.load()
+        dev = j3g.device
+        f = lambda t: t.detach().to(dev, torch.float32).contiguous()
+        j3g_, j2gc_, j3l, j2lc, j2l, j2g = f(j3g), f(j2gc), f(j3l), f(j2lc), f(j2l), f(j2g)
+        rows = rows.to(dev, torch.int32).contiguous()
+        cols = cols.to(dev, torch.int32).contiguous()
+        n = rows.shape[0]
+        out = torch.empty(3, device=dev)
+        _lib.check(lib.neat_junction_terms(n, _ptr(j3l), _ptr(j3g_), _ptr(j2lc), _ptr(j2gc_), _ptr(j2l), _ptr(j2g),
+                                           _ptr(rows), _ptr(cols), _ptr(out), _P(torch.cuda.current_stream(dev).cuda_stream)))
+        ctx.save_for_backward(j3l, j3g_, j2lc, j2gc_, rows, cols)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        j3l, j3g, j2lc, j2gc, rows, cols = ctx.saved_tensors
+        lib = _lib.load()
+        dev = j3g.device
+        G = j3g.shape[0]
+        g3 = torch.empty(G, 3, device=dev)
+        g2 = torch.empty(G, 2, device=dev)
+        g_out = g_out.to(dev, torch.float32).contiguous()
+        _lib.check(lib.neat_junction_terms_backward(rows.shape[0], G, _ptr(j3l), _ptr(j3g), _ptr(j2lc), _ptr(j2gc),
+                                                    _ptr(rows), _ptr(cols), _ptr(g_out), _ptr(g3), _ptr(g2),
+                                                    _P(torch.cuda.current_stream(dev).cuda_stream)))
+        return g3, g2, None, None, None, None, None, None
+
+
 class VolSDFLoss(nn.Module):
     def __init__(self, rgb_loss, eikonal_weight, line_weight, junction_3d_weight=0.1, junction_2d_weight=0.01):
         super().__init__()
@@ -156,10 +191,8 @@ class VolSDFLoss(nn.Module):
                 a0 = torch.as_tensor(a0, device=dev)
                 a1 = torch.as_tensor(a1, device=dev)
                 jcount = (cost[a0, a1] < 10).sum()
-            l3 = (j3l[a0] - j3g[a1]).abs().sum(-1).mean()
-            l2 = (j2lc[a0] - j2gc[a1]).abs().sum(-1).mean()
-            with torch.no_grad():
-                l2u = (j2l[a0] - j2g[a1]).abs().sum(-1).mean()
+            terms = _JunctionTerms.apply(j3g, j2gc, j3l, j2lc, j2l, j2g, a0, a1)
+            l3, l2, l2u = terms[0], terms[1], terms[2].detach()
             loss = loss + self.junction_3d_weight * l3 + self.junction_2d_weight * l2
             out.update(j3d_loss=l3, j2d_loss=l2, j2d_stat=l2u, jcount=jcount)
         out["loss"] = loss

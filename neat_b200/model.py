@@ -52,6 +52,43 @@ class _ProjectCalib(torch.autograd.Function):
         return out, None, None
 
 
+class _ProjectPoints(torch.autograd.Function):
+    """(project2D(K, R, T, X), project2D(I, R, T, X)) of the global junctions (neat_wfr_rend_a.py:484-486) as ONE kernel
+    each way (csrc/junction.cuh) instead of two chains of ~17 eager ops.  pose_inv: world-to-camera [16] from the
+    geometry kernel of the step; K4: the [4,4] intrinsics."""
+
+    @staticmethod
+    def forward(ctx, X, pose_inv, K4):
+        import ctypes
+        lib = _lib.load()
+        Xc = X.detach().float().contiguous()
+        N = Xc.shape[0]
+        pix = torch.empty(N, 2, device=Xc.device)
+        cal = torch.empty(N, 2, device=Xc.device)
+        P = ctypes.c_void_p
+        _lib.check(lib.neat_project_points(N, P(pose_inv.data_ptr()), P(K4.data_ptr()), 4, P(Xc.data_ptr()),
+                                           P(pix.data_ptr()), P(cal.data_ptr()),
+                                           P(torch.cuda.current_stream(Xc.device).cuda_stream)))
+        ctx.save_for_backward(Xc, pose_inv, K4)
+        return pix, cal
+
+    @staticmethod
+    def backward(ctx, g_pix, g_cal):
+        import ctypes
+        Xc, pose_inv, K4 = ctx.saved_tensors
+        lib = _lib.load()
+        P = ctypes.c_void_p
+        N = Xc.shape[0]
+        gX = torch.empty(N, 3, device=Xc.device)
+        gp = None if g_pix is None else g_pix.float().contiguous()
+        gc = None if g_cal is None else g_cal.float().contiguous()
+        _lib.check(lib.neat_project_points_backward(N, P(pose_inv.data_ptr()), P(K4.data_ptr()), 4, P(Xc.data_ptr()),
+                                                    None if gp is None else P(gp.data_ptr()),
+                                                    None if gc is None else P(gc.data_ptr()), P(gX.data_ptr()),
+                                                    P(torch.cuda.current_stream(Xc.device).cuda_stream)))
+        return gX, None, None
+
+
 class _WeightNormMLP(nn.Module):
     """lin0..lin{n-1} with nn.utils.weight_norm, parameters only: the math runs in the kernels."""
 
@@ -321,18 +358,16 @@ class VolSDFNetwork(nn.Module):
         # single device->host transfer
         glob = self.ffn(self.latents)
         st.junction_inputs = (glob.detach(), pose, K4)
-        layers = self._wn_layers()
-        st.wn_has_g = [g is not None for g, _, _ in layers]
-        params = [t for lay in layers for t in lay if t is not None]
+        st.param_layers = self._wn_layers()
         self._packed_version = None  # the step packs its own copy
         # the eikonal draw follows the junction block in the reference's RNG order; it is made lazily inside the
         # step when not replayed, so do the (host-side) junction block on the detached outputs afterwards.
-        rgb_values, lines3d, grad_theta = NeatStepFunction.apply(self.density.beta, rn, st, *params)
+        anchor = self.density.beta
+        if not anchor.requires_grad:  # the step hangs off one differentiable input; see NeatStepFunction.forward
+            anchor = anchor.detach().requires_grad_(True)
+        rgb_values, lines3d, grad_theta = NeatStepFunction.apply(anchor, rn, st)
         self.last_step = st
-        pinv = st.pose_inv[:3]
-        Rm, T = pinv[:, :3], pinv[:, 3:]
         K3 = K4[:3, :3]
-        I3 = torch.eye(3, device=dev)
         out.update(points=st.cam[None, None, :] + st.z[:, :, None] * st.dirs[:, None, :], rgb_values=rgb_values,
                    depth=st.depth, xyz=st.points3d, points3d=st.points3d, lines3d=lines3d, l3d=st.l3d,
                    lines2d=st.lines2d, lines2d_calib=_ProjectCalib.apply(lines3d, st.lines2d_calib, st.pose_inv.reshape(-1)),
@@ -343,8 +378,7 @@ class VolSDFNetwork(nn.Module):
         # in the loss, loss_wfr.py:104-108) stay on the host as in the reference, but behind ONE device->host transfer:
         # everything they need (cluster centroids, their count, the global junctions) is fetched together, and the
         # loss' assignment is handed over in the output dict so that it need not synchronise again.
-        j2d_global = self.project2D(K3, Rm, T, glob)
-        j2d_global_calib = self.project2D(I3, Rm, T, glob)
+        j2d_global, j2d_global_calib = _ProjectPoints.apply(glob, st.pose_inv.reshape(-1).contiguous(), K4)
         import time as _time
         _t0 = _time.perf_counter()
         st.junction_event.synchronize()

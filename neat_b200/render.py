@@ -98,12 +98,13 @@ class Renderer:
         ctx.pack_weights(flat)
         return flat
 
-    def weight_norm_backward(self, layers, flat_grad):
+    def weight_norm_backward(self, layers, flat_grad, targets, accumulate):
+        """Adjoint of effective_weights: flat_grad (layout of the flat parameter buffer) -> the (weight_g, weight_v,
+        bias) gradients, written (accumulate=False) or added (True) straight into `targets` (same structure)."""
         ctx = self.ctx
-        grads = [(None if g is None else torch.empty_like(g), torch.empty_like(v), torch.empty_like(b)) for g, v, b in layers]
-        arr = self._wn_table(layers, grads)
-        _lib.check(ctx.lib.neat_weight_norm_backward(ctx._h, arr, len(layers), _ptr(flat_grad), ctx._stream()))
-        return grads
+        arr = self._wn_table(layers, targets)
+        _lib.check(ctx.lib.neat_weight_norm_backward(ctx._h, arr, len(layers), _ptr(flat_grad), int(bool(accumulate)),
+                                                     ctx._stream()))
 
     # ---- small helpers over the C entry points ------------------------------------------------
     def camera_rays(self, uv, pose, K):
