@@ -1,6 +1,7 @@
 // C ABI of neat_b200 (include/neat_b200.h): context, weight packing, kernel launches.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -79,6 +80,7 @@ struct neat_ctx {
   Program prog_query, prog_render, prog_head[2], prog_head_bwd[2], prog_sdf_bwd;
   uint8_t* ones_tile = nullptr;  // X operand with column 0 = 1 (aux-plane sized, hi then lo)
   WJob* jobs_dev = nullptr;
+  std::vector<WJob> jobs_last;  // what jobs_dev holds
   int jobs_cap = 0;
   WnTable* wn_dev = nullptr;
   WnTable wn_host{};
@@ -827,8 +829,10 @@ inline int c8(int x) { return (x + 7) / 8 * 8; }
 // dW[row0 + i][col0 + j] += scale * sum_pt X[pt][i] Y[pt][j],  i < x_valid, j < y_valid ; optional bias
 void add_gemm(std::vector<WJob>& jobs, const Planes& X, int x_valid, const Planes& Y, int y_valid, float* out, int ld,
               int row0, int col0, float scale, float* bias, int n_tiles, int n_split) {
-  for (int m0 = 0; m0 < x_valid; m0 += 128) {
-    for (int sp = 0; sp < n_split; ++sp) {
+  // the two 128-row halves of one (GEMM, split) read the SAME Y tiles: adjacent block indices run at the same time
+  // on different SMs, so the second reader hits the L2 instead of HBM
+  for (int sp = 0; sp < n_split; ++sp) {
+    for (int m0 = 0; m0 < x_valid; m0 += 128) {
       WJob j{};
       j.x_base = X.base; j.x_stride = X.stride; j.x_hi = X.hi; j.x_lo = X.lo;
       j.y_base = Y.base; j.y_stride = Y.stride; j.y_hi = Y.hi; j.y_lo = Y.lo;
@@ -932,6 +936,39 @@ int neat_weight_gradients(neat_ctx* c, const neat_grad_group* groups, int n_grou
     }
   }
   if (jobs.empty()) return NEAT_OK;
+  {
+    // longest-processing-time-first: CTAs are handed to SMs in block order, so the expensive (job pairs) go first and
+    // the cheap ones fill the tail.  A pair = the 128-row halves of one (GEMM, split); it stays adjacent (shared Y tiles).
+    auto cost = [](const WJob& j) {
+      const long tiles = j.n_tiles > j.split ? (j.n_tiles - j.split + j.n_split - 1) / j.n_split : 0;
+      return tiles * (j.x_cols + j.n_cols);
+    };
+    auto same_group = [](const WJob& a, const WJob& b) {
+      return a.x_base == b.x_base && a.x_hi == b.x_hi && a.y_base == b.y_base && a.y_hi == b.y_hi && a.split == b.split &&
+             a.out == b.out && a.col0 == b.col0 && a.bias == b.bias;
+    };
+    std::vector<int> gid(jobs.size());
+    std::vector<long> gcost;
+    for (size_t i = 0; i < jobs.size(); ++i) {
+      if (i > 0 && same_group(jobs[i - 1], jobs[i])) {
+        gid[i] = gid[i - 1];
+        gcost[gid[i]] += cost(jobs[i]);
+      } else {
+        gid[i] = static_cast<int>(gcost.size());
+        gcost.push_back(cost(jobs[i]));
+      }
+    }
+    std::vector<int> order(jobs.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = static_cast<int>(i);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      if (gid[a] == gid[b]) return a < b;
+      if (gcost[gid[a]] != gcost[gid[b]]) return gcost[gid[a]] > gcost[gid[b]];
+      return gid[a] < gid[b];
+    });
+    std::vector<WJob> sorted(jobs.size());
+    for (size_t i = 0; i < order.size(); ++i) sorted[i] = jobs[order[i]];
+    jobs.swap(sorted);
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (static_cast<int>(jobs.size()) > c->jobs_cap) {
     CK(cudaStreamSynchronize(st));
@@ -939,7 +976,14 @@ int neat_weight_gradients(neat_ctx* c, const neat_grad_group* groups, int n_grou
     c->jobs_cap = static_cast<int>(jobs.size()) * 2;
     CK(cudaMalloc(&c->jobs_dev, sizeof(WJob) * c->jobs_cap));
   }
-  CK(cudaMemcpyAsync(c->jobs_dev, jobs.data(), sizeof(WJob) * jobs.size(), cudaMemcpyHostToDevice, st));
+  // the job table only depends on buffer addresses and sizes, which are the same every step (persistent workspaces):
+  // upload it when it changed, not every step (a > 64 KB copy from pageable memory blocks the host on the stream)
+  if (c->jobs_last.size() != jobs.size() ||
+      std::memcmp(c->jobs_last.data(), jobs.data(), sizeof(WJob) * jobs.size()) != 0) {
+    CK(cudaStreamSynchronize(st));  // a launch still reading the previous table must have finished
+    CK(cudaMemcpyAsync(c->jobs_dev, jobs.data(), sizeof(WJob) * jobs.size(), cudaMemcpyHostToDevice, st));
+    c->jobs_last = jobs;
+  }
   wgrad_kernel<<<static_cast<int>(jobs.size()), WG_THREADS, sizeof(WgradSmem) + 1024, st>>>(c->jobs_dev);
   ++g_launches;
   CK(cudaGetLastError());

@@ -5,5 +5,4 @@ timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
 tail -15 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py --steps 20 --no-cpu-baseline > gpurun_out/bench_1024.json 2>> gpurun_out/bench.err
 timeout 600 python bench.py --steps 20 --rays 8192 --no-cpu-baseline > gpurun_out/bench_8192.json 2>> gpurun_out/bench.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python scripts/profile_step.py 1024 4 > gpurun_out/ncu_list.log 2>&1
 tail -3 gpurun_out/bench.err

@@ -288,3 +288,91 @@ def test_train_step_device_rng_and_optimizer():
     assert bool(torch.isfinite(ts.bucket.flat).all())
     n = sum(p.numel() for p in ts.model.parameters())
     assert ts.bucket.flat.numel() == n
+
+
+def _project2d_ref(Km, pose_inv, X):
+    """The oracle's restatement of VolSDFNetwork.project2D (neat_wfr_rend_a.py:317-331); autograd gives the adjoint."""
+    from oracle import neat_oracle as O
+    return O.project2d(Km, pose_inv[:3, :3], pose_inv[:3, 3:], X)
+
+
+@pytest.mark.parametrize("N", [1, 200, 1024])
+def test_project_points_and_adjoint_vs_torch(N):
+    """neat_project_points / _backward (the global junctions' projections) against project2D + autograd."""
+    from neat_b200.model import _ProjectPoints
+    b = synth.make_batch(8, seed=5)
+    K4 = T(b["intrinsics"][0]).cuda().contiguous()
+    pose_inv = torch.linalg.inv(T(b["pose"][0]).double()).float().cuda().contiguous()
+    g = torch.Generator().manual_seed(N)
+    X = (torch.rand(N, 3, generator=g) * 2 - 1).cuda().requires_grad_(True)
+    pix, cal = _ProjectPoints.apply(X, pose_inv.reshape(-1), K4)
+    Xr = X.detach().clone().requires_grad_(True)
+    pix_r, cal_r = _project2d_ref(K4[:3, :3], pose_inv, Xr), _project2d_ref(torch.eye(3, device="cuda"), pose_inv, Xr)
+    assert G.rel_err(pix.detach().cpu(), pix_r.detach().cpu()) < 1e-5
+    assert G.rel_err(cal.detach().cpu(), cal_r.detach().cpu()) < 1e-5
+    wp, wc = torch.randn(N, 2, generator=g).cuda(), torch.randn(N, 2, generator=g).cuda()
+    ((pix * wp).sum() + (cal * wc).sum()).backward()
+    ((pix_r * wp).sum() + (cal_r * wc).sum()).backward()
+    assert G.rel_err(X.grad.cpu(), Xr.grad.cpu()) < 1e-4
+    # only one of the two outputs used (the loss detaches the pixel projection)
+    X2 = X.detach().clone().requires_grad_(True)
+    _, cal2 = _ProjectPoints.apply(X2, pose_inv.reshape(-1), K4)
+    (cal2 * wc).sum().backward()
+    Xr2 = X.detach().clone().requires_grad_(True)
+    (_project2d_ref(torch.eye(3, device="cuda"), pose_inv, Xr2) * wc).sum().backward()
+    assert G.rel_err(X2.grad.cpu(), Xr2.grad.cpu()) < 1e-4
+
+
+@pytest.mark.parametrize("n,Gn", [(1, 16), (37, 1024), (200, 1024)])
+def test_junction_terms_vs_torch(n, Gn):
+    """neat_junction_terms / _backward against the reference expressions (loss_wfr.py:110-121) + autograd."""
+    from neat_b200.loss import _JunctionTerms
+    g = torch.Generator().manual_seed(n)
+    r = lambda *s: torch.randn(*s, generator=g).cuda()
+    j3l, j2lc, j2l = r(n, 3), r(n, 2), r(n, 2) * 100
+    j3g, j2gc, j2g = r(Gn, 3).requires_grad_(True), r(Gn, 2).requires_grad_(True), r(Gn, 2) * 100
+    rows = torch.arange(n, device="cuda", dtype=torch.int32)
+    cols = torch.randperm(Gn, generator=g)[:n].to("cuda", torch.int32)
+    out = _JunctionTerms.apply(j3g, j2gc, j3l, j2lc, j2l, j2g, rows, cols)
+    a3, a2 = j3g.detach().clone().requires_grad_(True), j2gc.detach().clone().requires_grad_(True)
+    ri, ci = rows.long(), cols.long()
+    l3 = (j3l[ri] - a3[ci]).abs().sum(-1).mean()
+    l2 = (j2lc[ri] - a2[ci]).abs().sum(-1).mean()
+    l2u = (j2l[ri] - j2g[ci]).abs().sum(-1).mean()
+    for got, ref in zip(out.tolist(), (l3.item(), l2.item(), l2u.item())):
+        assert abs(got - ref) <= 1e-5 * max(1.0, abs(ref))
+    (0.1 * out[0] + 0.01 * out[1]).backward()
+    (0.1 * l3 + 0.01 * l2).backward()
+    assert torch.allclose(j3g.grad, a3.grad, rtol=1e-5, atol=1e-8)
+    assert torch.allclose(j2gc.grad, a2.grad, rtol=1e-5, atol=1e-8)
+
+
+def test_parameter_gradients_accumulate_and_overwrite():
+    """The step writes parameter gradients itself (one kernel): overwrite when .grad is None, add when it exists
+    (second backward before zero_grad, or views of a zeroed data-parallel bucket)."""
+    from neat_b200 import trainer as TR
+    ts = TR.TrainStep(synth.dtu_conf(), device="cuda:0", seed=3, rng="device")
+    inp, gt = TR.to_device(TR.host_batch(128, seed=2), torch.device("cuda:0"))
+    model, loss_fn = ts.model, ts.loss_fn
+    names = ["implicit_network.lin3.weight_v", "rendering_network.lin0.weight_g", "rendering_network.lin4.bias"]
+    params = dict(model.named_parameters())
+    for p in model.parameters():
+        p.grad = None
+    torch.manual_seed(0)
+    loss_fn(model(inp), gt)["loss"].backward()
+    g1 = {k: params[k].grad.clone() for k in names}
+    assert all(float(v.abs().sum()) > 0 for v in g1.values())
+    torch.manual_seed(0)  # same device-RNG draws -> same gradient, added on top
+    loss_fn(model(inp), gt)["loss"].backward()
+    for k in names:
+        assert G.rel_err(params[k].grad.cpu(), (2 * g1[k]).cpu()) < 1e-5, k
+    # a frozen parameter is left alone
+    params[names[0]].requires_grad_(False)
+    params[names[0]].grad = None
+    for p in model.parameters():
+        if p.requires_grad:
+            p.grad = None
+    torch.manual_seed(0)
+    loss_fn(model(inp), gt)["loss"].backward()
+    assert params[names[0]].grad is None
+    assert G.rel_err(params[names[1]].grad.cpu(), g1[names[1]].cpu()) < 1e-5
