@@ -153,18 +153,18 @@ typedef struct {
   int R, S;
   const float* z;          /* [R,S]   */
   const float* sdf;        /* [R,S]   */
-  const float* rgb;        /* [R,S,3] */
-  const float* lines;      /* [R,S,6] */
+  const float* rgb;        /* [R,S,3] or NULL: rgb_values is not computed  (the step composites the attraction  */
+  const float* lines;      /* [R,S,6] or NULL: lines3d is not computed      head first, the colours later)     */
   const float* normals;    /* [R,S,3] or NULL (no normal map) */
   const float* rays_o;     /* [3]     */
   const float* rays_d;     /* [R,3]   */
   const float* beta_param; /* density.beta */
   float beta_min;
-  float* weights;          /* [R,S]   */
+  float* weights;          /* [R,S]   or NULL */
   float* rgb_values;       /* [R,3]   */
   float* lines3d;          /* [R,6]   */
-  float* depth;            /* [R]     */
-  float* points3d;         /* [R,3]   */
+  float* depth;            /* [R]     or NULL */
+  float* points3d;         /* [R,3]   or NULL */
   float* normal_map;       /* [R,3] or NULL */
 } neat_composite_args;
 int neat_composite_forward(const neat_composite_args* a, void* stream);

@@ -72,16 +72,17 @@ class NeatStepFunction(torch.autograd.Function):
             eik_done = torch.cuda.Event()
             eik_done.record(side)
         grad_theta.record_stream(main)
-        st.rgb, st.rend_save = renderer.head_forward(0, pts, M, st.grad, st.feat, training=True)
+        # The attraction head goes first: lines3d -> junction clustering -> the step's single device->host hand-over
+        # are enqueued BEFORE the rendering head, so the host-side junction matching (and the enqueueing of the loss)
+        # overlaps ~0.5 ms of remaining forward kernels instead of an idle GPU.
         st.lines, st.att_save = renderer.head_forward(1, pts, M, st.grad, st.feat, training=True)
-        w, rgb_values, lines3d, depth, points3d, _ = renderer.composite(z, st.sdf, st.rgb, st.lines, None, cam, dirs,
-                                                                        beta, False)
+        w, lines3d, depth, points3d = renderer.composite_lines(z, st.sdf, st.lines, cam, dirs, beta)
         st.weights, st.depth, st.points3d = w, depth, points3d
-        # junction clustering needs only lines3d: launch it now and start the (single) device->host transfer of the step,
-        # so that the host-side Hungarian overlaps the remaining forward kernels (surface point, geometry, eikonal points)
         if st.junction_inputs is not None:
             cent_d, n_d = renderer.dbscan_async(lines3d.view(-1, 3), 0.01)
             st.junction_event, st.junction_host = renderer.to_host_async([n_d, cent_d] + list(st.junction_inputs))
+        st.rgb, st.rend_save = renderer.head_forward(0, pts, M, st.grad, st.feat, training=True)
+        rgb_values = renderer.composite_rgb(z, st.sdf, st.rgb, cam, dirs, beta)
         p3 = renderer.explicit_points(points3d)
         st.sdf3, st.grad3, _, _, _ = renderer.sdf_outputs(p3, R, clamp=True, want_feat=False, tag="surface")
         st.lines2d, st.lines2d_calib, st.l3d, st.pose_inv = renderer.line_geometry(pose, K, st.uv_proj, points3d, st.grad3,

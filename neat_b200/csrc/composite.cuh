@@ -82,11 +82,13 @@ __global__ void __launch_bounds__(128) composite_fwd_kernel(CompositeParams p) {
     const float ex = warp_excl_scan(fe, tot);
     if (i < S) {
       const float w = (1.0f - expf(-fe)) * expf(-(carry + ex));
-      p.weights[static_cast<size_t>(r) * S + i] = w;
+      if (p.weights) p.weights[static_cast<size_t>(r) * S + i] = w;
       const size_t q = static_cast<size_t>(r) * S + i;
-      acc[0] += w * p.rgb[3 * q]; acc[1] += w * p.rgb[3 * q + 1]; acc[2] += w * p.rgb[3 * q + 2];
+      if (p.rgb) { acc[0] += w * p.rgb[3 * q]; acc[1] += w * p.rgb[3 * q + 1]; acc[2] += w * p.rgb[3 * q + 2]; }
+      if (p.lines) {
 #pragma unroll
-      for (int c = 0; c < 6; ++c) acc[3 + c] += w * p.lines[6 * q + c];
+        for (int c = 0; c < 6; ++c) acc[3 + c] += w * p.lines[6 * q + c];
+      }
       const float v0 = zi * d0, v1 = zi * d1, v2 = zi * d2;
       acc[9] += w * sqrtf(v0 * v0 + v1 * v1 + v2 * v2);
       acc[10] += w * (o0 + v0); acc[11] += w * (o1 + v1); acc[12] += w * (o2 + v2);
@@ -101,10 +103,10 @@ __global__ void __launch_bounds__(128) composite_fwd_kernel(CompositeParams p) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = warp_sum(acc[i]);
   if (lane == 0) {
-    for (int c = 0; c < 3; ++c) p.rgb_values[3 * r + c] = acc[c];
-    for (int c = 0; c < 6; ++c) p.lines3d[6 * r + c] = acc[3 + c];
-    p.depth[r] = acc[9];
-    for (int c = 0; c < 3; ++c) p.points3d[3 * r + c] = acc[10 + c];
+    if (p.rgb) for (int c = 0; c < 3; ++c) p.rgb_values[3 * r + c] = acc[c];
+    if (p.lines) for (int c = 0; c < 6; ++c) p.lines3d[6 * r + c] = acc[3 + c];
+    if (p.depth) p.depth[r] = acc[9];
+    if (p.points3d) for (int c = 0; c < 3; ++c) p.points3d[3 * r + c] = acc[10 + c];
     if (p.normal_map) for (int c = 0; c < 3; ++c) p.normal_map[3 * r + c] = acc[13 + c];
   }
 }

@@ -165,6 +165,31 @@ class Renderer:
         _lib.check(ctx.lib.neat_composite_forward(ctypes.byref(a), ctx._stream()))
         return w, rgb_values, lines3d, depth, points3d, nmap
 
+    def composite_lines(self, z, sdf, lines, cam, dirs, beta_param):
+        """First half of the training step's compositing: weights, lines3d, depth, points3d (everything the junction
+        clustering and the geometry need) as soon as the attraction head is done."""
+        ctx = self.ctx
+        dev = ctx.device
+        R, S = z.shape
+        w = self.pool.get("composite.w", R * S).view(R, S)
+        lines3d = torch.empty(R, 6, device=dev)
+        depth = torch.empty(R, device=dev)
+        points3d = torch.empty(R, 3, device=dev)
+        a = _lib.CompositeArgs(R, S, _ptr(z), _ptr(sdf), None, _ptr(lines), None, _ptr(cam), _ptr(dirs), _ptr(beta_param),
+                               self.beta_min, _ptr(w), None, _ptr(lines3d), _ptr(depth), _ptr(points3d), None)
+        _lib.check(ctx.lib.neat_composite_forward(ctypes.byref(a), ctx._stream()))
+        return w, lines3d, depth, points3d
+
+    def composite_rgb(self, z, sdf, rgb, cam, dirs, beta_param):
+        """Second half: rgb_values = sum_i w_i rgb_i once the rendering head is done."""
+        ctx = self.ctx
+        R, S = z.shape
+        rgb_values = torch.empty(R, 3, device=ctx.device)
+        a = _lib.CompositeArgs(R, S, _ptr(z), _ptr(sdf), _ptr(rgb), None, None, _ptr(cam), _ptr(dirs), _ptr(beta_param),
+                               self.beta_min, None, _ptr(rgb_values), None, None, None, None)
+        _lib.check(ctx.lib.neat_composite_forward(ctypes.byref(a), ctx._stream()))
+        return rgb_values
+
     def line_geometry(self, pose, K, uv_proj, points3d, grad3d, lines3d):
         ctx = self.ctx
         dev = ctx.device
