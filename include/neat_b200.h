@@ -294,6 +294,21 @@ typedef struct {
 int neat_weight_gradients(neat_ctx* ctx, const neat_grad_group* groups, int n_groups, float* flat_grad,
                           void* stream);
 
+/* ---- optimizer step: torch.optim.Adam(lr) of code/training/volsdf_train.py:178,374 ----
+ * One launch for every parameter tensor: param -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps)
+ * with m, v updated in place (torch's default Adam: no amsgrad, L2 weight decay added to the gradient).  grad is
+ * multiplied by grad_scale first (1 / world size after the data-parallel all-reduce(SUM); 1 otherwise).
+ * step = 1 for the first update.  At most 128 tensors per call.                                                */
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  long long numel;
+} neat_adam_tensor;
+int neat_adam_step(const neat_adam_tensor* tensors, int n, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

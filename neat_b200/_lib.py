@@ -54,6 +54,8 @@ SIGNATURES = {
     "neat_project_points_backward": (_I, [_I, _P, _P, _I, _P, _P, _P, _P, _P]),
     "neat_junction_terms": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "neat_junction_terms_backward": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "neat_adam_step": (_I, [_P, _I, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _I,
+                           ctypes.c_float, _P]),
     "neat_loss_forward_backward": (_I, [_P, _P]),
     "neat_project_calib_backward": (_I, [_I, _P, _P, _P, _P, _P]),
     "neat_dbscan_workspace_bytes": (ctypes.c_size_t, [_I]),
@@ -67,6 +69,10 @@ SIGNATURES = {
     "neat_sdf_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "neat_weight_gradients": (_I, [_P, _P, _I, _P, _P]),
 }
+
+
+class AdamTensor(ctypes.Structure):
+    _fields_ = [("param", _P), ("grad", _P), ("exp_avg", _P), ("exp_avg_sq", _P), ("numel", ctypes.c_longlong)]
 
 
 class CompositeBwdArgs(ctypes.Structure):

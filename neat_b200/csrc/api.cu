@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -22,6 +23,7 @@
 #include "weight_norm.cuh"
 #include "wgrad.cuh"
 #include "junction.cuh"
+#include "adam.cuh"
 
 using namespace neat;
 
@@ -680,6 +682,55 @@ int neat_junction_terms_backward(int n, int n_global, const float* j3d_local, co
   CK(cudaMemsetAsync(g_j2d_global_calib, 0, sizeof(float) * 2 * n_global, st));
   junction_terms_bwd_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, j3d_local, j3d_global, j2d_local_calib, j2d_global_calib,
                                                              rows, cols, g_out, g_j3d_global, g_j2d_global_calib);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+// ---------------------------------------------------------------- optimizer step
+namespace {
+struct AdamCache {  // one table per device: re-uploaded only when the tensor list changes (it never does in training)
+  AdamTable host{};
+  AdamTable* dev = nullptr;
+  int device = -1;
+  bool valid = false;
+};
+AdamCache g_adam[16];
+}  // namespace
+
+int neat_adam_step(const neat_adam_tensor* tensors, int n, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int step, float grad_scale, void* stream) {
+  if (n < 0 || n > ADAM_MAX_TENSORS || (n && !tensors) || step < 1) return fail(NEAT_EINVAL, "bad argument");
+  if (n == 0) return NEAT_OK;
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) return fail(NEAT_EINVAL, "device index out of range");
+  AdamCache& c = g_adam[dev];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AdamTable t{};
+  t.n = n;
+  int blocks = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!tensors[i].param || !tensors[i].grad || !tensors[i].exp_avg || !tensors[i].exp_avg_sq || tensors[i].numel < 0)
+      return fail(NEAT_EINVAL, "adam: null tensor");
+    t.t[i] = tensors[i];
+    t.blk_start[i] = blocks;
+    blocks += static_cast<int>((tensors[i].numel + ADAM_BLOCK_ELEMS - 1) / ADAM_BLOCK_ELEMS);
+  }
+  for (int i = n; i <= ADAM_MAX_TENSORS; ++i) t.blk_start[i] = blocks;
+  if (!c.dev) CK(cudaMalloc(&c.dev, sizeof(AdamTable)));
+  if (!c.valid || std::memcmp(&c.host, &t, sizeof(AdamTable)) != 0) {
+    CK(cudaStreamSynchronize(st));
+    CK(cudaMemcpyAsync(c.dev, &t, sizeof(AdamTable), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));  // `t` is a stack object
+    c.host = t;
+    c.valid = true;
+  }
+  if (blocks == 0) return NEAT_OK;
+  const double bc1 = 1.0 - std::pow(static_cast<double>(beta1), step);
+  const double bc2 = 1.0 - std::pow(static_cast<double>(beta2), step);
+  adam_step_kernel<<<blocks, 256, 0, st>>>(c.dev, lr, beta1, beta2, eps, weight_decay, static_cast<float>(bc1),
+                                          static_cast<float>(1.0 / std::sqrt(bc2)), grad_scale);
   ++g_launches;
   CK(cudaGetLastError());
   return NEAT_OK;

@@ -217,10 +217,22 @@ __global__ void __launch_bounds__(32 * SMP_WARPS) sampler_bounds_kernel(SamplerP
   for (int i = lane; i < Lold; i += 32) { m.dist[i] = zg[i]; m.dstar[i] = sg[i]; }   // old (sorted)
   for (int i = lane; i < n; i += 32) { m.aux[i] = zn[i]; m.aux[SMP_MAX_NEW + i] = sn[i]; }  // new
   __syncwarp();
+  // The new samples are non-decreasing for every draw the reference makes (stratified depths, inverse CDF of a sorted
+  // u); then both ranks are binary searches.  Checked at run time: a draw that is not sorted (fp32 rounding at an
+  // interval boundary) takes the general counting path, so the merge is always the stable sort of the reference.
+  bool sorted = true;
+  for (int j = lane; j < n - 1; j += 32) sorted = sorted && (m.aux[j] <= m.aux[j + 1]);
+  sorted = __all_sync(0xffffffffu, sorted);
   for (int i = lane; i < Lold; i += 32) {  // rank of old i = i + #{new < z_i}
     const float v = m.dist[i];
     int c = 0;
-    for (int j = 0; j < n; ++j) c += m.aux[j] < v;
+    if (sorted) {
+      int lo = 0, hi = n;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (m.aux[mid] < v) lo = mid + 1; else hi = mid; }
+      c = lo;
+    } else {
+      for (int j = 0; j < n; ++j) c += m.aux[j] < v;
+    }
     m.z[i + c] = v; m.s[i + c] = m.dstar[i];
   }
   for (int j = lane; j < n; j += 32) {  // rank of new j = #{old <= s_j} + #{new k: s_k < s_j or (== and k < j)}
@@ -228,7 +240,11 @@ __global__ void __launch_bounds__(32 * SMP_WARPS) sampler_bounds_kernel(SamplerP
     int lo = 0, hi = Lold;
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (m.dist[mid] <= v) lo = mid + 1; else hi = mid; }
     int c = lo;
-    for (int k = 0; k < n; ++k) { const float u = m.aux[k]; c += (u < v) || (u == v && k < j); }
+    if (sorted) {
+      c += j;
+    } else {
+      for (int k = 0; k < n; ++k) { const float u = m.aux[k]; c += (u < v) || (u == v && k < j); }
+    }
     m.z[c] = v; m.s[c] = m.aux[SMP_MAX_NEW + j];
   }
   __syncwarp();

@@ -26,6 +26,17 @@ class GradBucket:
     def scalars(self):
         return self.flat[self.n:]
 
+    def all_reduce_sum(self, group=None):
+        """SUM only; returns the scale (1 / world size) the consumer still has to apply (neat_b200.optim.Adam folds it
+        into its single update kernel: grad_scale)."""
+        if not (dist.is_available() and dist.is_initialized()):
+            return 1.0
+        ws = dist.get_world_size(group)
+        if ws == 1:
+            return 1.0
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        return 1.0 / ws
+
     def all_reduce_mean(self, group=None):
         if not (dist.is_available() and dist.is_initialized()):
             return

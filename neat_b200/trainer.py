@@ -5,6 +5,7 @@ import torch
 from . import synth
 from .loss import VolSDFLoss
 from .model import VolSDFNetwork
+from .optim import Adam
 from .parallel import GradBucket
 
 
@@ -55,14 +56,14 @@ class TrainStep:
         self.model.rng = rng
         self.loss_fn = VolSDFLoss(**synth.loss_conf())
         self.bucket = GradBucket(self.model.parameters())
-        # same update rule as the reference's torch.optim.Adam(lr) (volsdf_train.py:178); fused = one kernel, step on device
-        self.opt = torch.optim.Adam(self.model.parameters(), lr=lr, fused=True)
+        # same update rule as the reference's torch.optim.Adam(lr) (volsdf_train.py:178), all tensors in one launch
+        self.opt = Adam(self.model.parameters(), lr=lr)
 
     def step(self, inp, gt):
         out = self.model(inp)
         lo = self.loss_fn(out, gt)
         self.bucket.zero()
         lo["loss"].backward()
-        self.bucket.all_reduce_mean()
+        self.opt.grad_scale = self.bucket.all_reduce_sum()  # the 1/world scale rides in the Adam kernel
         self.opt.step()
         return lo["loss"]

@@ -376,3 +376,34 @@ def test_parameter_gradients_accumulate_and_overwrite():
     loss_fn(model(inp), gt)["loss"].backward()
     assert params[names[0]].grad is None
     assert G.rel_err(params[names[1]].grad.cpu(), g1[names[1]].cpu()) < 1e-5
+
+
+def test_fused_adam_matches_torch_adam():
+    """neat_b200.optim.Adam (one launch for all tensors) against torch.optim.Adam over several steps, incl. an lr
+    schedule (ExponentialLR as in volsdf_train.py:180-182), a gradient scale and weight decay."""
+    from neat_b200.optim import Adam
+    g = torch.Generator().manual_seed(0)
+    shapes = [(256, 39), (256,), (217, 256), (1,), (3, 256), (1024, 256), (5000,)]
+    ref_p = [torch.randn(*s, generator=g).cuda().requires_grad_(True) for s in shapes]
+    my_p = [p.detach().clone().requires_grad_(True) for p in ref_p]
+    for wd, scale in ((0.0, 1.0), (0.01, 0.25)):
+        ref = torch.optim.Adam(ref_p, lr=5e-4, weight_decay=wd)
+        mine = Adam(my_p, lr=5e-4, weight_decay=wd, grad_scale=scale)
+        sr = torch.optim.lr_scheduler.ExponentialLR(ref, 0.9)
+        sm = torch.optim.lr_scheduler.ExponentialLR(mine, 0.9)
+        for it in range(5):
+            for a, b in zip(ref_p, my_p):
+                gr = torch.randn(a.shape, generator=g).cuda()
+                a.grad = gr * scale
+                b.grad = gr.clone()
+            ref.step(); mine.step(); sr.step(); sm.step()
+            for a, b in zip(ref_p, my_p):
+                assert torch.allclose(a, b, rtol=2e-6, atol=2e-7), (it, a.shape, float((a - b).abs().max()))
+        sd = mine.state_dict()
+        assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and int(sd["state"][0]["step"]) == 5
+        assert torch.allclose(sd["state"][2]["exp_avg"], ref.state_dict()["state"][2]["exp_avg"], rtol=1e-5, atol=1e-7)
+    # a parameter without a gradient is skipped, as in torch
+    my_p[0].grad = None
+    before = my_p[0].detach().clone()
+    mine.step()
+    assert torch.equal(before, my_p[0].detach())
