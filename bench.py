@@ -25,6 +25,7 @@ sys.path.insert(0, ROOT)
 
 F_SDF, F_REND, F_ATT = 1049088.0, 542720.0, 531968.0  # FLOP per point
 S = 98
+WGRAD_DRAM_BYTES_1024 = 5.927e9  # ncu, one wgrad launch at 1024 rays (profiles/r01_v4_ncu_full_summary.csv)
 
 
 def peaks():
@@ -141,6 +142,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": "DTU-shaped synthetic batch: %d rays/GPU x 98 samples, 8x256 SDF + 4x256 rendering/attraction "
                           "MLPs, ErrorBoundSampler (<=5 x 128 SDF queries/ray), train step = fwd+loss+bwd+Adam" % args.rays,
+              "optimizer": "Adam(lr=5e-4), all parameter tensors in one launch (neat_b200.optim.Adam)",
               "rays_per_gpu": args.rays, "samples_per_ray": S, "beta": args.beta, "parallelism": "dp%d" % world,
               "rng": "training draws (stratified jitter, inverse-CDF u, extra columns, eikonal points) made on the device",
               "precision_mode": "bf16x3 (hi/lo split operands, fp32 accumulate) on tcgen05",
@@ -239,17 +241,35 @@ def main():
         value = world * args.rays * args.steps / (ms_total * 1e-3)
         e2e = world * args.rays * args.steps / (ms_e2e * 1e-3)
         M = args.rays * S
-        # per point: forward F, normal pass F (sdf_render); tangent F + reverse F (sdf_bwd); the two outer-product
-        # accumulations 2 F plus the heads' (wgrad) -- SURVEY.md Appendix A, 6 F_sdf per render point in total
+        # Tensor work per point: forward F, normal pass F (sdf_render); tangent F + reverse F (sdf_bwd); the two
+        # outer-product accumulations 2 F plus the heads' (wgrad) -- SURVEY.md Appendix A, 6 F_sdf per render point.
         flops = {"sdf_bwd_M%d" % M: 2 * F_SDF * M, "sdf_render_M%d" % M: 2 * F_SDF * M,
                  "sampler": 128.0 * k_iters * args.rays * F_SDF,
-                 "head_fwd": (F_REND + F_ATT) * M, "head_bwd": (F_REND + F_ATT) * M,
+                 "head_fwd": 0.5 * (F_REND + F_ATT) * M, "head_bwd": 0.5 * (F_REND + F_ATT) * M,  # per launch (one head)
                  "wgrad": (2 * F_SDF + F_REND + F_ATT) * M + 2 * F_SDF * 2 * args.rays}
+        # wgrad is bound by HBM, not by the tensor pipe (ncu: DRAM ~70 %, tensor ~13 %): its algorithmic bytes are the
+        # saved operand tiles it has to read ONCE: per 128-point tile 33 main tiles (128 KB:
+        # 256 columns x 128 points x bf16 hi + lo) + 5 aux tiles (24 KB) for the SDF net and 2 x (9 main + 2 aux) for the
+        # heads = 52.7 KB per render point; eikonal points carry the SDF part only (33.9 KB per point).
+        WG_SDF_B, WG_HEAD_B = (33 * 131072 + 5 * 24576) / 128.0, 2 * (9 * 131072 + 2 * 24576) / 128.0
+        hbm_bytes = {"wgrad": (WG_SDF_B + WG_HEAD_B) * M + WG_SDF_B * 2 * args.rays}
         shares = {k: v[1] / ms_total for k, v in timers.items()}
         dom = max((k for k in timers if k in flops), key=lambda k: timers[k][1])
         n_l, ms_dom = timers[dom]
-        achieved = flops[dom] / (ms_dom / n_l * 1e-3) / 1e12
-        peak = pk["bf16_tflops_sustained"]
+        sec_dom = ms_dom / n_l * 1e-3
+        tensor_tflops = flops[dom] / sec_dom / 1e12
+        if dom in hbm_bytes:
+            achieved, peak, unit, bound = hbm_bytes[dom] / sec_dom / 1e9, pk["hbm_gbs"], "GB/s", "hbm"
+            peak_kind = pk_kind + " copy bandwidth (read + write)"
+            note = ("achieved = ALGORITHMIC bytes (every saved operand tile read once) / CUDA-event time; `traffic` = DRAM bytes "
+                    "of one launch from ncu (the 128-row halves of a GEMM each read the Y tiles).  The same launch does "
+                    "%.1f algorithmic TFLOP/s = %.3f of the sustained bf16 tensor rate (x3 issued: bf16x3)"
+                    % (tensor_tflops, tensor_tflops / pk["bf16_tflops_sustained"]))
+        else:
+            achieved, peak, unit, bound = tensor_tflops, pk["bf16_tflops_sustained"], "TFLOP/s", "tensor"
+            peak_kind = pk_kind + " sustained bf16 (cuBLAS)"
+            note = ("achieved = ALGORITHMIC fp32-equivalent FLOPs (2*MAC) / CUDA-event time; the kernel issues 3 bf16 MMAs "
+                    "per algorithmic MAC (hi*hi + hi*lo + lo*hi) to meet the 1e-4 parity bound, so the tensor pipe does 3x this")
         line = {"metric": "train_step_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16x3->f32", "data": "synthetic", "config": config,
@@ -258,15 +278,14 @@ def main():
                 "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": TR.h2d_bytes(hb), "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps, "last_loss": loss_host},
                 "gpu_launches": int(launches), "clocks": clk,
-                "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "roofline": {"bound": bound, "kernel": dom, "achieved": achieved, "peak": peak, "unit": unit,
                              "frac": achieved / peak,
                              # dram__bytes_read.sum + dram__bytes_write.sum of one wgrad launch at 1024 rays, from the
-                             # ncu --set full capture in profiles/r01_wgrad_ncu_full.txt
-                             "traffic": 6.527e9 if (dom == "wgrad" and args.rays == 1024) else None,
-                             "peak_kind": pk_kind + " sustained bf16 (cuBLAS)",
-                             "note": "achieved = ALGORITHMIC fp32-equivalent FLOPs (2*MAC) / CUDA-event time; the kernel "
-                                     "issues 3 bf16 MMAs per algorithmic MAC (hi*hi + hi*lo + lo*hi) to meet the 1e-4 "
-                                     "parity bound, so the tensor pipe does 3x this"},
+                             # ncu --set full capture summarised in profiles/ (see profiles/README.md)
+                             "traffic": WGRAD_DRAM_BYTES_1024 if (dom == "wgrad" and args.rays == 1024) else None,
+                             "peak_kind": peak_kind, "note": note,
+                             "tensor_tflops_algorithmic": {k: round(flops[k] / (timers[k][1] / timers[k][0] * 1e-3) / 1e12, 1)
+                                                           for k in timers if k in flops}},
                 "kernel_time_share": {k: round(v, 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1])},
                 "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in timers.items()},
                 "host_junction_block": getattr(ts.model, "last_host_ms", None), "per_rank": per_rank}
