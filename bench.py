@@ -197,8 +197,10 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    k_acc = torch.zeros(1, dtype=torch.int32, device=dev)  # the sampler's k is data dependent and drifts as beta trains
     for _ in range(args.steps):
         ts.step(inp, gt)
+        k_acc += ts.model.last_step.n_iters
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -206,6 +208,7 @@ def main():
     timers = rn.timer_ms()
     rn.timers = None
     k_iters = int(ts.model.last_step.n_iters.item())
+    k_mean = float(k_acc.item()) / args.steps
 
     # ---- end to end from host buffers (same initial state and trajectory as the loop above) ----------------
     del ts
@@ -244,7 +247,7 @@ def main():
         # Tensor work per point: forward F, normal pass F (sdf_render); tangent F + reverse F (sdf_bwd); the two
         # outer-product accumulations 2 F plus the heads' (wgrad) -- SURVEY.md Appendix A, 6 F_sdf per render point.
         flops = {"sdf_bwd_M%d" % M: 2 * F_SDF * M, "sdf_render_M%d" % M: 2 * F_SDF * M,
-                 "sampler": 128.0 * k_iters * args.rays * F_SDF,
+                 "sampler": 128.0 * k_mean * args.rays * F_SDF,
                  "head_fwd": 0.5 * (F_REND + F_ATT) * M, "head_bwd": 0.5 * (F_REND + F_ATT) * M,  # per launch (one head)
                  "wgrad": (2 * F_SDF + F_REND + F_ATT) * M + 2 * F_SDF * 2 * args.rays}
         # wgrad is bound by HBM, not by the tensor pipe (ncu: DRAM ~70 %, tensor ~13 %): its algorithmic bytes are the
@@ -273,8 +276,8 @@ def main():
         line = {"metric": "train_step_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16x3->f32", "data": "synthetic", "config": config,
-                "sampler_iters_k": k_iters,
-                "mlp_samples_per_sec": world * (M + 128 * k_iters * args.rays + 3 * args.rays) * args.steps / (ms_total * 1e-3),
+                "sampler_iters_k": k_iters, "sampler_iters_k_mean": round(k_mean, 3),
+                "mlp_samples_per_sec": world * (M + 128 * k_mean * args.rays + 3 * args.rays) * args.steps / (ms_total * 1e-3),
                 "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": TR.h2d_bytes(hb), "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps, "last_loss": loss_host},
                 "gpu_launches": int(launches), "clocks": clk,

@@ -48,11 +48,8 @@ class NeatStepFunction(torch.autograd.Function):
         R, S = z.shape
         M = R * S
         st.R, st.S, st.dirs, st.cam, st.z, st.n_iters = R, S, dirs, cam, z, n_it
-        pts = renderer.ray_points(cam, dirs, z)
-        st.sdf, st.grad, st.act, st.feat, st.sdf_save = renderer.sdf_outputs(pts, M, clamp=True, training=True, tag="render")
-        # eikonal points (neat_wfr_rend_a.py:515-527): R uniform in the bounding cube + R near-surface.  They only need
-        # the sampler's output, and their 2R/128 tiles fit into the tail of the render launch (148 persistent CTAs, the
-        # last round of tiles leaves most SMs idle): launched on a side stream right behind it.
+        # eikonal points (neat_wfr_rend_a.py:515-527): R uniform in the bounding cube + R near-surface; they only need the
+        # sampler's output
         if st.eik_uniform is None:
             r = renderer.scene_bounding_sphere
             if renderer.sampler.rng == "device":
@@ -62,32 +59,46 @@ class NeatStepFunction(torch.autograd.Function):
         near = cam[None, :] + z_eik * dirs
         st.eik_pts = torch.cat([st.eik_uniform.to(dev, torch.float32), near], 0).contiguous()
         pe = renderer.explicit_points(st.eik_pts)
+        # Stream plan.  Every tile-MLP launch is 148 persistent CTAs (one per SM) whose last round of tiles leaves most
+        # SMs idle, and the small launches (eikonal points: 16 tiles, surface points: 8 tiles) would each occupy a
+        # handful of SMs for the latency of a whole tile.  They go to a side stream, where the block scheduler fits them
+        # into the tails of the big launches:
+        #   main : render -> attraction head -> line compositing -> DBSCAN -> host hand-over -> rendering head -> colours
+        #   side : eikonal points (forked before the render launch) ...... surface points -> geometry (after the lines)
+        # The big launches stay serialised (running the two heads concurrently was measured: no gain at 1024 rays, 3 %
+        # slower at 8192).  The junction hand-over only needs the attraction head, so the host-side matching (and the
+        # enqueueing of the loss) overlaps the rendering head instead of an idle GPU.
         main, side = torch.cuda.current_stream(dev), renderer.side_stream()
         fork = torch.cuda.Event()
         fork.record(main)
+        pts = renderer.ray_points(cam, dirs, z)
+        st.sdf, st.grad, st.act, st.feat, st.sdf_save = renderer.sdf_outputs(pts, M, clamp=True, training=True, tag="render")
         with torch.cuda.stream(side):
             side.wait_event(fork)
             _, grad_theta, _, _, st.eik_save = renderer.sdf_outputs(pe, 2 * R, clamp=False, training=True,
                                                                     want_feat=False, want_sdf=False, tag="eik")
-            eik_done = torch.cuda.Event()
-            eik_done.record(side)
         grad_theta.record_stream(main)
-        # The attraction head goes first: lines3d -> junction clustering -> the step's single device->host hand-over
-        # are enqueued BEFORE the rendering head, so the host-side junction matching (and the enqueueing of the loss)
-        # overlaps ~0.5 ms of remaining forward kernels instead of an idle GPU.
         st.lines, st.att_save = renderer.head_forward(1, pts, M, st.grad, st.feat, training=True)
         w, lines3d, depth, points3d = renderer.composite_lines(z, st.sdf, st.lines, cam, dirs, beta)
         st.weights, st.depth, st.points3d = w, depth, points3d
         if st.junction_inputs is not None:
             cent_d, n_d = renderer.dbscan_async(lines3d.view(-1, 3), 0.01)
             st.junction_event, st.junction_host = renderer.to_host_async([n_d, cent_d] + list(st.junction_inputs))
+        lines_done = torch.cuda.Event()
+        lines_done.record(main)
         st.rgb, st.rend_save = renderer.head_forward(0, pts, M, st.grad, st.feat, training=True)
+        with torch.cuda.stream(side):
+            side.wait_event(lines_done)
+            p3 = renderer.explicit_points(points3d)
+            st.sdf3, st.grad3, _, _, _ = renderer.sdf_outputs(p3, R, clamp=True, want_feat=False, tag="surface")
+            st.lines2d, st.lines2d_calib, st.l3d, st.pose_inv = renderer.line_geometry(pose, K, st.uv_proj, points3d,
+                                                                                       st.grad3, lines3d)
+            side_done = torch.cuda.Event()
+            side_done.record(side)
+        for t in (st.sdf3, st.grad3, st.lines2d, st.lines2d_calib, st.l3d, st.pose_inv):
+            t.record_stream(main)
         rgb_values = renderer.composite_rgb(z, st.sdf, st.rgb, cam, dirs, beta)
-        p3 = renderer.explicit_points(points3d)
-        st.sdf3, st.grad3, _, _, _ = renderer.sdf_outputs(p3, R, clamp=True, want_feat=False, tag="surface")
-        st.lines2d, st.lines2d_calib, st.l3d, st.pose_inv = renderer.line_geometry(pose, K, st.uv_proj, points3d, st.grad3,
-                                                                                   lines3d)
-        main.wait_event(eik_done)
+        main.wait_event(side_done)
         fctx.renderer, fctx.st = renderer, st
         fctx.beta_shape = beta_param.shape
         return rgb_values, lines3d.view(R, 2, 3), grad_theta
@@ -105,6 +116,9 @@ class NeatStepFunction(torch.autograd.Function):
         l3b = lines3d_bar.reshape(R, 6).contiguous().float() if lines3d_bar is not None else z(R, 6)
         gtb = grad_theta_bar.contiguous().float() if grad_theta_bar is not None else z(2 * R, 3)
         pool = renderer.pool
+        main, side = torch.cuda.current_stream(dev), renderer.side_stream()
+        fork = torch.cuda.Event()  # the eikonal points' backward depends on grad_theta_bar only
+        fork.record(main)
         rgb_pre_bar = pool.get("bwd.rgb_pre_bar", M * 3).view(M, 3)
         lines_bar = pool.get("bwd.lines_bar", M * 6).view(M, 6)
         sdf_bar = pool.get("bwd.sdf_bar", M)
@@ -127,13 +141,11 @@ class NeatStepFunction(torch.autograd.Function):
         with renderer.timed("sdf_bwd_M%d" % M):
             _lib.check(lib.neat_sdf_backward(ctx._h, ctypes.byref(pts), _ptr(n_bar), _ptr(sdf_bar), _ptr(feat_bar),
                                              _ptr(st.act), _ptr(st.sdf_save), _ptr(sb), _ptr(scratch), stream))
-        # the eikonal points' double backward rides in the tail of the launch above (side stream, own scratch)
+        # the eikonal points' double backward fills the tails of the launches above (side stream, own scratch; it was
+        # forked at the top of backward)
         pe = renderer.explicit_points(st.eik_pts)
         sbe = pool.get("bwd.sdf_eik", int(lib.neat_sdf_bwd_save_bytes(ctx._h, 2 * R)), torch.uint8)
         scratch_e = pool.get("bwd.scratch_eik", int(lib.neat_sdf_bwd_scratch_bytes(ctx._h, 2 * R)), torch.uint8)
-        main, side = torch.cuda.current_stream(dev), renderer.side_stream()
-        fork = torch.cuda.Event()
-        fork.record(main)
         with torch.cuda.stream(side):
             side.wait_event(fork)
             _lib.check(lib.neat_sdf_backward(ctx._h, ctypes.byref(pe), _ptr(gtb), None, None, None, _ptr(st.eik_save),
