@@ -84,6 +84,11 @@ int neat_sdf_points(neat_ctx* ctx, const float* x, int M, float* sdf, void* stre
  * or one camera centre [3] (o_stride 0); sdf[R,n]                                              */
 int neat_sdf_rays(neat_ctx* ctx, const float* rays_o, int o_stride, const float* rays_d, const float* z, int R,
                   int n, float* sdf, void* stream);
+/* Dense-grid evaluation for mesh extraction (code/utils/plots.py:101-108, 318-329): the grid
+ * points are generated in the kernel.  Axis k = np.linspace(lo[k], hi[k], n[k]) (float64, cast to float32); point order =
+ * np.meshgrid(x, y, z) raveled (idx = (iy * nx + ix) * nz + iz), i.e. the reference's `grid_points`.  clamp = 0: the raw
+ * network output implicit_network(x)[:, 0] that the mesh extraction uses; 1: get_sdf_vals' sphere clamp.  sdf [nx*ny*nz]. */
+int neat_sdf_grid(neat_ctx* ctx, const double* lo, const double* hi, const int* n, int clamp, float* sdf, void* stream);
 
 /* ---- ErrorBoundSampler.get_z_vals (code/model/ray_sampler.py:130-283) ------------------------ */
 typedef struct {
@@ -293,6 +298,16 @@ typedef struct {
 } neat_grad_group;
 int neat_weight_gradients(neat_ctx* ctx, const neat_grad_group* groups, int n_groups, float* flat_grad,
                           void* stream);
+
+/* ---- wireframe finalisation: per-image line voting, code/neat-final-parsing.py:226-260 ----
+ * lines2d [N,4], lines3d [N,2,3], points3d [N,3] (the `l3d` support points) are the eval-mode outputs of one image;
+ * gt_lines [G,4] the image's 2D wireframe segments.  Every prediction votes twice (both end-point orders) for its nearest
+ * ground-truth line; votes with squared distance < dis_threshold are kept.  Outputs per ground-truth line g:
+ * counts[g] (votes), lines3d_mean[g] [2,3] (mean of the voting 3D lines, oriented like the vote), scores[g] (mean distance
+ * of the votes' support points to that mean line); rows without votes are zero.                                  */
+size_t neat_line_vote_workspace_bytes(int N, int G);
+int neat_line_vote(const float* lines2d, const float* lines3d, const float* points3d, int N, const float* gt_lines, int G,
+                   float dis_threshold, void* workspace, float* lines3d_mean, float* scores, float* counts, void* stream);
 
 /* ---- optimizer step: torch.optim.Adam(lr) of code/training/volsdf_train.py:178,374 ----
  * One launch for every parameter tensor: param -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps)

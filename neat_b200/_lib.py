@@ -35,6 +35,7 @@ SIGNATURES = {
     "neat_pack_weights": (_I, [_P, _P, _P]),
     "neat_sdf_points": (_I, [_P, _P, _I, _P, _P]),
     "neat_sdf_rays": (_I, [_P, _P, _I, _P, _P, _I, _I, _P, _P]),
+    "neat_sdf_grid": (_I, [_P, _P, _P, _P, _I, _P, _P]),
     "neat_sampler_workspace_bytes": (ctypes.c_size_t, [_I]),
     "neat_sampler_run": (_I, [_P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P]),
     "neat_sampler_finish": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P]),
@@ -54,6 +55,8 @@ SIGNATURES = {
     "neat_project_points_backward": (_I, [_I, _P, _P, _I, _P, _P, _P, _P, _P]),
     "neat_junction_terms": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "neat_junction_terms_backward": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "neat_line_vote_workspace_bytes": (ctypes.c_size_t, [_I, _I]),
+    "neat_line_vote": (_I, [_P, _P, _P, _I, _P, _I, ctypes.c_float, _P, _P, _P, _P, _P]),
     "neat_adam_step": (_I, [_P, _I, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _I,
                            ctypes.c_float, _P]),
     "neat_loss_forward_backward": (_I, [_P, _P]),

@@ -24,6 +24,7 @@
 #include "wgrad.cuh"
 #include "junction.cuh"
 #include "adam.cuh"
+#include "parsing.cuh"
 
 using namespace neat;
 
@@ -309,7 +310,7 @@ static int launch_query(neat_ctx* c, SdfQueryParams& p, void* stream) {
   p.prog = c->prog_query;
   p.packed = c->packed;
   p.multires = c->plan.cfg.multires;
-  p.sphere_r = c->plan.cfg.sphere_radius;
+  p.sphere_r = p.sphere_r < 0.f ? 0.f : c->plan.cfg.sphere_radius;  // < 0 on entry: no sphere clamp (raw network sdf)
   p.sphere_scale = c->plan.cfg.sphere_scale;
   const int n_tiles = (p.M + TILE_M - 1) / TILE_M;
   const int grid = n_tiles < c->num_sms ? n_tiles : c->num_sms;
@@ -327,6 +328,27 @@ int neat_sdf_points(neat_ctx* c, const float* x, int M, float* sdf, void* stream
   p.sdf = sdf;
   p.M = M;
   p.n_per_ray = 1;
+  return launch_query(c, p, stream);
+}
+
+int neat_sdf_grid(neat_ctx* c, const double* lo, const double* hi, const int* n, int clamp, float* sdf, void* stream) {
+  if (!c || !lo || !hi || !n || !sdf) return fail(NEAT_EINVAL, "bad argument");
+  long long M = 1;
+  SdfQueryParams p{};
+  for (int k = 0; k < 3; ++k) {
+    if (n[k] < 1) return fail(NEAT_EINVAL, "grid size must be >= 1");
+    M *= n[k];
+    p.grid_n[k] = n[k];
+    p.grid_lo[k] = lo[k];
+    p.grid_hi[k] = hi[k];
+    p.grid_step[k] = n[k] > 1 ? (hi[k] - lo[k]) / (n[k] - 1) : 0.0;  // np.linspace: step = delta / div
+    if (n[k] == 1) p.grid_hi[k] = lo[k];
+  }
+  if (M > 0x7fffff00LL) return fail(NEAT_EINVAL, "grid too large (more than 2^31 points): evaluate it in slabs");
+  p.sdf = sdf;
+  p.M = static_cast<int>(M);
+  p.n_per_ray = 1;
+  p.sphere_r = clamp ? 0.f : -1.f;
   return launch_query(c, p, stream);
 }
 
@@ -682,6 +704,35 @@ int neat_junction_terms_backward(int n, int n_global, const float* j3d_local, co
   CK(cudaMemsetAsync(g_j2d_global_calib, 0, sizeof(float) * 2 * n_global, st));
   junction_terms_bwd_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, j3d_local, j3d_global, j2d_local_calib, j2d_global_calib,
                                                              rows, cols, g_out, g_j3d_global, g_j2d_global_calib);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+// ---------------------------------------------------------------- finalisation: per-image line voting
+size_t neat_line_vote_workspace_bytes(int N, int G) {
+  if (N < 0 || G < 0) return 0;
+  return al256(sizeof(int) * 2 * static_cast<size_t>(N)) + al256(sizeof(float) * 8 * static_cast<size_t>(G));
+}
+
+int neat_line_vote(const float* lines2d, const float* lines3d, const float* points3d, int N, const float* gt_lines, int G,
+                   float dis_threshold, void* workspace, float* lines3d_mean, float* scores, float* counts, void* stream) {
+  if (N <= 0 || G <= 0 || !lines2d || !lines3d || !points3d || !gt_lines || !workspace || !lines3d_mean || !scores || !counts)
+    return fail(NEAT_EINVAL, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* b = static_cast<uint8_t*>(workspace);
+  int* assign = reinterpret_cast<int*>(b);
+  b += al256(sizeof(int) * 2 * static_cast<size_t>(N));
+  float* sums = reinterpret_cast<float*>(b);                 // [G,6]
+  float* score_sums = sums + 6 * static_cast<size_t>(G);     // [G]
+  CK(cudaMemsetAsync(sums, 0, sizeof(float) * 7 * static_cast<size_t>(G), st));
+  CK(cudaMemsetAsync(counts, 0, sizeof(float) * static_cast<size_t>(G), st));
+  const int blocks = (2 * N + 255) / 256;
+  line_vote_assign_kernel<<<blocks, 256, 0, st>>>(lines2d, lines3d, N, gt_lines, G, dis_threshold, assign, sums, counts);
+  ++g_launches;
+  line_vote_score_kernel<<<blocks, 256, 0, st>>>(points3d, N, assign, sums, counts, score_sums);
+  ++g_launches;
+  line_vote_finish_kernel<<<(G + 127) / 128, 128, 0, st>>>(G, sums, counts, score_sums, lines3d_mean, scores);
   ++g_launches;
   CK(cudaGetLastError());
   return NEAT_OK;

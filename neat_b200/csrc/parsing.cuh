@@ -1,0 +1,98 @@
+// Per-image line voting of the wireframe finalisation (code/neat-final-parsing.py:226-260):
+// every predicted 2D line (both end-point orders) votes for its nearest ground-truth 2D line; the 3D lines of the votes
+// within the distance threshold are averaged per ground-truth line and scored by the mean distance of their support
+// points (l3d) to the averaged 3D line.  The reference materialises the [2N, G] distance matrix and then loops over the
+// labels in Python; here it is two passes over the 2N entries with the G ground-truth lines staged in shared memory.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace neat {
+
+constexpr int VOTE_GT_TILE = 1024;  // ground-truth lines staged per shared-memory pass (16 KB)
+
+// pass 1: assign[e] = argmin_g |l2d_e - gt_g|^2 (first minimum), -1 if the minimum is >= threshold;
+//         sums[g][0..5] += oriented 3D line, counts[g] += 1.   e < N: original end-point order, e >= N: swapped.
+__global__ void __launch_bounds__(256) line_vote_assign_kernel(const float* __restrict__ lines2d, const float* __restrict__ lines3d,
+                                                               int N, const float* __restrict__ gt, int G, float thr,
+                                                               int* __restrict__ assign, float* __restrict__ sums,
+                                                               float* __restrict__ counts) {
+  __shared__ float4 sgt[VOTE_GT_TILE];
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = e < 2 * N;
+  const int i = live ? (e < N ? e : e - N) : 0;
+  const bool sw = e >= N;
+  float4 l = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) {
+    const float4 v = *reinterpret_cast<const float4*>(lines2d + 4 * static_cast<size_t>(i));
+    l = sw ? make_float4(v.z, v.w, v.x, v.y) : v;
+  }
+  float best = INFINITY;
+  int arg = -1;
+  for (int g0 = 0; g0 < G; g0 += VOTE_GT_TILE) {
+    const int n = min(VOTE_GT_TILE, G - g0);
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += blockDim.x) sgt[k] = *reinterpret_cast<const float4*>(gt + 4 * static_cast<size_t>(g0 + k));
+    __syncthreads();
+    if (live) {
+      for (int k = 0; k < n; ++k) {
+        const float4 t = sgt[k];
+        const float dx0 = l.x - t.x, dy0 = l.y - t.y, dx1 = l.z - t.z, dy1 = l.w - t.w;
+        // summed in the order of torch.sum over the last dimension of 4
+        const float d = ((dx0 * dx0 + dy0 * dy0) + dx1 * dx1) + dy1 * dy1;
+        if (d < best) { best = d; arg = g0 + k; }
+      }
+    }
+  }
+  if (!live) return;
+  const bool ok = arg >= 0 && best < thr;
+  assign[e] = ok ? arg : -1;
+  if (ok) {
+    const float* p = lines3d + 6 * static_cast<size_t>(i);
+    float* s = sums + 6 * static_cast<size_t>(arg);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      atomicAdd(s + c, sw ? p[3 + c] : p[c]);
+      atomicAdd(s + 3 + c, sw ? p[c] : p[3 + c]);
+    }
+    atomicAdd(counts + arg, 1.0f);
+  }
+}
+
+// pass 2: score_sums[g] += |(p - a) x (p - b)| / max(|b - a|, 1e-6) with (a, b) = sums[g] / counts[g], p = support point
+__global__ void __launch_bounds__(256) line_vote_score_kernel(const float* __restrict__ points3d, int N, const int* __restrict__ assign,
+                                                              const float* __restrict__ sums, const float* __restrict__ counts,
+                                                              float* __restrict__ score_sums) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 2 * N) return;
+  const int g = assign[e];
+  if (g < 0) return;
+  const int i = e < N ? e : e - N;
+  const float inv = 1.0f / counts[g];
+  float a[3], b[3], p[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    a[c] = sums[6 * g + c] * inv;
+    b[c] = sums[6 * g + 3 + c] * inv;
+    p[c] = points3d[3 * static_cast<size_t>(i) + c];
+  }
+  const float u[3] = {p[0] - a[0], p[1] - a[1], p[2] - a[2]}, v[3] = {p[0] - b[0], p[1] - b[1], p[2] - b[2]};
+  const float cx = u[1] * v[2] - u[2] * v[1], cy = u[2] * v[0] - u[0] * v[2], cz = u[0] * v[1] - u[1] * v[0];
+  const float len = sqrtf((b[0] - a[0]) * (b[0] - a[0]) + (b[1] - a[1]) * (b[1] - a[1]) + (b[2] - a[2]) * (b[2] - a[2]));
+  atomicAdd(score_sums + g, sqrtf(cx * cx + cy * cy + cz * cz) / fmaxf(len, 1e-6f));
+}
+
+// finalise: lines3d_mean[g] = sums / counts, scores[g] = score_sums / counts (rows without votes: zeros)
+__global__ void line_vote_finish_kernel(int G, const float* __restrict__ sums, const float* __restrict__ counts,
+                                        const float* __restrict__ score_sums, float* __restrict__ lines3d_mean,
+                                        float* __restrict__ scores) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const float n = counts[g];
+  const float inv = n > 0.f ? 1.0f / n : 0.f;
+#pragma unroll
+  for (int c = 0; c < 6; ++c) lines3d_mean[6 * g + c] = sums[6 * g + c] * inv;
+  scores[g] = score_sums[g] * inv;
+}
+
+}  // namespace neat

@@ -21,6 +21,11 @@ struct SdfQueryParams {
   int M;
   int multires;
   float sphere_r, sphere_scale;
+  // dense-grid mode (grid_n[0] > 0): point idx = (iy * nx + ix) * nz + iz  ->  (X[ix], Y[iy], Z[iz]) with
+  // A[i] = float(lo + i * step) in float64, the last one = hi: the raveled np.meshgrid(x, y, z) of np.linspace axes
+  // that utils/plots.py:318-324 builds, generated in the kernel instead of materialising [M,3]
+  int grid_n[3];
+  double grid_lo[3], grid_hi[3], grid_step[3];
 };
 
 // positional encoding of x into the aux columns of the A tile (zero padded to 48 columns)
@@ -48,7 +53,13 @@ __device__ __forceinline__ void pe_to_aux(uint8_t* a_hi, uint8_t* a_lo, int row,
 
 // the point handled by this thread: explicit, or o + z * d with the reference's rounding (mul, then add)
 __device__ __forceinline__ void load_point(const SdfQueryParams& p, int pt, float x[3]) {
-  if (p.x) {
+  if (p.grid_n[0] > 0) {
+    const int iz = pt % p.grid_n[2], t = pt / p.grid_n[2];
+    const int idx[3] = {t % p.grid_n[0], t / p.grid_n[0], iz};
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      x[c] = static_cast<float>(idx[c] == p.grid_n[c] - 1 ? p.grid_hi[c] : p.grid_lo[c] + idx[c] * p.grid_step[c]);
+  } else if (p.x) {
     x[0] = p.x[3 * pt + 0]; x[1] = p.x[3 * pt + 1]; x[2] = p.x[3 * pt + 2];
   } else {
     const int r = pt / p.n_per_ray;

@@ -407,3 +407,57 @@ def test_fused_adam_matches_torch_adam():
     before = my_p[0].detach().clone()
     mine.step()
     assert torch.equal(before, my_p[0].detach())
+
+
+@pytest.mark.parametrize("N,Gn,seed", [(1, 1, 0), (300, 40, 1), (5000, 333, 2), (2048, 1500, 3)])
+def test_line_vote_vs_oracle(N, Gn, seed):
+    """neat_line_vote (section 8f-2) against the restatement of neat-final-parsing.py:226-260."""
+    from neat_b200 import parsing
+    from oracle import parsing_oracle as PO
+    g = torch.Generator().manual_seed(seed)
+    gt = torch.rand(Gn, 4, generator=g) * 500
+    pick = torch.randint(0, Gn, (N,), generator=g)
+    l2 = gt[pick] + torch.randn(N, 4, generator=g) * 1.5
+    flip = torch.rand(N, generator=g) < 0.5
+    l2[flip] = l2[flip][:, [2, 3, 0, 1]]
+    far = torch.rand(N, generator=g) < 0.2
+    l2[far] += 300.0                                       # some predictions have no ground-truth line nearby
+    base = torch.randn(Gn, 2, 3, generator=g)
+    l3 = base[pick] + 0.01 * torch.randn(N, 2, 3, generator=g)
+    l3[flip] = l3[flip][:, [1, 0]]
+    t = torch.rand(N, 1, generator=g)
+    p3 = l3[:, 0] * t + l3[:, 1] * (1 - t) + 0.005 * torch.randn(N, 3, generator=g)
+    labels, mean, scores, counts = parsing.vote_lines(l2.cuda(), l3.cuda(), p3.cuda(), gt.cuda(), 10.0)
+    r_labels, r_mean, r_scores, r_counts = PO.vote_lines(l2, l3, p3, gt, 10.0)
+    assert torch.equal(labels.cpu(), r_labels)
+    assert torch.equal(counts.cpu(), r_counts)
+    if len(r_labels):
+        assert G.rel_err(mean.cpu(), r_mean) < 1e-5
+        assert float((scores.cpu() - r_scores).abs().max()) <= 1e-5 * max(1.0, float(r_scores.abs().max()))
+        # end points -> global junctions (host assignment solver) as the reference does with scipy
+        gj = torch.cat([r_mean.reshape(-1, 3)[::3] + 0.001, torch.randn(50, 3, generator=g)])
+        assert parsing.match_endpoints(gj.cuda(), mean) == PO.match_endpoints(gj, r_mean)
+
+
+@pytest.mark.parametrize("name", ["toy_beta0.1", "dtu_beta0.1"])
+def test_sdf_grid_vs_oracle_and_module(name):
+    """neat_sdf_grid (section 8f-4): in-kernel grid generation == the reference's grid_points fed through
+    implicit_network(x)[:, 0] (oracle on CPU), in the reference's point order."""
+    from neat_b200 import grid
+    from neat_b200.model import VolSDFNetwork
+    from oracle import neat_oracle as O
+    g, conf, sd_np = G.load(name)
+    model = VolSDFNetwork(conf)
+    model.load_state_dict({k: T(v.copy()) for k, v in sd_np.items()}, strict=True)
+    model = model.cuda().eval()
+    res, bound = 21, (-1.3, 1.7)
+    got = grid.sdf_grid(model, res, bound)
+    pts = grid.grid_points(res, bound)
+    P, _ = G.oracle_params(conf, sd_np)
+    ref = O.sdf_forward(P, pts)[:, 0]
+    assert got.shape == (res ** 3,)
+    assert G.rel_err(got.cpu(), ref) < 1e-4
+    same = model.implicit_network(pts.cuda())[:, 0]
+    assert G.rel_err(got.cpu(), same.cpu()) < 2e-5
+    clamped = grid.sdf_grid(model, res, bound, clamp=True)
+    assert G.rel_err(clamped.cpu(), model.implicit_network.get_sdf_vals(pts.cuda()).flatten().cpu()) < 2e-5
