@@ -309,6 +309,13 @@ size_t neat_line_vote_workspace_bytes(int N, int G);
 int neat_line_vote(const float* lines2d, const float* lines3d, const float* points3d, int N, const float* gt_lines, int G,
                    float dis_threshold, void* workspace, float* lines3d_mean, float* scores, float* counts, void* stream);
 
+/* visibility_checking for ONE view (code/neat-final-parsing.py:305-337): lines3d [L,2,3] projected with project2D(K, R, T)
+ * (pose_inv [16] = world-to-camera, K 3x3 with row stride k_ld); visible[l] is SET to 1 when the squared distance to the
+ * nearest ground-truth 2D line gt_lines [G,4], in either end-point order, is < dis_threshold (never cleared: call once per
+ * view on the same buffer to accumulate "seen in any view", or on a per-view column).  mindis [L] optional.         */
+int neat_line_visibility(const float* lines3d, int L, const float* pose_inv, const float* K, int k_ld, const float* gt_lines,
+                         int G, float dis_threshold, uint8_t* visible, float* mindis, void* stream);
+
 /* ---- optimizer step: torch.optim.Adam(lr) of code/training/volsdf_train.py:178,374 ----
  * One launch for every parameter tensor: param -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps)
  * with m, v updated in place (torch's default Adam: no amsgrad, L2 weight decay added to the gradient).  grad is

@@ -738,6 +738,18 @@ int neat_line_vote(const float* lines2d, const float* lines3d, const float* poin
   return NEAT_OK;
 }
 
+int neat_line_visibility(const float* lines3d, int L, const float* pose_inv, const float* K, int k_ld, const float* gt_lines,
+                         int G, float dis_threshold, uint8_t* visible, float* mindis, void* stream) {
+  if (L < 0 || G < 0 || !pose_inv || !K || (L && (!lines3d || !visible)) || (G && !gt_lines))
+    return fail(NEAT_EINVAL, "bad argument");
+  if (L == 0) return NEAT_OK;
+  line_visibility_kernel<<<(L + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(lines3d, L, pose_inv, K, k_ld, gt_lines,
+                                                                                      G, dis_threshold, visible, mindis);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
 // ---------------------------------------------------------------- optimizer step
 namespace {
 struct AdamCache {  // one table per device: re-uploaded only when the tensor list changes (it never does in training)

@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "composite.cuh"
+
 namespace neat {
 
 constexpr int VOTE_GT_TILE = 1024;  // ground-truth lines staged per shared-memory pass (16 KB)
@@ -93,6 +95,51 @@ __global__ void line_vote_finish_kernel(int G, const float* __restrict__ sums, c
 #pragma unroll
   for (int c = 0; c < 6; ++c) lines3d_mean[6 * g + c] = sums[6 * g + c] * inv;
   scores[g] = score_sums[g] * inv;
+}
+
+// visibility_checking (code/neat-final-parsing.py:305-337) for one view: project every 3D line with project2D(K, R, T),
+// distance to the nearest ground-truth 2D line in either end-point order, visible[l] |= (min distance < threshold).
+__global__ void __launch_bounds__(256) line_visibility_kernel(const float* __restrict__ lines3d, int L,
+                                                              const float* __restrict__ pose_inv, const float* __restrict__ K,
+                                                              int k_ld, const float* __restrict__ gt, int G, float thr,
+                                                              uint8_t* __restrict__ visible, float* __restrict__ mindis) {
+  __shared__ float4 sgt[VOTE_GT_TILE];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < L;
+  float4 l = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) {
+    float K3[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) K3[3 * r + c] = K[r * k_ld + c];
+    const float* p = lines3d + 6 * static_cast<size_t>(i);
+    const float a[3] = {p[0], p[1], p[2]}, b[3] = {p[3], p[4], p[5]};
+    float ua[2], ub[2];
+    project2d(K3, pose_inv, a, ua);
+    project2d(K3, pose_inv, b, ub);
+    l = make_float4(ua[0], ua[1], ub[0], ub[1]);
+  }
+  float best = INFINITY;
+  for (int g0 = 0; g0 < G; g0 += VOTE_GT_TILE) {
+    const int n = min(VOTE_GT_TILE, G - g0);
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += blockDim.x) sgt[k] = *reinterpret_cast<const float4*>(gt + 4 * static_cast<size_t>(g0 + k));
+    __syncthreads();
+    if (live) {
+      for (int k = 0; k < n; ++k) {
+        const float4 t = sgt[k];
+        const float a0 = l.x - t.x, a1 = l.y - t.y, a2 = l.z - t.z, a3 = l.w - t.w;
+        const float b0 = l.x - t.z, b1 = l.y - t.w, b2 = l.z - t.x, b3 = l.w - t.y;
+        const float d1 = ((a0 * a0 + a1 * a1) + a2 * a2) + a3 * a3;
+        const float d2 = ((b0 * b0 + b1 * b1) + b2 * b2) + b3 * b3;
+        best = fminf(best, fminf(d1, d2));
+      }
+    }
+  }
+  if (!live) return;
+  if (mindis) mindis[i] = best;
+  if (best < thr) visible[i] = 1;
 }
 
 }  // namespace neat

@@ -73,8 +73,9 @@ __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, u
 // ask the L2 to fetch [gmem, gmem + bytes) (16-byte aligned, size % 16 == 0); no completion tracking.
 // Used by wgrad for its next tile (measured 1.60 -> 1.43 ms).  The same hint in front of the backward / normal-pass
 // epilogues' global loads made those kernels SLOWER (sdf_bwd 1.37 -> 1.57 ms) and was removed.
-// g_l2_prefetch (neat_debug_set_l2_prefetch) switches the hints off for A/B measurements.
-__constant__ int g_l2_prefetch = 1;
+// g_l2_prefetch (neat_debug_set_l2_prefetch): 0 switches the hints off, n > 0 is wgrad's prefetch distance in tiles
+// (measured at 8192 rays: distance 1 -> 11.05 ms, 2 -> 10.67 ms, 3 slower).
+__constant__ int g_l2_prefetch = 2;
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem, uint32_t bytes) {
   if (g_l2_prefetch)
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");

@@ -88,9 +88,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WJob* __rest
         bulk_g2s(sm.x_lo, xs + job.x_lo, xb, &sm.full);
         bulk_g2s(sm.y_hi, ys + job.y_hi, yb, &sm.full);
         bulk_g2s(sm.y_lo, ys + job.y_lo, yb, &sm.full);
-        if (t + 1 < my_tiles) {  // the next tile streams from HBM into the L2 while this one is multiplied
-          const uint8_t* xn = xs + static_cast<uint64_t>(job.n_split) * job.x_stride;
-          const uint8_t* yn = ys + static_cast<uint64_t>(job.n_split) * job.y_stride;
+        // the tile `dist` ahead streams from HBM into the L2 while this one is multiplied (g_l2_prefetch = dist; the
+        // first iteration also requests the tiles in between)
+        const int dist = g_l2_prefetch;
+        for (int a = (t == 0 ? 1 : dist); a <= dist; ++a) {
+          if (t + a >= my_tiles) break;
+          const uint8_t* xn = xs + static_cast<uint64_t>(a) * job.n_split * job.x_stride;
+          const uint8_t* yn = ys + static_cast<uint64_t>(a) * job.n_split * job.y_stride;
           bulk_prefetch_l2(xn + job.x_hi, xb);
           bulk_prefetch_l2(xn + job.x_lo, xb);
           bulk_prefetch_l2(yn + job.y_hi, yb);

@@ -63,3 +63,26 @@ def refine_global_junctions(model, sdf_threshold=0.05):
     order = torch.argsort(s)
     gj, s = gj[order], s[order]
     return gj, s, s.abs() < sdf_threshold
+
+
+def line_visibility(lines3d, pose, intrinsics, gt_lines, mindis_th=25.0):
+    """One view of visibility_checking (neat-final-parsing.py:314-335): lines3d [L,2,3], pose [4,4] camera-to-world,
+    intrinsics [4,4] | [3,3], gt_lines [G,4] -> (visible [L] bool, mindis [L]).  The caller ORs / counts over views
+    (`lines3d_visibility.sum(dim=1) >= min_visible_views`, :336)."""
+    lib = _lib.load()
+    dev = lines3d.device
+    if dev.type != "cuda":
+        raise _lib.NeatError("neat_b200.parsing runs on CUDA tensors only (no CPU path)")
+    l3 = lines3d.detach().to(dev, torch.float32).reshape(-1, 6).contiguous()
+    gt = gt_lines.detach().to(dev, torch.float32).reshape(-1, 4).contiguous()
+    K = intrinsics.detach().to(dev, torch.float32).contiguous()
+    pose_inv = torch.linalg.inv(pose.detach().to(dev, torch.float32)).contiguous()   # pose.inverse(), :320
+    L, Gn = l3.shape[0], gt.shape[0]
+    vis = torch.zeros(L, dtype=torch.uint8, device=dev)
+    mind = torch.full((L,), float("inf"), device=dev)
+    if L and Gn:
+        with torch.cuda.device(dev):
+            _lib.check(lib.neat_line_visibility(_P(l3.data_ptr()), L, _P(pose_inv.data_ptr()), _P(K.data_ptr()), K.shape[-1],
+                                                _P(gt.data_ptr()), Gn, float(mindis_th), _P(vis.data_ptr()),
+                                                _P(mind.data_ptr()), _P(torch.cuda.current_stream(dev).cuda_stream)))
+    return vis.bool(), mind

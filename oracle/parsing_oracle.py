@@ -42,3 +42,17 @@ def match_endpoints(global_junctions, lines3d, junc_match_threshold=0.05):
     cdist = torch.cdist(global_junctions, endpoints)
     ai, aj = linear_sum_assignment(cdist.cpu().numpy())
     return [(int(a), int(b)) for a, b in zip(ai, aj) if cdist[a, b] < junc_match_threshold]
+
+
+def line_visibility(lines3d, pose, K3, gt_lines, mindis_th=25.0):
+    """One view of visibility_checking (neat-final-parsing.py:314-335).  lines3d [L,2,3], pose [4,4], K3 [3,3],
+    gt_lines [G,4] -> (visible [L] bool, mindis [L])."""
+    from oracle import neat_oracle as O
+    proj_mat = pose.inverse()[:3]                                                  # :320
+    R, T = proj_mat[:, :3], proj_mat[:, 3:]
+    lines2d_all = O.project2d(K3, R, T, lines3d).reshape(-1, 4)                    # :324
+    dis1 = torch.sum((lines2d_all[:, None] - gt_lines[None][:, :, [0, 1, 2, 3]]) ** 2, dim=-1)   # :329
+    dis2 = torch.sum((lines2d_all[:, None] - gt_lines[None][:, :, [2, 3, 0, 1]]) ** 2, dim=-1)   # :330
+    dis = torch.min(dis1, dis2)
+    mindis, _ = dis.min(dim=1)                                                    # :333
+    return mindis < mindis_th, mindis

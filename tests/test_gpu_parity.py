@@ -461,3 +461,28 @@ def test_sdf_grid_vs_oracle_and_module(name):
     assert G.rel_err(got.cpu(), same.cpu()) < 2e-5
     clamped = grid.sdf_grid(model, res, bound, clamp=True)
     assert G.rel_err(clamped.cpu(), model.implicit_network.get_sdf_vals(pts.cuda()).flatten().cpu()) < 2e-5
+
+
+@pytest.mark.parametrize("L,Gn", [(1, 1), (700, 90), (4000, 1100)])
+def test_line_visibility_vs_oracle(L, Gn):
+    """neat_line_visibility (one view of visibility_checking, neat-final-parsing.py:305-337) vs the restatement."""
+    from neat_b200 import parsing
+    from oracle import parsing_oracle as PO
+    b = synth.make_batch(8, seed=11)
+    pose, K4 = T(b["pose"][0]), T(b["intrinsics"][0])
+    g = torch.Generator().manual_seed(L)
+    l3 = (torch.rand(L, 2, 3, generator=g) - 0.5) * 1.2
+    # ground-truth 2D lines: projections of a subset of the 3D lines (some with swapped end points) + noise, + clutter
+    from oracle import neat_oracle as O
+    pinv = pose.inverse()[:3]
+    proj = O.project2d(K4[:3, :3], pinv[:, :3], pinv[:, 3:], l3).reshape(-1, 4)
+    pick = torch.randint(0, L, (Gn,), generator=g)
+    gt = proj[pick] + torch.randn(Gn, 4, generator=g) * 2.0
+    gt[::2] = gt[::2][:, [2, 3, 0, 1]]
+    gt[::5] += 400.0
+    vis, dis = parsing.line_visibility(l3.cuda(), pose.cuda(), K4.cuda(), gt.cuda(), 25.0)
+    ref_vis, ref_dis = PO.line_visibility(l3, pose, K4[:3, :3], gt, 25.0)
+    near = (ref_dis - 25.0).abs() < 1e-2 * 25.0            # decisions exactly at the threshold may flip under fp32 rounding
+    assert torch.equal(vis.cpu()[~near], ref_vis[~near])
+    assert float(((dis.cpu() - ref_dis).abs() / ref_dis.clamp_min(1.0)).max()) < 1e-3
+    assert L == 1 or int(vis.sum()) > 0
