@@ -5,6 +5,7 @@
 #include <cmath>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -80,8 +81,9 @@ struct neat_ctx {
   float* g_scale = nullptr;
   int32_t* g_fsrc = nullptr;
   uint32_t* g_fdst = nullptr;
-  Program prog_query, prog_render, prog_head[2], prog_head_bwd[2], prog_sdf_bwd;
+  Program prog_query{}, prog_render{}, prog_head[2]{}, prog_head_bwd[2]{}, prog_sdf_bwd{};  // zero: pf_base = nullptr
   uint8_t* ones_tile = nullptr;  // X operand with column 0 = 1 (aux-plane sized, hi then lo)
+  int epilogue_prefetch = 0;  // NEAT_EPILOGUE_PREFETCH=1: producer-warp L2 hints for the backward epilogues (experiment)
   WJob* jobs_dev = nullptr;
   std::vector<WJob> jobs_last;  // what jobs_dev holds
   int jobs_cap = 0;
@@ -126,6 +128,7 @@ int neat_create(const neat_net_config* cfg, neat_ctx** out) {
     delete c;
     return fail(NEAT_EUNSUPPORTED, e.what());
   }
+  if (const char* e = std::getenv("NEAT_EPILOGUE_PREFETCH")) c->epilogue_prefetch = std::atoi(e);
   CK(cudaGetDevice(&c->device));
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, c->device));
@@ -169,13 +172,29 @@ int neat_create(const neat_net_config* cfg, neat_ctx** out) {
     const int L = P.cfg.sdf_layers, HL = P.cfg.head_layers;
     Program& b = c->prog_sdf_bwd;
     b.n = 0;
-    for (int l = 0; l < L - 1; ++l, ++b.n) b.s[b.n] = mk_step(P.sdf_f[l], b.n, 1, b.n == 0, 1);
-    for (int l = L - 1; l >= 1; --l, ++b.n) b.s[b.n] = mk_step(P.sdf_t[l], b.n, 1, l == L - 1, 1);
+    const SdfSaveLayout sfl = sdf_save_layout(L, true);
+    for (int l = 0; l < L - 1; ++l, ++b.n) {  // tangent step l: the epilogue reads sigma'_l and a_l
+      b.s[b.n] = mk_step(P.sdf_f[l], b.n, 1, b.n == 0, 1);
+      b.s[b.n].pf_off[0] = sfl.d1 + l * D1_BYTES;
+      b.s[b.n].pf_bytes[0] = D1_BYTES;
+      b.s[b.n].pf_off[1] = sfl.a + l * TILE_MAIN_BYTES;
+      b.s[b.n].pf_bytes[1] = TILE_MAIN_BYTES;
+    }
+    for (int l = L - 1; l >= 1; --l, ++b.n) {  // reverse step of layer l: the epilogue reads sigma'_{l-1} (+ its own zhat scratch)
+      b.s[b.n] = mk_step(P.sdf_t[l], b.n, 1, l == L - 1, 1);
+      b.s[b.n].pf_off[0] = sfl.d1 + (l - 1) * D1_BYTES;
+      b.s[b.n].pf_bytes[0] = D1_BYTES;
+    }
     for (int h = 0; h < 2; ++h) {
       Program& hb = c->prog_head_bwd[h];
       const std::vector<PLayer>& tr = h == 0 ? P.rend_t : P.att_t;
       hb.n = 0;
-      for (int l = HL - 1; l >= 1; --l, ++hb.n) hb.s[hb.n] = mk_step(tr[l], hb.n, 1, hb.n == 0, 1);
+      const HeadSaveLayout hsl = head_save_layout(HL);
+      for (int l = HL - 1; l >= 1; --l, ++hb.n) {  // the epilogue reads the ReLU masks = hi plane of u_l
+        hb.s[hb.n] = mk_step(tr[l], hb.n, 1, hb.n == 0, 1);
+        hb.s[hb.n].pf_off[0] = hsl.u + (l - 1) * TILE_MAIN_BYTES;
+        hb.s[hb.n].pf_bytes[0] = PLANE_MAIN_BYTES;
+      }
       hb.s[hb.n] = mk_step(tr[0], hb.n, 1, 0, 0);
       ++hb.n;
       hb.s[hb.n] = mk_step(h == 0 ? P.rend_t0_aux : P.att_t0_aux, hb.n, 0, 0, 1);
@@ -882,6 +901,10 @@ int neat_head_backward(neat_ctx* c, int head, int M, const float* out_bar, const
     return fail(NEAT_EINVAL, "bad argument");
   HeadBwdParams p{};
   p.prog = c->prog_head_bwd[head];
+  if (c->epilogue_prefetch) {
+    p.prog.pf_base = static_cast<const uint8_t*>(fwd_save);
+    p.prog.pf_stride = head_save_layout(c->plan.cfg.head_layers).total;
+  }
   p.packed = c->packed;
   p.M = M; p.HL = c->plan.cfg.head_layers; p.out_dim = head == 0 ? 3 : 6;
   p.out_bar = out_bar;
@@ -911,6 +934,10 @@ int neat_sdf_backward(neat_ctx* c, const neat_points* pts, const float* n_bar, c
   if (int e = fill_points(c, pts, p.pts)) return e;
   const neat_net_config& g = c->plan.cfg;
   p.prog = c->prog_sdf_bwd;
+  if (c->epilogue_prefetch) {  // off by default: measured slower (sdf_bwd 1.42 -> 1.52 ms), see engine.cuh producer_loop
+    p.prog.pf_base = static_cast<const uint8_t*>(fwd_save);
+    p.prog.pf_stride = sdf_save_layout(g.sdf_layers, true).total;
+  }
   p.packed = c->packed;
   p.L = g.sdf_layers; p.skip = g.sdf_skip; p.H = g.sdf_hidden; p.E = c->plan.E; p.F = g.feat;
   p.n_bar = n_bar; p.s_bar = s_bar; p.feat_bar = feat_bar; p.act = act;

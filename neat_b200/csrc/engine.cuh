@@ -76,23 +76,47 @@ __device__ __forceinline__ void engine_fini(EngineSmem<STAGES>& sm) {
   if (warp_idx_uniform() == EPI_WARPS) tmem_dealloc(sm.tmem_base, TMEM_COLS);
 }
 
-// producer warp (all lanes, converged; one elected lane issues): stream every slab of every step, for every tile
+// producer warp (all lanes, converged; one elected lane issues): stream every slab of every step, for every tile.
+// While the slabs of step i are streamed it also asks the L2 for what the epilogue of step i+1 will read from the
+// tile's record (Step::pf_*), one slice per k-step: those epilogue loads are dependent-latency bound (a thread can keep
+// one 8-column unit in flight), so turning their HBM misses (~1.2 us) into L2 hits (~0.35 us) is worth more than any
+// instruction tuning -- was the hypothesis.  MEASURED: slower either way (issued by an epilogue thread: sdf_bwd 1.37 ->
+// 1.57 ms; issued here: 1.42 -> 1.52 ms), so Program::pf_base stays nullptr unless NEAT_EPILOGUE_PREFETCH=1 asks for the
+// experiment.  A second rejected idea from the same session: dropping the fp32 sigma' and zhat tensors and rebuilding
+// them from the saved bf16 hi/lo activations (-14 % DRAM bytes for sdf_bwd) nearly doubled the executed instructions
+// (294 M -> 515 M) and cost 0.1 ms: these epilogues are instruction/latency bound, not byte bound.
 template <int STAGES>
 __device__ __forceinline__ void producer_loop(EngineSmem<STAGES>& sm, const Program& prog, const uint8_t* packed,
                                               int n_tiles) {
   uint32_t stage = 0, phase = 0;
+  const bool pf_on = prog.pf_base != nullptr && g_l2_prefetch != 0;
   for (int t = 0; t < n_tiles; ++t) {
+    const uint64_t tile = blockIdx.x + static_cast<uint64_t>(t) * gridDim.x;
     for (int i = 0; i < prog.n; ++i) {
       const PLayer w = prog.s[i].w;
       const uint32_t slab = static_cast<uint32_t>(w.npad) * 64u;
       const uint32_t bytes = prog.fast ? slab / 2 : slab;  // the hi plane is the first half of a slab
       const int nk = w.nk_main + w.nk_aux;
       const uint8_t* src = packed + w.off;
+      // prefetch target: the next step of this tile, or the first step of this CTA's next tile
+      const bool wrap = i + 1 == prog.n;
+      const Step& nx = prog.s[wrap ? 0 : i + 1];
+      const bool pf = pf_on && (!wrap || t + 1 < n_tiles);
+      const uint8_t* rec = prog.pf_base + (tile + (wrap ? gridDim.x : 0)) * prog.pf_stride;
       for (int ks = 0; ks < nk; ++ks) {
         mbar_wait(&sm.empty[stage], phase ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&sm.full[stage], bytes);
           bulk_g2s(sm.w[stage], src + static_cast<size_t>(ks) * slab, bytes, &sm.full[stage]);
+          if (pf) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              const uint32_t total = nx.pf_bytes[r];
+              const uint32_t piece = ((total + nk - 1) / nk + 127u) & ~127u;
+              const uint32_t lo = piece * ks;
+              if (lo < total) bulk_prefetch_l2(rec + nx.pf_off[r] + lo, min(piece, total - lo));
+            }
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }

@@ -32,11 +32,17 @@ struct Step {          // one GEMM of a kernel's program
   uint8_t wait_a;      // 1: wait (group by group) until the epilogue published the main columns of the A tile
   uint8_t wait_aux;    // 1: wait until the aux columns were published
   uint8_t commit_d;    // 1: signal the epilogue when this GEMM (and all before it) completed
+  // what the EPILOGUE of this step reads from the tile's read-only record (Program::pf_base + tile * pf_stride + off):
+  // the weight-producer warp asks the L2 for it one step ahead, spread over the previous step's k-steps
+  uint32_t pf_off[2];
+  uint32_t pf_bytes[2];
 };
 
 struct Program {
   int n;
   int fast;  // 0: bf16x3 (hi*hi + hi*lo + lo*hi, the parity mode); 1: plain bf16 (hi*hi only; ~1e-2 accuracy)
+  const uint8_t* pf_base;   // per-tile records the epilogues read (nullptr: no prefetching)
+  uint64_t pf_stride;
   Step s[MAX_STEPS];
 };
 

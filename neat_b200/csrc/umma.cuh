@@ -71,10 +71,10 @@ __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, u
                : "memory");
 }
 // ask the L2 to fetch [gmem, gmem + bytes) (16-byte aligned, size % 16 == 0); no completion tracking.
-// Used by wgrad for its next tile (measured 1.60 -> 1.43 ms).  The same hint in front of the backward / normal-pass
-// epilogues' global loads made those kernels SLOWER (sdf_bwd 1.37 -> 1.57 ms) and was removed.
-// g_l2_prefetch (neat_debug_set_l2_prefetch): 0 switches the hints off, n > 0 is wgrad's prefetch distance in tiles
-// (measured at 8192 rays: distance 1 -> 11.05 ms, 2 -> 10.67 ms, 3 slower).
+// Used (a) by wgrad for the tiles ahead of the one being multiplied (none: 1.60 ms, distance 1: 1.43 ms) and (b) by the
+// weight-producer warp of the backward kernels for the saved tensors the NEXT step's epilogue reads (engine.cuh).  The
+// same hint issued by an epilogue thread made sdf_bwd slower (1.37 -> 1.57 ms): the issuing warp stalls, and the tile
+// waits for its slowest warp.  g_l2_prefetch (neat_debug_set_l2_prefetch): 0 = all hints off, n > 0 = wgrad's distance.
 __constant__ int g_l2_prefetch = 2;
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem, uint32_t bytes) {
   if (g_l2_prefetch)
