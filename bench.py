@@ -126,6 +126,66 @@ def cpu_baseline(R_cpu, beta, steps, threads):
     return R_cpu / sec, sec, k
 
 
+def eval_mode(args, rank, world, dev, lib):
+    """Extra, informational: the eval-mode forward (sampler + SDF with normals + both heads + compositing + geometry,
+    no backward) over a chunk of rays per GPU; rays shard over ranks with no collective."""
+    import torch
+    import torch.distributed as dist
+    from neat_b200 import synth
+    from neat_b200 import trainer as TR
+    from neat_b200.model import VolSDFNetwork
+    torch.manual_seed(42)
+    model = VolSDFNetwork(synth.dtu_conf())
+    with torch.no_grad():
+        model.density.beta.fill_(args.beta)
+    model = model.to(dev).eval()
+    hb = TR.host_batch(args.rays, seed=1 + rank)
+    inp, _ = TR.to_device(hb, dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        model(inp)
+    barrier()
+    l0 = lib.neat_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = model(inp)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        i2, _ = TR.to_device(hb, dev)
+        o = model(i2)
+        host = o["lines3d"].cpu()  # the result a caller keeps (neat-final-parsing.py:213)
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms, ms_e2e = float(t[0]), float(t[1])
+        print(json.dumps({"metric": "eval_forward_rays_per_sec", "value": world * args.rays * args.steps / (ms * 1e-3),
+                          "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                          "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "bf16x3->f32", "data": "synthetic",
+                          "config": {"workload": "eval-mode forward, %d rays/GPU per call x 98 samples, DTU nets" % args.rays,
+                                     "beta": args.beta, "parallelism": "dp%d" % world},
+                          "e2e": {"value": world * args.rays * args.steps / (ms_e2e * 1e-3), "unit": "rays/s",
+                                  "h2d_bytes_per_step": sum(hb[k].numel() * 4 for k in ("intrinsics", "pose", "uv", "uv_proj")),
+                                  "d2h_bytes_per_step": int(host.numel() * 4)},
+                          "gpu_launches": int(lib.neat_launch_count() - l0)}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -136,6 +196,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-rays", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="train", choices=["train", "eval"],
+                    help="train: the headline train step; eval: the eval-mode forward over a chunk of `--rays` rays "
+                         "(BASELINE configs[4]: full-image inference, chunked as neat-final-parsing.py / eval.py do)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -174,6 +237,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    if args.mode == "eval":
+        return eval_mode(args, rank, world, dev, lib)
     ts = TR.TrainStep(synth.dtu_conf(), device=dev, seed=42, beta=args.beta)
     hb = TR.host_batch(args.rays, seed=1 + rank)
     inp, gt = TR.to_device(hb, dev)

@@ -580,7 +580,7 @@ int neat_camera_rays(const float* uv, const float* pose, const float* K, int R, 
 
 int neat_composite_forward(const neat_composite_args* a, void* stream) {
   if (!a || a->R <= 0 || a->S <= 0 || !a->z || !a->sdf || !a->rays_o || !a->rays_d || !a->beta_param ||
-      (a->rgb && !a->rgb_values) || (a->lines && !a->lines3d) || (!a->rgb && !a->lines))
+      (a->rgb && !a->rgb_values) || (a->lines && !a->lines3d) || (!a->rgb && !a->lines && !a->weights))
     return fail(NEAT_EINVAL, "bad argument");
   CompositeParams p{};
   p.R = a->R; p.S = a->S; p.z = a->z; p.sdf = a->sdf; p.rgb = a->rgb; p.lines = a->lines; p.normals = a->normals;

@@ -302,13 +302,23 @@ class VolSDFNetwork(nn.Module):
 
     # ------------------------------------------------------------------ reference helpers kept for callers
     def project2D(self, K, R, T, points3d):
+        """VolSDFNetwork.project2D (neat_wfr_rend_a.py:317-331) for the evaluation callers, on the projection kernel
+        (csrc/junction.cuh).  K [3,3], R [3,3], T [3,1]: world-to-camera; points3d [...,3] -> [...,2].  No gradient."""
+        import ctypes
+        rn = self._get_renderer()
+        dev = rn.ctx.device
         shape = points3d.shape
-        X = points3d.reshape(-1, 3)
-        x = (K @ (R @ X.t() + T)).t()
-        den = x[:, -1:]
-        sign = torch.where(den >= 0, torch.ones_like(den), -torch.ones_like(den))
-        eps = torch.where(den.abs() < 1e-8, torch.full_like(den, 1e-8), torch.zeros_like(den))
-        return (x / (den + eps * sign)).reshape(*shape)[..., :2]
+        X = points3d.detach().to(dev, torch.float32).reshape(-1, 3).contiguous()
+        rt = torch.zeros(4, 4, device=dev)
+        rt[:3, :3] = R.detach().to(dev, torch.float32)
+        rt[:3, 3] = T.detach().to(dev, torch.float32).reshape(3)
+        K3 = K.detach().to(dev, torch.float32).contiguous()
+        out = torch.empty(X.shape[0], 2, device=dev)
+        P = ctypes.c_void_p
+        with torch.cuda.device(dev):
+            _lib.check(rn.ctx.lib.neat_project_points(X.shape[0], P(rt.data_ptr()), P(K3.data_ptr()), K3.shape[-1],
+                                                      P(X.data_ptr()), P(out.data_ptr()), None, rn.ctx._stream()))
+        return out.reshape(*shape[:-1], 2)
 
     def cluster_dbscan(self, points, eps=0.01, min_samples=2):
         """points: [N,3] device tensor (or numpy array, as the reference passes) -> cluster centroids [C,3].
@@ -322,11 +332,15 @@ class VolSDFNetwork(nn.Module):
         return rn.dbscan(points.detach().to(rn.ctx.device, torch.float32).reshape(-1, 3).contiguous(), eps)
 
     def volume_rendering(self, z_vals, sdf):
-        sigma = self.density(sdf.reshape(-1, z_vals.shape[1]))
-        d = torch.cat([z_vals[:, 1:] - z_vals[:, :-1], torch.full_like(z_vals[:, :1], 1e10)], -1)
-        fe = d * sigma
-        sh = torch.cat([torch.zeros_like(fe[:, :1]), fe[:, :-1]], -1)
-        return (1 - torch.exp(-fe)) * torch.exp(-torch.cumsum(sh, -1))
+        """VolSDFNetwork.volume_rendering (neat_wfr_rend_a.py:540-554): weights [R,S] from depths and sdf, on the
+        compositing kernel (weights-only call).  No gradient."""
+        rn = self._get_renderer()
+        dev = rn.ctx.device
+        z = z_vals.detach().to(dev, torch.float32).contiguous()
+        R, S = z.shape
+        s = sdf.detach().to(dev, torch.float32).reshape(R, S).contiguous()
+        beta = self.density.beta.detach().reshape(1).float().contiguous()
+        return rn.composite_weights(z, s, beta)
 
     # ------------------------------------------------------------------ forward
     def forward(self, input):

@@ -180,6 +180,17 @@ class Renderer:
         _lib.check(ctx.lib.neat_composite_forward(ctypes.byref(a), ctx._stream()))
         return w, lines3d, depth, points3d
 
+    def composite_weights(self, z, sdf, beta_param):
+        """volume_rendering alone: the alpha-compositing weights [R,S]."""
+        ctx = self.ctx
+        R, S = z.shape
+        w = torch.empty(R, S, device=ctx.device)
+        zero = torch.zeros(R, 3, device=ctx.device)
+        a = _lib.CompositeArgs(R, S, _ptr(z), _ptr(sdf), None, None, None, _ptr(zero), _ptr(zero), _ptr(beta_param),
+                               self.beta_min, _ptr(w), None, None, None, None, None)
+        _lib.check(ctx.lib.neat_composite_forward(ctypes.byref(a), ctx._stream()))
+        return w
+
     def composite_rgb(self, z, sdf, rgb, cam, dirs, beta_param):
         """Second half: rgb_values = sum_i w_i rgb_i once the rendering head is done."""
         ctx = self.ctx

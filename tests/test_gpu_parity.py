@@ -486,3 +486,28 @@ def test_line_visibility_vs_oracle(L, Gn):
     assert torch.equal(vis.cpu()[~near], ref_vis[~near])
     assert float(((dis.cpu() - ref_dis).abs() / ref_dis.clamp_min(1.0)).max()) < 1e-3
     assert L == 1 or int(vis.sum()) > 0
+
+
+def test_module_helper_methods_run_on_kernels():
+    """model.project2D / model.volume_rendering (reference API kept for the evaluation callers,
+    neat_wfr_rend_a.py:317-331, 540-554) against the oracle."""
+    from neat_b200.model import VolSDFNetwork
+    from oracle import neat_oracle as O
+    g, conf, sd_np = G.load("dtu_beta0.1")
+    model = VolSDFNetwork(conf)
+    model.load_state_dict({k: T(v.copy()) for k, v in sd_np.items()}, strict=True)
+    model = model.cuda().eval()
+    gen = torch.Generator().manual_seed(0)
+    b = synth.make_batch(8, seed=2)
+    K3 = T(b["intrinsics"][0])[:3, :3]
+    pinv = T(b["pose"][0]).inverse()[:3]
+    X = torch.rand(50, 2, 3, generator=gen) - 0.5
+    got = model.project2D(K3.cuda(), pinv[:, :3].cuda(), pinv[:, 3:].cuda(), X.cuda())
+    assert got.shape == (50, 2, 2)
+    assert G.rel_err(got.cpu(), O.project2d(K3, pinv[:, :3], pinv[:, 3:], X)) < 1e-5
+    z = torch.sort(torch.rand(33, 98, generator=gen) * 6, dim=1).values
+    sdf = torch.randn(33 * 98, 1, generator=gen) * 0.3
+    w = model.volume_rendering(z.cuda(), sdf.cuda())
+    beta = float(model.density.get_beta())
+    ref = O.volume_weights(z, sdf.reshape(33, 98), torch.tensor(beta))
+    assert w.shape == (33, 98) and G.rel_err(w.cpu(), ref) < 1e-5

@@ -33,7 +33,15 @@ def _worker(rank, world, port, q):
     local = bucket.flat[:bucket.n].clone()
     bucket.scalars()[0] = float(loss)
     bucket.scalars()[1] = 1.0
+    summed = bucket.flat.clone()
     bucket.all_reduce_mean()
+    # the SUM-only variant (the 1/world scale is applied inside the Adam kernel, neat_b200.optim.Adam.grad_scale)
+    keep = bucket.flat.clone()
+    bucket.flat.copy_(summed)
+    scale = bucket.all_reduce_sum()
+    assert abs(scale - 1.0 / world) < 1e-12
+    assert torch.allclose(bucket.flat * scale, keep, atol=1e-6)
+    bucket.flat.copy_(keep)
     q.put((rank, local, bucket.flat.clone()))
     dist.barrier()
     dist.destroy_process_group()
@@ -65,3 +73,4 @@ def test_bucket_single_process_is_noop():
     before = b.flat.clone()
     b.all_reduce_mean()
     assert torch.equal(before, b.flat)
+    assert b.all_reduce_sum() == 1.0 and torch.equal(before, b.flat)

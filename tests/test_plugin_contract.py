@@ -58,20 +58,12 @@ def test_unsupported_confs_are_rejected():
         VolSDFNetwork(c)
 
 
-def test_loss_cpu_path_matches_oracle():
-    """VolSDFLoss on CPU tensors (the pure-torch mirror of loss_wfr.py used when outputs are not on CUDA) equals
-    the oracle's restatement, which is pinned against the reference."""
-    from oracle import neat_oracle as O
-    rs = np.random.RandomState(0)
-    R = 64
-    T = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))
-    out = {"rgb_values": T(rs.uniform(size=(R, 3))), "lines2d": T(rs.uniform(0, 500, size=(R, 2, 2))),
-           "lines2d_calib": T(rs.normal(size=(R, 2, 2))), "grad_theta": T(rs.normal(size=(2 * R, 3))),
-           "K": T([[560, 0, 256], [0, 560, 256], [0, 0, 1]]), "j3d_local": torch.zeros(0, 3)}
-    gt = {"rgb": T(rs.uniform(size=(1, R, 3))), "lines2d": T(np.concatenate([rs.uniform(0, 500, size=(1, R, 4)),
-                                                                             rs.uniform(0.3, 1, size=(1, R, 1))], -1))}
-    ours = VolSDFLoss(**synth.loss_conf())(out, gt)
-    ref = O.neat_loss(out, gt["rgb"][0], gt["lines2d"][0], out["K"])
-    for k in ("loss", "rgb_loss", "eikonal_loss", "line_loss", "l2d_loss"):
-        assert float(ours[k]) == pytest.approx(float(ref[k]), rel=1e-6), k
-    assert int(ours["count"]) == int(ref["count"])
+def test_loss_has_no_cpu_path():
+    """VolSDFLoss is a CUDA-kernel path only: CPU tensors raise instead of falling back to eager PyTorch (the CPU
+    restatement of loss_wfr.py is oracle.neat_oracle.neat_loss, pinned in test_oracle_golden.py)."""
+    R = 8
+    out = {"rgb_values": torch.zeros(R, 3), "lines2d": torch.zeros(R, 2, 2), "lines2d_calib": torch.zeros(R, 2, 2),
+           "grad_theta": torch.ones(2 * R, 3), "K": torch.eye(3), "j3d_local": torch.zeros(0, 3)}
+    gt = {"rgb": torch.zeros(1, R, 3), "lines2d": torch.zeros(1, R, 5)}
+    with pytest.raises(_lib.NeatError):
+        VolSDFLoss(**synth.loss_conf())(out, gt)
