@@ -153,7 +153,10 @@ __device__ __forceinline__ float interval_dstar(float a, float s0, float s1) {
 // get_error_bound (ray_sampler.py:285-293) for one ray held in shared memory; all lanes return the max
 __device__ __forceinline__ float error_bound(const RaySmem& m, int L, float beta_q) {
   const int lane = threadIdx.x & 31;
-  const int k0 = lane * SMP_C;
+  // blocked ownership sized to the CURRENT interval count: every lane owns C = ceil((L-1)/32) consecutive intervals, so
+  // all 32 lanes work at every iteration (with a fixed block of SMP_C = 20, 60 % of the lanes idle at L = 256)
+  const int C = (L - 1 + 31) >> 5;
+  const int k0 = lane * C;
   float t_int[SMP_C], t_eps[SMP_C];
   float s_int = 0.f, s_eps = 0.f;
   const float inv4b2 = 1.0f / (4.0f * beta_q * beta_q);
@@ -161,7 +164,7 @@ __device__ __forceinline__ float error_bound(const RaySmem& m, int L, float beta
   for (int j = 0; j < SMP_C; ++j) {
     const int k = k0 + j;
     float ti = 0.f, te = 0.f;
-    if (k < L - 1) {
+    if (j < C && k < L - 1) {
       const float d = m.dist[k];
       ti = d * laplace_density(m.s[k], beta_q);
       te = expf(-m.dstar[k] / beta_q) * (d * d) * inv4b2;
@@ -177,7 +180,7 @@ __device__ __forceinline__ float error_bound(const RaySmem& m, int L, float beta
   for (int j = 0; j < SMP_C; ++j) {
     const int k = k0 + j;
     p_eps += t_eps[j];  // inclusive
-    if (k < L - 1) mx = fmaxf(mx, (fminf(expf(p_eps), 1.0e6f) - 1.0f) * expf(-p_int));
+    if (j < C && k < L - 1) mx = fmaxf(mx, (fminf(expf(p_eps), 1.0e6f) - 1.0f) * expf(-p_int));
     p_int += t_int[j];
   }
   return warp_max(mx);
@@ -285,7 +288,8 @@ __global__ void __launch_bounds__(32 * SMP_WARPS) sampler_draw_kernel(SamplerPar
     const int L = p.n_eval * (iter + 1);
     load_ray(m, p, r, L);
     const float beta = p.beta[r];
-    const int k0 = lane * SMP_C;
+    const int C = (L - 1 + 31) >> 5;  // see error_bound
+    const int k0 = lane * C;
     // transmittance T[k] = exp(-sum_{j<k} dist_j sigma_j), pdf over the L-1 intervals
     float fe[SMP_C], te[SMP_C];
     float s_fe = 0.f, s_te = 0.f;
@@ -294,7 +298,7 @@ __global__ void __launch_bounds__(32 * SMP_WARPS) sampler_draw_kernel(SamplerPar
     for (int j = 0; j < SMP_C; ++j) {
       const int k = k0 + j;
       float f = 0.f, e = 0.f;
-      if (k < L - 1) {
+      if (j < C && k < L - 1) {
         const float d = m.dist[k];
         f = d * laplace_density(m.s[k], beta);
         if (more) e = expf(-m.dstar[k] / beta) * (d * d) * inv4b2;
@@ -310,7 +314,7 @@ __global__ void __launch_bounds__(32 * SMP_WARPS) sampler_draw_kernel(SamplerPar
     for (int j = 0; j < SMP_C; ++j) {
       const int k = k0 + j;
       float v = 0.f;
-      if (k < L - 1) {
+      if (j < C && k < L - 1) {
         const float T = expf(-p_fe);
         if (more) {
           p_te += te[j];
@@ -335,7 +339,7 @@ __global__ void __launch_bounds__(32 * SMP_WARPS) sampler_draw_kernel(SamplerPar
     for (int j = 0; j < SMP_C; ++j) {
       const int k = k0 + j;
       p_pdf += pdf[j];
-      if (k < L - 1) m.aux[k + 1] = p_pdf;
+      if (j < C && k < L - 1) m.aux[k + 1] = p_pdf;
     }
     __syncwarp();
     // inverse-CDF sampling (:231-249)
