@@ -28,6 +28,40 @@ struct WJob {
   int split, n_split;
 };
 
+// 16-byte vector reduction into global memory (sm_90+): one L2 transaction instead of four
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// scalar fire-and-forget reduction; a plain atomicAdd on a generic pointer compiles to a RETURNING ATOM plus a
+// shared-memory CAS fallback loop
+__device__ __forceinline__ void red_add_f32(float* addr, float a) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
+}
+// adds scale * v[0..31] to row[0..31] (columns c0.. of a dW row), skipping columns >= n_valid.  MIS = float index of
+// row[0] modulo 4 (the same for every row of a job whose leading dimension is a multiple of 4): the first (4 - MIS) % 4
+// elements and the ragged tail go out as scalar REDs, everything else as 16-byte vector REDs.  MIS < 0: scalar only.
+template <int MIS>
+__device__ __forceinline__ void flush_row32(float* row, const float* v, int n_valid, float scale) {
+  constexpr int HEAD = MIS < 0 ? 32 : (4 - MIS) % 4;
+#pragma unroll
+  for (int j = 0; j < HEAD; ++j)
+    if (j < n_valid) red_add_f32(row + j, scale * v[j]);
+#pragma unroll
+  for (int j = HEAD; j + 3 < 32; j += 4) {
+    if (j + 3 < n_valid) {
+      red_add_v4(row + j, scale * v[j], scale * v[j + 1], scale * v[j + 2], scale * v[j + 3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (j + k < n_valid) red_add_f32(row + j + k, scale * v[j + k]);
+    }
+  }
+  constexpr int TAIL = HEAD + (32 - HEAD) / 4 * 4;
+#pragma unroll
+  for (int j = TAIL; j < 32; ++j)
+    if (j < n_valid) red_add_f32(row + j, scale * v[j]);
+}
+
 constexpr int WG_X_PLANE = 128 / 8 * A_CHUNK_BYTES;  // 32768
 constexpr int WG_Y_PLANE = 256 / 8 * A_CHUNK_BYTES;    // 65536
 constexpr int WG_ONES_BYTES = 2 * A_CHUNK_BYTES;  // 16 columns
@@ -146,21 +180,28 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WJob* __rest
       const uint32_t tm = sm.tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
       const bool row_ok = i < job.x_valid;
       float* orow = job.out + static_cast<size_t>(job.row0 + i) * job.ld + job.col0;
+      // alignment class of the job's rows (uniform when ld % 4 == 0; the 32-column blocks keep it)
+      const int mis = (job.ld & 3) == 0 ? static_cast<int>((reinterpret_cast<uintptr_t>(job.out + job.col0) >> 2) & 3) : -1;
       for (int c0 = 0; c0 < job.n_cols; c0 += 32) {
         float v[32];
         tmem_ld32(tm + c0, v);   // n_cols is a multiple of 16: the upper half of the last load may be stale
         tmem_ld_wait();
         if (row_ok) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c0 + j < job.y_valid) atomicAdd(orow + c0 + j, job.scale * v[j]);
+          const int nv = job.y_valid - c0;  // valid columns of this 32-column block
+          switch (mis) {
+            case 0: flush_row32<0>(orow + c0, v, nv, job.scale); break;
+            case 1: flush_row32<1>(orow + c0, v, nv, job.scale); break;
+            case 2: flush_row32<2>(orow + c0, v, nv, job.scale); break;
+            case 3: flush_row32<3>(orow + c0, v, nv, job.scale); break;
+            default: flush_row32<-1>(orow + c0, v, nv, job.scale); break;
+          }
         }
       }
       if (job.bias) {
         float v[32];
         tmem_ld32(tm + 256, v);
         tmem_ld_wait();
-        if (row_ok) atomicAdd(job.bias + job.row0 + i, job.scale * v[0]);
+        if (row_ok) red_add_f32(job.bias + job.row0 + i, job.scale * v[0]);
       }
     }
   }
