@@ -116,8 +116,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_bwd_kernel(const __grid_c
             for (int j = 0; j < 2; ++j) mraw[g][j] = ldg128(u_hi + ((c0 >> 3) + j) * A_CHUNK_BYTES + e.row * 16);
           }
         }
+        uint8_t* zsave = brec + bl.zb + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES;  // z_bar_{l-1}
         epi_wait_d(sm, e);
-        epi_planes_free(sm, e);
         uint32_t mbits[2] = {0u, 0u};  // 16 mask bits per group (the raw vectors are dead before the accumulator loads)
 #pragma unroll
         for (int g = 0; g < N_GROUPS; ++g) {
@@ -139,11 +139,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_bwd_kernel(const __grid_c
 #pragma unroll
             for (int k = 0; k < 16; ++k)
               if (!((m >> k) & 1u)) acc[k] = 0.f;
-            store_a16(sm.a_hi, sm.a_lo, e.row, c0, acc);
+            store_a16_save(sm.a_hi, sm.a_lo, zsave, e.row, c0, acc);
           }
           epi_publish_group(sm, g);
         }
-        epi_store_main(sm, e, sm.a_hi, sm.a_lo, brec + bl.zb + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);
       }
       // ---- first layer: dL/d(feature) (step HL-1) and dL/d(normal) (step HL)
       {
@@ -293,9 +292,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
             aln = ldg128(a_lo + (c >> 3) * A_CHUNK_BYTES + e.row * 16);
           }
         };
+        uint8_t* psave = brec + bl.p + static_cast<size_t>(l) * TILE_MAIN_BYTES;  // p_{l+1}
         issue(0);
         epi_wait_d(sm, e);  // D = q_l = W_l p_l
-        epi_planes_free(sm, e);
 #pragma unroll
         for (int u = 0; u < N_UNITS; ++u) {
           const int c = epi_unit_col(e, u);
@@ -314,12 +313,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
               zh[(c + i) * TILE_M + e.row] = SP_BETA * (1.0f - s1[i]) * a[i] * q[i];  // sigma'' g_{l+1} q_l
               q[i] *= s1[i];                                                            // p_{l+1}
             }
-            store_a8(sm.a_hi, sm.a_lo, e.row, c, q);
+            store_a8_save(sm.a_hi, sm.a_lo, psave, e.row, c, q);
           }
           if ((u & 1) && l < L - 2) epi_publish_group(sm, u >> 1);  // -> F_{l+1}
         }
-        if (l == L - 2) fence_proxy_async();
-        epi_store_main(sm, e, sm.a_hi, sm.a_lo, brec + bl.p + static_cast<size_t>(l) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);  // p_{l+1}
       }
       // ---------------------------------------------------------------- z_bar_{L-1} = o_bar = [s_bar | feat_bar]
       epi_planes_free(sm, e);
@@ -373,9 +370,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
             }
           }
         };
+        uint8_t* zsave = brec + bl.zb + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES;  // z_bar_{l-1}
         issue(0);
         epi_wait_d(sm, e);  // D = W_l^T z_bar_l  (gradient w.r.t. the input of layer l)
-        epi_planes_free(sm, e);
+        if (l == L - 1) epi_planes_free(sm, e);  // the bulk store of z_bar_{L-1} out of the A planes (above)
 #pragma unroll
         for (int u = 0; u < N_UNITS; ++u) {
           const int c = epi_unit_col(e, u);
@@ -389,12 +387,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 8; ++j) gq[j] = s1[j] * gq[j] + zz[j];
-            store_a8(sm.a_hi, sm.a_lo, e.row, c, gq);
+            store_a8_save(sm.a_hi, sm.a_lo, zsave, e.row, c, gq);
           }
           if ((u & 1) && l >= 2) epi_publish_group(sm, u >> 1);  // -> T_{l-1}
         }
-        if (l < 2) fence_proxy_async();
-        epi_store_main(sm, e, sm.a_hi, sm.a_lo, brec + bl.zb + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);  // z_bar_{l-1}
       }
     }
     if (e.lead) bulk_wait0();

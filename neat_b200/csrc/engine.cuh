@@ -308,6 +308,38 @@ __device__ __forceinline__ void store_a16(uint8_t* a_hi, uint8_t* a_lo, int row,
     sts128(s_lo + j * A_CHUNK_BYTES, lo);
   }
 }
+// The same columns to the A tile AND to a saved operand tile in global memory (same chunk-major layout, hi plane then
+// lo plane, TILE_MAIN = 2 x 64 KB).  The save records used to leave the SM as 128 KB bulk (TMA) stores out of the A
+// planes; the next epilogue then had to wait until the copy engine had finished READING the planes, i.e. every layer's
+// store had to fit into the ~3 us of the next layer's MMAs -- 40 GB/s per SM, the whole HBM write bandwidth in bursts.
+// Measured with the stores disabled: 20-27 % of every training kernel.  Written from registers (each warp stores 512
+// contiguous bytes per chunk, streaming hint) nothing waits for them.  gtile == nullptr: shared memory only.
+__device__ __forceinline__ void store_a16_save(uint8_t* a_hi, uint8_t* a_lo, uint8_t* gtile, int row, int c0, const float* v) {
+  const uint32_t off = (c0 >> 3) * A_CHUNK_BYTES + row * 16;
+  const uint32_t s_hi = smem_u32(a_hi) + off, s_lo = smem_u32(a_lo) + off;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    uint4 hi, lo;
+    split8(v + 8 * j, hi, lo);
+    sts128(s_hi + j * A_CHUNK_BYTES, hi);
+    sts128(s_lo + j * A_CHUNK_BYTES, lo);
+    if (gtile) {
+      __stcs(reinterpret_cast<uint4*>(gtile + off + j * A_CHUNK_BYTES), hi);
+      __stcs(reinterpret_cast<uint4*>(gtile + (A_MAIN_COLS / 8) * A_CHUNK_BYTES + off + j * A_CHUNK_BYTES), lo);
+    }
+  }
+}
+__device__ __forceinline__ void store_a8_save(uint8_t* a_hi, uint8_t* a_lo, uint8_t* gtile, int row, int c0, const float* v) {
+  uint4 hi, lo;
+  split8(v, hi, lo);
+  const uint32_t off = (c0 >> 3) * A_CHUNK_BYTES + row * 16;
+  sts128(smem_u32(a_hi) + off, hi);
+  sts128(smem_u32(a_lo) + off, lo);
+  if (gtile) {
+    __stcs(reinterpret_cast<uint4*>(gtile + off), hi);
+    __stcs(reinterpret_cast<uint4*>(gtile + (A_MAIN_COLS / 8) * A_CHUNK_BYTES + off), lo);
+  }
+}
 __device__ __forceinline__ void store_a8(uint8_t* a_hi, uint8_t* a_lo, int row, int c0, const float* v) {
   uint4 hi, lo;
   split8(v, hi, lo);

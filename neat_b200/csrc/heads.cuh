@@ -114,8 +114,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_fwd_kernel(const __grid_c
       for (int l = 0; l < p.HL - 1; ++l) {
         const Step st = p.prog.s[l];
         const float4* bias = reinterpret_cast<const float4*>(p.packed + st.w.bias_off);
+        uint8_t* usave = tr ? rec + lay.u + static_cast<size_t>(l) * TILE_MAIN_BYTES : nullptr;  // u_{l+1}
         epi_wait_d(sm, e);
-        if (tr) epi_planes_free(sm, e);
         // (TMEM columns past npad are allocated but hold stale data: loaded unconditionally, never used)
         float nxt[16];
         tmem_ld16(e.tm + st.d_col + epi_col(e, 0), nxt);
@@ -136,11 +136,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_fwd_kernel(const __grid_c
               acc[4 * j + 2] = fmaxf(acc[4 * j + 2] + b.z, 0.f);
               acc[4 * j + 3] = fmaxf(acc[4 * j + 3] + b.w, 0.f);
             }
-            store_a16(sm.a_hi, sm.a_lo, e.row, c0, acc);
+            store_a16_save(sm.a_hi, sm.a_lo, usave, e.row, c0, acc);
           }
           epi_publish_group(sm, g);
         }
-        if (tr) epi_store_main(sm, e, sm.a_hi, sm.a_lo, rec + lay.u + static_cast<size_t>(l) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);
       }
       {
         const Step st = p.prog.s[p.HL - 1];

@@ -99,8 +99,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
         const Step st = p.prog.s[l];
         const float4* bias = reinterpret_cast<const float4*>(p.packed + st.w.bias_off);
         float* d1 = d1_base + static_cast<size_t>(l) * (256 * TILE_M);
+        uint8_t* usave = tr ? rec + lay.u + static_cast<size_t>(l) * TILE_MAIN_BYTES : nullptr;  // u_{l+1}
         epi_wait_d(sm, e);
-        if (tr) epi_planes_free(sm, e);
         // (TMEM columns past npad are allocated but hold stale data: loaded unconditionally, never used)
         float nxt[16];
         tmem_ld16(e.tm + st.d_col + epi_col(e, 0), nxt);
@@ -125,11 +125,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
                 d1[(c0 + 4 * j + k) * TILE_M + e.row] = dd;
               }
             }
-            store_a16(sm.a_hi, sm.a_lo, e.row, c0, acc);
+            store_a16_save(sm.a_hi, sm.a_lo, usave, e.row, c0, acc);
           }
           epi_publish_group(sm, g);
         }
-        if (tr) epi_store_main(sm, e, sm.a_hi, sm.a_lo, rec + lay.u + static_cast<size_t>(l) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);
       }
 
       // ------------------------------------------------------------ last layer: sdf (step L-1) + features (step L)
@@ -138,7 +137,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
         const Step ss = p.prog.s[L - 1], sf = p.prog.s[L];
         const float4* bias = reinterpret_cast<const float4*>(p.packed + sf.w.bias_off);
         epi_wait_d(sm, e);
-        if (tr) epi_planes_free(sm, e);
         if (e.j == 0) {
           float acc[16];
           tmem_ld16(e.tm + ss.d_col, acc);
@@ -183,11 +181,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
             float a[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) a[j] = d1[(c0 + j) * TILE_M + e.row] * __ldg(w_row + c0 + j);
-            store_a16(sm.a_hi, sm.a_lo, e.row, c0, a);
+            store_a16_save(sm.a_hi, sm.a_lo, tr ? rec + lay.a + static_cast<size_t>(L - 2) * TILE_MAIN_BYTES : nullptr, e.row, c0, a);
           }
           epi_publish_group(sm, g);
         }
-        if (tr) epi_store_main(sm, e, sm.a_hi, sm.a_lo, rec + lay.a + static_cast<size_t>(L - 2) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);
       }
       // ------------------------------------------------------------ transposed layers l = L-2 .. 1: D = v_l -> a_{l-1}
       for (int l = L - 2; l >= 1; --l) {
@@ -203,9 +200,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
             for (int j = 0; j < 8; ++j) s1n[j] = d1[(c + j) * TILE_M + e.row];  // written by this very thread
           }
         };
+        uint8_t* asave = tr ? rec + lay.a + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES : nullptr;  // a_{l-1}
         issue(0);
         epi_wait_d(sm, e);
-        if (tr) epi_planes_free(sm, e);
 #pragma unroll
         for (int u = 0; u < N_UNITS; ++u) {
           const int c = epi_unit_col(e, u);
@@ -226,11 +223,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] *= s1[j];
-            store_a8(sm.a_hi, sm.a_lo, e.row, c, acc);
+            store_a8_save(sm.a_hi, sm.a_lo, asave, e.row, c, acc);
           }
           if (u & 1) epi_publish_group(sm, u >> 1);
         }
-        if (tr) epi_store_main(sm, e, sm.a_hi, sm.a_lo, rec + lay.a + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES, PLANE_MAIN_BYTES);
       }
       // ------------------------------------------------------------ layer 0: D = v_0 [E]; n = J^T (v_0 + r)
       {

@@ -1,4 +1,5 @@
-"""Where does the host time of a train step go?  (synchronised wall-clock per phase)"""
+"""Where does the HOST time of a train step go?  cProfile over free-running steps (the step's only synchronisation is the
+junction hand-over), sorted by own time and by cumulative time."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -10,21 +11,19 @@ R = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 ts = TR.TrainStep(synth.dtu_conf(), device="cuda:0", seed=42, beta=0.1)
 hb = TR.host_batch(R, seed=1)
 inp, gt = TR.to_device(hb, "cuda:0")
-for _ in range(3): ts.step(inp, gt)
-torch.cuda.synchronize()
-import cProfile, pstats
-def phase(fn):
-    torch.cuda.synchronize(); t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize(); return r, (time.perf_counter() - t0) * 1e3
-acc = {}
-N = 10
-for _ in range(N):
-    out, t = phase(lambda: ts.model(inp)); acc["forward(model)"] = acc.get("forward(model)", 0) + t
-    lo, t = phase(lambda: ts.loss_fn(out, gt)); acc["loss"] = acc.get("loss", 0) + t
-    _, t = phase(lambda: ts.bucket.zero()); acc["zero"] = acc.get("zero", 0) + t
-    _, t = phase(lambda: lo["loss"].backward()); acc["backward"] = acc.get("backward", 0) + t
-    _, t = phase(lambda: ts.opt.step()); acc["adam"] = acc.get("adam", 0) + t
-print({k: round(v / N, 3) for k, v in acc.items()}, "sum", round(sum(acc.values()) / N, 3))
-pr = cProfile.Profile(); pr.enable()
 for _ in range(5): ts.step(inp, gt)
+torch.cuda.synchronize()
+N = 40
+t0 = time.perf_counter()
+for _ in range(N): ts.step(inp, gt)
+torch.cuda.synchronize()
+print("free-running: %.3f ms/step" % ((time.perf_counter() - t0) * 1e3 / N))
+import cProfile, pstats
+pr = cProfile.Profile(); pr.enable()
+for _ in range(N): ts.step(inp, gt)
 torch.cuda.synchronize(); pr.disable()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
+st = pstats.Stats(pr)
+print("==== by own time (per step = /%d)" % N)
+st.sort_stats("tottime").print_stats(38)
+print("==== by cumulative time")
+st.sort_stats("cumulative").print_stats(45)
