@@ -25,7 +25,7 @@ sys.path.insert(0, ROOT)
 
 F_SDF, F_REND, F_ATT = 1049088.0, 542720.0, 531968.0  # FLOP per point
 S = 98
-WGRAD_DRAM_BYTES_1024 = 5.927e9  # ncu, one wgrad launch at 1024 rays (profiles/r01_v4_ncu_full_summary.csv)
+WGRAD_DRAM_BYTES_1024 = 6.133e9  # ncu, one wgrad launch at 1024 rays (profiles/r01_v5_ncu_full_summary.csv)
 
 
 def peaks():
