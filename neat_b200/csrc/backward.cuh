@@ -56,7 +56,7 @@ struct HeadBwdParams {
   const float* out_bar;     // [M, out_dim]  dL/d(pre-activation output of the head)
   const uint8_t* fwd_save;  // head forward save records
   uint8_t* bwd_save;        // [n_tiles][head_bwd_layout.total]
-  float* feat_bar;          // [n_tiles][256][128] fp32
+  float* feat_bar;          // [n_tiles][64][128][4] fp32 (engine.cuh: f4_at)
   float* n_bar;             // [M,3]
   int accumulate;           // 0: overwrite feat_bar / n_bar, 1: add
 };
@@ -155,12 +155,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_bwd_kernel(const __grid_c
             float acc[16];
             tmem_ld16(e.tm + sf.d_col + c0, acc);
             tmem_ld_wait();
-            if (p.accumulate) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) acc[j] += fb[(c0 + j) * TILE_M + e.row];
+            for (int j = 0; j < 4; ++j) {
+              float4* q = f4_at(fb, c0 + 4 * j, e.row);
+              float4 o = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+              if (p.accumulate) {
+                const float4 old = *q;
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+              }
+              *q = o;
             }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) fb[(c0 + j) * TILE_M + e.row] = acc[j];
           }
         }
         if (e.j == 0) {
@@ -207,7 +211,7 @@ struct SdfBwdParams {
   int L, skip, H, E, F;
   const float* n_bar;     // [M,3]
   const float* s_bar;     // [M] or nullptr (eikonal points)
-  const float* feat_bar;  // [n_tiles][256][128] or nullptr
+  const float* feat_bar;  // [n_tiles][64][128][4] (f4_at) or nullptr
   const float* act;       // [M] or nullptr (= 1)
   const uint8_t* fwd_save;  // sdf_render training records
   uint8_t* bwd_save;        // [n_tiles][sdf_bwd_layout.total]
@@ -286,8 +290,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
         auto issue = [&](int u) {
           const int c = epi_unit_col(e, u);
           if (c < npad) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) s1n[j] = __ldg(d1 + (c + j) * TILE_M + e.row);
+            f4_unpack(__ldg(f4_at(d1, c, e.row)), s1n);
+            f4_unpack(__ldg(f4_at(d1, c + 4, e.row)), s1n + 4);
             ahn = ldg128(a_hi + (c >> 3) * A_CHUNK_BYTES + e.row * 16);
             aln = ldg128(a_lo + (c >> 3) * A_CHUNK_BYTES + e.row * 16);
           }
@@ -308,11 +312,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
             tmem_ld8(e.tm + st.d_col + c, q);
             unpack_hilo8(ah, al, a);
             tmem_ld_wait();
+            float zv[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              zh[(c + i) * TILE_M + e.row] = SP_BETA * (1.0f - s1[i]) * a[i] * q[i];  // sigma'' g_{l+1} q_l
-              q[i] *= s1[i];                                                            // p_{l+1}
+              zv[i] = SP_BETA * (1.0f - s1[i]) * a[i] * q[i];  // zhat_l = sigma'' g_{l+1} q_l
+              q[i] *= s1[i];                                     // p_{l+1}
             }
+            *f4_at(zh, c, e.row) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+            *f4_at(zh, c + 4, e.row) = make_float4(zv[4], zv[5], zv[6], zv[7]);
             store_a8_save(sm.a_hi, sm.a_lo, psave, e.row, c, q);
           }
           if ((u & 1) && l < L - 2) epi_publish_group(sm, u >> 1);  // -> F_{l+1}
@@ -328,7 +335,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
           if (c0 < npadF) {
             float v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = (fb && valid) ? __ldg(fb + (c0 + j) * TILE_M + e.row) : 0.f;
+            for (int j = 0; j < 4; ++j) {
+              const float4 t = fb ? __ldg(f4_at(fb, c0 + 4 * j, e.row)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              v[4 * j] = valid ? t.x : 0.f; v[4 * j + 1] = valid ? t.y : 0.f;
+              v[4 * j + 2] = valid ? t.z : 0.f; v[4 * j + 3] = valid ? t.w : 0.f;
+            }
             store_a16(sm.a_hi, sm.a_lo, e.row, c0, v);
           }
         }
@@ -363,11 +374,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
         auto issue = [&](int u) {
           const int c = epi_unit_col(e, u);
           if (c < ncols) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              s1n[j] = __ldg(d1 + (c + j) * TILE_M + e.row);
-              zzn[j] = zh[(c + j) * TILE_M + e.row];  // written by this very thread in the tangent sweep
-            }
+            f4_unpack(__ldg(f4_at(d1, c, e.row)), s1n);
+            f4_unpack(__ldg(f4_at(d1, c + 4, e.row)), s1n + 4);
+            f4_unpack(*f4_at(zh, c, e.row), zzn);  // written by this very thread in the tangent sweep
+            f4_unpack(*f4_at(zh, c + 4, e.row), zzn + 4);
           }
         };
         uint8_t* zsave = brec + bl.zb + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES;  // z_bar_{l-1}

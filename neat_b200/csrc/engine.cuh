@@ -231,6 +231,15 @@ __device__ __forceinline__ void unpack_hilo8(const uint4& h, const uint4& l, flo
     v[2 * i + 1] = __uint_as_float(hw[i] & 0xFFFF0000u) + __uint_as_float(lw[i] & 0xFFFF0000u);
   }
 }
+// fp32 per-tile tensors that only travel between epilogues (sigma', zhat, feat_bar) are stored [col / 4][row][4]: a thread's
+// 4 consecutive columns are ONE 16-byte access and a warp's access is 512 contiguous bytes (the first layout, [col][row],
+// cost one 4-byte access per column: 4x the load/store instructions of these LSU-bound epilogues)
+__device__ __forceinline__ float4* f4_at(float* base, int col, int row) { return reinterpret_cast<float4*>(base) + (col >> 2) * TILE_M + row; }
+__device__ __forceinline__ const float4* f4_at(const float* base, int col, int row) {
+  return reinterpret_cast<const float4*>(base) + (col >> 2) * TILE_M + row;
+}
+__device__ __forceinline__ void f4_unpack(const float4& v, float* o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+
 // after this thread finished writing its slice of group g of the A tile (and reading that part of the accumulator).
 // Every lane fences its own writes, the warp converges, ONE lane arrives: 16 arrivals per barrier phase instead of
 // 512 serialized shared-memory atomics on one word.  All publish / store helpers must be called warp-uniformly.

@@ -117,13 +117,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
             for (int j = 0; j < 4; ++j) {
               const float4 b = __ldg(bias + (c0 >> 2) + j);
               const float bb[4] = {b.x, b.y, b.z, b.w};
+              float dd[4];
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                float hv, dd;
-                softplus100_d1(acc[4 * j + k] + bb[k], hv, dd);
+                float hv;
+                softplus100_d1(acc[4 * j + k] + bb[k], hv, dd[k]);
                 acc[4 * j + k] = hv;
-                d1[(c0 + 4 * j + k) * TILE_M + e.row] = dd;
               }
+              *f4_at(d1, c0 + 4 * j, e.row) = make_float4(dd[0], dd[1], dd[2], dd[3]);
             }
             store_a16_save(sm.a_hi, sm.a_lo, usave, e.row, c0, acc);
           }
@@ -180,7 +181,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
           if (c0 < npad) {
             float a[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) a[j] = d1[(c0 + j) * TILE_M + e.row] * __ldg(w_row + c0 + j);
+            for (int j = 0; j < 4; ++j) f4_unpack(*f4_at(d1, c0 + 4 * j, e.row), a + 4 * j);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] *= __ldg(w_row + c0 + j);
             store_a16_save(sm.a_hi, sm.a_lo, tr ? rec + lay.a + static_cast<size_t>(L - 2) * TILE_MAIN_BYTES : nullptr, e.row, c0, a);
           }
           epi_publish_group(sm, g);
@@ -196,8 +199,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
         auto issue = [&](int u) {
           const int c = epi_unit_col(e, u);
           if (c < npad) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) s1n[j] = d1[(c + j) * TILE_M + e.row];  // written by this very thread
+            f4_unpack(*f4_at(d1, c, e.row), s1n);          // written by this very thread
+            f4_unpack(*f4_at(d1, c + 4, e.row), s1n + 4);
           }
         };
         uint8_t* asave = tr ? rec + lay.a + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES : nullptr;  // a_{l-1}
