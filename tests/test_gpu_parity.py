@@ -511,3 +511,56 @@ def test_module_helper_methods_run_on_kernels():
     beta = float(model.density.get_beta())
     ref = O.volume_weights(z, sdf.reshape(33, 98), torch.tensor(beta))
     assert w.shape == (33, 98) and G.rel_err(w.cpu(), ref) < 1e-5
+
+
+@pytest.mark.parametrize("conf_name,R", [("toy", 77), ("toy", 1), ("dtu", 33), ("dtu", 130)])
+def test_ragged_ray_counts_forward_backward_vs_oracle(conf_name, R):
+    """Ray counts that fill neither a 128-point tile nor a 4-ray CTA of the per-ray kernels (R x S not a multiple of 128,
+    down to a single ray): the whole training step -- outputs, loss terms and EVERY parameter gradient -- against
+    autograd through the oracle at the same sample positions (device-drawn samples handed to the oracle)."""
+    from neat_b200.loss import VolSDFLoss
+    from neat_b200.model import VolSDFNetwork
+    from oracle import neat_oracle as O
+    conf = synth.toy_conf() if conf_name == "toy" else synth.dtu_conf()
+    sd_np = synth.make_state_dict(conf, seed=5, perturb=0.15, beta=0.1)
+    model = VolSDFNetwork(conf)
+    model.load_state_dict({k: T(v.copy()) for k, v in sd_np.items()}, strict=True)
+    model = model.cuda().train()
+    model.rng = "device"
+    res = (512, 512) if conf_name == "toy" else (1200, 1600)
+    b = synth.make_batch(R, seed=4, img_res=res, focal=560.0 if conf_name == "toy" else 2900.0)
+    inp = {"intrinsics": T(b["intrinsics"]).cuda(), "uv": T(b["uv"]).cuda(), "pose": T(b["pose"]).cuda(),
+           "uv_proj": T(b["uv_proj"]).cuda(), "wireframe": [WF(b["wf_vertices"])]}
+    torch.manual_seed(7)
+    out = model(inp)
+    lo = VolSDFLoss(**synth.loss_conf())(out, {"rgb": T(b["rgb"]), "lines2d": T(b["lines2d"])})
+    lo["loss"].backward()
+    torch.cuda.synchronize()
+    st = model.last_step
+    assert st.z.shape[0] == R
+    P, leaves = G.oracle_params(conf, sd_np, track=True)
+    z_eik = ((st.eik_pts[R:].cpu() - st.cam.cpu()[None]) * st.dirs.cpu()).sum(1, keepdim=True)
+    S = st.z.shape[1]
+    sc = G.sampler_conf(conf)
+    dummy = O.SamplerRandoms(torch.zeros(R, sc.N_samples_eval), torch.zeros(R, sc.N_samples),
+                             torch.zeros(sc.N_samples_extra, dtype=torch.long), torch.zeros(R, dtype=torch.long))
+    rnd = O.TrainRandoms(dummy, st.eik_uniform.cpu())
+    oo = O.neat_forward(P, sc, T(b["intrinsics"][0]), T(b["pose"][0]), T(b["uv"][0]), T(b["uv_proj"][0]),
+                        gt_vertices=T(b["wf_vertices"]), training=True, rnd=rnd, samples=(st.z.cpu(), z_eik))
+    for k in ("rgb_values", "lines3d", "lines2d_calib", "grad_theta", "points3d", "depth"):
+        assert out[k].shape[0] == oo[k].shape[0]
+        assert G.rel_err(out[k].detach().cpu(), oo[k].detach()) < 1e-4, k
+    ol = O.neat_loss(oo, T(b["rgb"][0]), T(b["lines2d"][0]), oo["K"])
+    ol["loss"].backward()
+    for k in ("loss", "rgb_loss", "eikonal_loss", "line_loss"):
+        assert abs(float(ol[k]) - float(lo[k])) < 1e-4 * max(1.0, abs(float(ol[k]))), k
+    for n, p in model.named_parameters():
+        ref = leaves[n].grad
+        if ref is None:   # e.g. latents / ffn when no junction was matched
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, n
+            continue
+        ref = ref.numpy().astype(np.float64)
+        got = p.grad.detach().cpu().numpy().astype(np.float64)
+        norm = max(np.sqrt((ref * ref).sum()), 1e-12)
+        tol = 5e-2 if n == "density.beta" else 2e-3
+        assert np.abs(got - ref).max() <= tol * norm + 1e-9, (n, np.abs(got - ref).max() / norm)
