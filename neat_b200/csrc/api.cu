@@ -1006,7 +1006,10 @@ int neat_weight_gradients(neat_ctx* c, const neat_grad_group* groups, int n_grou
     const neat_grad_group& G = groups[gi];
     if (G.M <= 0) continue;
     const int nt = (G.M + TILE_M - 1) / TILE_M;
-    const int ns = std::max(1, std::min(8, nt / 48));
+    // tile-range splits per GEMM: ~48 tiles per CTA, at most 32 (measured: 784 tiles -> 16 splits 1.29 -> 1.22 ms vs 8;
+    // 6272 tiles -> 32 splits 10.9 -> 9.6..10.1 ms; more splits only add flush traffic).  NEAT_WGRAD_SPLIT overrides the cap.
+    static const int max_split = [] { const char* e = std::getenv("NEAT_WGRAD_SPLIT"); return e ? std::atoi(e) : 32; }();
+    const int ns = std::max(1, std::min(max_split, nt / 48));
     if (G.sdf_fwd_save && G.sdf_bwd_save) {
       const Planes pe = aux_planes(G.sdf_fwd_save, fl.total, fl.pe, c16(E));
       const Planes p0 = aux_planes(G.sdf_bwd_save, bl.total, bl.p_aux, c16(E));
