@@ -25,7 +25,8 @@ sys.path.insert(0, ROOT)
 
 F_SDF, F_REND, F_ATT = 1049088.0, 542720.0, 531968.0  # FLOP per point
 S = 98
-WGRAD_DRAM_BYTES_1024 = 6.133e9  # ncu, one wgrad launch at 1024 rays (profiles/r01_v5_ncu_full_summary.csv)
+# ncu DRAM bytes (read + write) of one launch at 1024 rays (profiles/r01_v5_ncu_full_summary.csv)
+NCU_DRAM_BYTES_1024 = {"wgrad": 6.165e9, "sdf_bwd": 5.809e9, "sdf_render": 3.073e9}
 
 
 def peaks():
@@ -315,29 +316,41 @@ def main():
                  "sampler": 128.0 * k_mean * args.rays * F_SDF,
                  "head_fwd": 0.5 * (F_REND + F_ATT) * M, "head_bwd": 0.5 * (F_REND + F_ATT) * M,  # per launch (one head)
                  "wgrad": (2 * F_SDF + F_REND + F_ATT) * M + 2 * F_SDF * 2 * args.rays}
-        # wgrad is bound by HBM, not by the tensor pipe (ncu: DRAM ~70 %, tensor ~13 %): its algorithmic bytes are the
-        # saved operand tiles it has to read ONCE: per 128-point tile 33 main tiles (128 KB:
-        # 256 columns x 128 points x bf16 hi + lo) + 5 aux tiles (24 KB) for the SDF net and 2 x (9 main + 2 aux) for the
-        # heads = 52.7 KB per render point; eikonal points carry the SDF part only (33.9 KB per point).
-        WG_SDF_B, WG_HEAD_B = (33 * 131072 + 5 * 24576) / 128.0, 2 * (9 * 131072 + 2 * 24576) / 128.0
-        hbm_bytes = {"wgrad": (WG_SDF_B + WG_HEAD_B) * M + WG_SDF_B * 2 * args.rays}
+        # The training kernels are bound by HBM at least as much as by the tensor pipe (ncu: wgrad DRAM 62 % / tensor
+        # 27 %, sdf_bwd 58 % / 20 %, sdf_render 35 % / 24 % of peak), so each of them gets BOTH fractions and the larger one
+        # names the bound.  Algorithmic bytes = compulsory HBM traffic per 128-point tile:
+        #   wgrad      reads every saved operand tile once: 33 main (128 KB: 256 columns x 128 points x bf16 hi + lo) + 5
+        #              aux (24 KB) for the SDF net, 2 x (9 main + 2 aux) for the heads = 52.7 KB per render point
+        #   sdf_bwd    reads sigma' twice (tangent + reverse sweep, 8 x 128 KB each) + a_l (8 main) + feat_bar (128 KB),
+        #              writes p (8 main + aux) and z_bar (9 main + aux) = 42.4 KB per point (the zhat scratch is L2 traffic)
+        #   sdf_render writes sigma' (8 x 128 KB), u (8 main), a (8 main), PE (aux), the feature tile = 25.2 KB per point
+        MAIN, AUX = 131072.0, 24576.0
+        WG_SDF_B, WG_HEAD_B = (33 * MAIN + 5 * AUX) / 128.0, 2 * (9 * MAIN + 2 * AUX) / 128.0
+        BWD_B = (16 * MAIN + 8 * MAIN + MAIN + (8 * MAIN + AUX) + (9 * MAIN + AUX)) / 128.0 + 20.0
+        REND_B = (8 * MAIN + 8 * MAIN + 8 * MAIN + AUX + MAIN) / 128.0 + 20.0
+        hbm_bytes = {"wgrad": (WG_SDF_B + WG_HEAD_B) * M + WG_SDF_B * 2 * args.rays,
+                     "sdf_bwd_M%d" % M: BWD_B * M, "sdf_render_M%d" % M: REND_B * M}
         shares = {k: v[1] / ms_total for k, v in timers.items()}
-        dom = max((k for k in timers if k in flops), key=lambda k: timers[k][1])
+        # dominant KERNEL = longest single launch ("sampler" is a group of up to 5 query launches + the per-ray kernels)
+        dom = max((k for k in timers if k in flops and k != "sampler"), key=lambda k: timers[k][1] / timers[k][0])
         n_l, ms_dom = timers[dom]
         sec_dom = ms_dom / n_l * 1e-3
         tensor_tflops = flops[dom] / sec_dom / 1e12
-        if dom in hbm_bytes:
-            achieved, peak, unit, bound = hbm_bytes[dom] / sec_dom / 1e9, pk["hbm_gbs"], "GB/s", "hbm"
+        tensor_frac = tensor_tflops / pk["bf16_tflops_sustained"]
+        hbm_gbs = hbm_bytes[dom] / sec_dom / 1e9 if dom in hbm_bytes else 0.0
+        hbm_frac = hbm_gbs / pk["hbm_gbs"]
+        if hbm_frac >= tensor_frac:
+            achieved, peak, unit, bound = hbm_gbs, pk["hbm_gbs"], "GB/s", "hbm"
             peak_kind = pk_kind + " copy bandwidth (read + write)"
-            note = ("achieved = ALGORITHMIC bytes (every saved operand tile read once) / CUDA-event time; `traffic` = DRAM bytes "
-                    "of one launch from ncu (the 128-row halves of a GEMM each read the Y tiles).  The same launch does "
-                    "%.1f algorithmic TFLOP/s = %.3f of the sustained bf16 tensor rate (x3 issued: bf16x3)"
-                    % (tensor_tflops, tensor_tflops / pk["bf16_tflops_sustained"]))
+            note = ("achieved = ALGORITHMIC bytes (compulsory HBM traffic of the kernel, each saved tile moved once) / "
+                    "CUDA-event time; `traffic` = DRAM bytes of one launch from ncu.  The same launch does %.1f algorithmic "
+                    "TFLOP/s = %.3f of the sustained bf16 tensor rate (x3 issued: bf16x3)" % (tensor_tflops, tensor_frac))
         else:
             achieved, peak, unit, bound = tensor_tflops, pk["bf16_tflops_sustained"], "TFLOP/s", "tensor"
             peak_kind = pk_kind + " sustained bf16 (cuBLAS)"
             note = ("achieved = ALGORITHMIC fp32-equivalent FLOPs (2*MAC) / CUDA-event time; the kernel issues 3 bf16 MMAs "
                     "per algorithmic MAC (hi*hi + hi*lo + lo*hi) to meet the 1e-4 parity bound, so the tensor pipe does 3x this")
+        ncu_traffic = NCU_DRAM_BYTES_1024.get(dom.split("_M")[0]) if args.rays == 1024 else None
         line = {"metric": "train_step_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16x3->f32", "data": "synthetic", "config": config,
@@ -348,9 +361,10 @@ def main():
                 "gpu_launches": int(launches), "clocks": clk,
                 "roofline": {"bound": bound, "kernel": dom, "achieved": achieved, "peak": peak, "unit": unit,
                              "frac": achieved / peak,
-                             # dram__bytes_read.sum + dram__bytes_write.sum of one wgrad launch at 1024 rays, from the
-                             # ncu --set full capture summarised in profiles/ (see profiles/README.md)
-                             "traffic": WGRAD_DRAM_BYTES_1024 if (dom == "wgrad" and args.rays == 1024) else None,
+                             # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at 1024 rays,
+                             # from the ncu --set full capture summarised in profiles/r01_v5_ncu_full_summary.csv
+                             "traffic": ncu_traffic,
+                             "other_bound": {"tensor_frac": round(tensor_frac, 4), "hbm_frac": round(hbm_frac, 4)},
                              "peak_kind": peak_kind, "note": note,
                              "tensor_tflops_algorithmic": {k: round(flops[k] / (timers[k][1] / timers[k][0] * 1e-3) / 1e12, 1)
                                                            for k in timers if k in flops}},
