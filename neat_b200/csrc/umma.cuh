@@ -138,6 +138,22 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One k-step of the bf16x3 product as ONE instruction sequence: D (+)= Ahi*Bhi [+ Ahi*Blo + Alo*Bhi unless `fast`], then
+// tcgen05.commit -> `bar`.  Issued by the elected lane; keeping the three MMAs, their predicates and the commit in one asm
+// block spares the per-MMA predicate set-up and lets the caller keep everything in uniform registers.
+__device__ __forceinline__ void umma_kstep_bf16x3(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                                  uint32_t idesc, uint32_t accumulate, uint32_t fast, uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred pacc, pfull;\n\t"
+      "setp.ne.b32 pacc, %6, 0;\n\t"
+      "setp.eq.b32 pfull, %7, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %3, %5, pacc;\n\t"
+      "@pfull tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %4, %5, 1;\n\t"
+      "@pfull tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %3, %5, 1;\n\t"
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t}"
+      ::"r"(d_tmem), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate), "r"(fast), "r"(smem_u32(bar))
+      : "memory");
+}
 // all previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
