@@ -7,6 +7,7 @@ weight_g,weight_v}, rendering_network.*, attraction_network.*, density.beta, lat
 input / output dict keys (code/model/networks/neat_wfr_rend_a.py:257-538).  All heavy work runs in the
 sm_100a kernels behind include/neat_b200.h; there is no PyTorch / CPU fallback."""
 import math
+import time as _time
 
 import numpy as np
 import torch
@@ -374,8 +375,9 @@ class VolSDFNetwork(nn.Module):
         st.junction_inputs = (glob.detach(), pose, K4)
         st.param_layers = self._wn_layers()
         self._packed_version = None  # the step packs its own copy
-        # the eikonal draw follows the junction block in the reference's RNG order; it is made lazily inside the
-        # step when not replayed, so do the (host-side) junction block on the detached outputs afterwards.
+        # RNG order of the reference: the sampler's draws, then the eikonal uniform_ (neat_wfr_rend_a.py:518); the junction
+        # block in between draws nothing, so the step makes the eikonal draw right after the sampler and the (host-side)
+        # junction block follows on the detached outputs.
         anchor = self.density.beta
         if not anchor.requires_grad:  # the step hangs off one differentiable input; see NeatStepFunction.forward
             anchor = anchor.detach().requires_grad_(True)
@@ -393,7 +395,6 @@ class VolSDFNetwork(nn.Module):
         # everything they need (cluster centroids, their count, the global junctions) is fetched together, and the
         # loss' assignment is handed over in the output dict so that it need not synchronise again.
         j2d_global, j2d_global_calib = _ProjectPoints.apply(glob, st.pose_inv.reshape(-1).contiguous(), K4)
-        import time as _time
         _t0 = _time.perf_counter()
         st.junction_event.synchronize()
         _t1 = _time.perf_counter()
