@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_bwd_kernel(const __grid_c
 #pragma unroll
             for (int k = 0; k < 16; ++k)
               if (!((m >> k) & 1u)) acc[k] = 0.f;
-            store_a16_save(sm.a_hi, sm.a_lo, zsave, e.row, c0, acc);
+            store_a16_save(sm.a_hi, sm.a_lo, zsave, e.row, c0, acc);  // (global stores after the publish: spills here)
           }
           epi_publish_group(sm, g);
         }

@@ -346,6 +346,30 @@ __device__ __forceinline__ void store_a16_save(uint8_t* a_hi, uint8_t* a_lo, uin
     }
   }
 }
+// The three steps of store_a16_save as separate calls, so that a kernel can put the group's publish (fence.proxy.async =
+// MEMBAR + FENCE, then the mbarrier arrive the MMA warp is waiting for) BETWEEN the shared-memory stores and the global
+// ones: the fence then does not have to wait for the global stores' round trip.
+__device__ __forceinline__ void split16(const float* v, uint4 hi[2], uint4 lo[2]) {
+  split8(v, hi[0], lo[0]);
+  split8(v + 8, hi[1], lo[1]);
+}
+__device__ __forceinline__ void sts16(uint8_t* a_hi, uint8_t* a_lo, int row, int c0, const uint4 hi[2], const uint4 lo[2]) {
+  const uint32_t off = (c0 >> 3) * A_CHUNK_BYTES + row * 16;
+  const uint32_t s_hi = smem_u32(a_hi) + off, s_lo = smem_u32(a_lo) + off;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    sts128(s_hi + j * A_CHUNK_BYTES, hi[j]);
+    sts128(s_lo + j * A_CHUNK_BYTES, lo[j]);
+  }
+}
+__device__ __forceinline__ void stg16(uint8_t* gtile, int row, int c0, const uint4 hi[2], const uint4 lo[2]) {
+  const uint32_t off = (c0 >> 3) * A_CHUNK_BYTES + row * 16;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    __stcs(reinterpret_cast<uint4*>(gtile + off + j * A_CHUNK_BYTES), hi[j]);
+    __stcs(reinterpret_cast<uint4*>(gtile + (A_MAIN_COLS / 8) * A_CHUNK_BYTES + off + j * A_CHUNK_BYTES), lo[j]);
+  }
+}
 __device__ __forceinline__ void store_a8_save(uint8_t* a_hi, uint8_t* a_lo, uint8_t* gtile, int row, int c0, const float* v) {
   uint4 hi, lo;
   split8(v, hi, lo);

@@ -129,7 +129,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_fwd_kernel(const __grid_c
 #pragma unroll
           for (int j = 0; j < 16; ++j) acc[j] = nxt[j];
           if (g + 1 < N_GROUPS) tmem_ld16(e.tm + st.d_col + epi_col(e, g + 1), nxt);
-          if (c0 < st.w.npad) {
+          uint4 hi[2], lo[2];
+          const bool has = c0 < st.w.npad;
+          if (has) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float4 b = __ldg(bias + (c0 >> 2) + j);
@@ -138,9 +140,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_fwd_kernel(const __grid_c
               acc[4 * j + 2] = fmaxf(acc[4 * j + 2] + b.z, 0.f);
               acc[4 * j + 3] = fmaxf(acc[4 * j + 3] + b.w, 0.f);
             }
-            store_a16_save(sm.a_hi, sm.a_lo, usave, e.row, c0, acc);
+            split16(acc, hi, lo);
+            sts16(sm.a_hi, sm.a_lo, e.row, c0, hi, lo);
           }
           epi_publish_group(sm, g);
+          if (has && usave) stg16(usave, e.row, c0, hi, lo);  // after the publish: nothing waits for these
         }
       }
       {

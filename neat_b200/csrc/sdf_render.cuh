@@ -112,7 +112,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
 #pragma unroll
           for (int j = 0; j < 16; ++j) acc[j] = nxt[j];
           if (g + 1 < N_GROUPS) tmem_ld16(e.tm + st.d_col + epi_col(e, g + 1), nxt);
-          if (c0 < st.w.npad) {
+          uint4 hi[2], lo[2];
+          const bool has = c0 < st.w.npad;
+          if (has) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float4 b = __ldg(bias + (c0 >> 2) + j);
@@ -126,9 +128,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
               }
               *f4_at(d1, c0 + 4 * j, e.row) = make_float4(dd[0], dd[1], dd[2], dd[3]);
             }
-            store_a16_save(sm.a_hi, sm.a_lo, usave, e.row, c0, acc);
+            split16(acc, hi, lo);
+            sts16(sm.a_hi, sm.a_lo, e.row, c0, hi, lo);
           }
           epi_publish_group(sm, g);
+          if (has && usave) stg16(usave, e.row, c0, hi, lo);  // after the publish: nothing waits for these
         }
       }
 
