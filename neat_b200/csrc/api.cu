@@ -117,25 +117,18 @@ extern "C" {
 
 const char* neat_last_error(void) { return g_err.c_str(); }
 
-int neat_create(const neat_net_config* cfg, neat_ctx** out) {
-  if (!cfg || !out) return fail(NEAT_EINVAL, "null argument");
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(NEAT_ENODEV, "no CUDA device");
-  neat_ctx* c = new neat_ctx();
+// fills a fresh context; on any error the caller (neat_create) destroys it, so every early return here is leak-free
+static int init_ctx(neat_ctx* c, const neat_net_config* cfg) {
   try {
     build_plan(*cfg, c->plan);
   } catch (const std::exception& e) {
-    delete c;
     return fail(NEAT_EUNSUPPORTED, e.what());
   }
   if (const char* e = std::getenv("NEAT_EPILOGUE_PREFETCH")) c->epilogue_prefetch = std::atoi(e);
   CK(cudaGetDevice(&c->device));
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, c->device));
-  if (prop.major != 10) {
-    delete c;
-    return fail(NEAT_ENODEV, "neat_b200 needs an sm_100a device (tcgen05/TMEM)");
-  }
+  if (prop.major != 10) return fail(NEAT_ENODEV, "neat_b200 needs an sm_100a device (tcgen05/TMEM)");
   c->num_sms = prop.multiProcessorCount;
   const GatherTables& g = c->plan.g;
   CK(cudaMalloc(&c->packed, c->plan.packed_bytes));
@@ -217,6 +210,18 @@ int neat_create(const neat_net_config* cfg, neat_ctx** out) {
                           static_cast<int>(engine_smem_bytes(RENDER_STAGES))));
   CK(cudaFuncSetAttribute(sdf_query_kernel<QUERY_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           static_cast<int>(engine_smem_bytes(QUERY_STAGES))));
+  return NEAT_OK;
+}
+
+int neat_create(const neat_net_config* cfg, neat_ctx** out) {
+  if (!cfg || !out) return fail(NEAT_EINVAL, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(NEAT_ENODEV, "no CUDA device");
+  neat_ctx* c = new neat_ctx();
+  if (int e = init_ctx(c, cfg)) {
+    neat_destroy(c);  // frees whatever was allocated before the failure; g_err keeps the message
+    return e;
+  }
   *out = c;
   return NEAT_OK;
 }
@@ -452,11 +457,11 @@ int neat_sampler_run(neat_ctx* c, const neat_sampler_config* s, const float* ray
     q.skip_flag = &w.st->done;
     if (int e = launch_query(c, q, stream)) return e;
     sampler_bounds_kernel<<<grid, 32 * SMP_WARPS, 0, st>>>(p, it);
-  ++g_launches;
+    ++g_launches;
     sampler_draw_kernel<<<grid, 32 * SMP_WARPS, 0, st>>>(p, it);
-  ++g_launches;
+    ++g_launches;
     sampler_finish_kernel<<<1, 1, 0, st>>>(w.st, it, s->max_iters);
-  ++g_launches;
+    ++g_launches;
   }
   if (n_iters_dev) CK(cudaMemcpyAsync(n_iters_dev, &w.st->n_iters, sizeof(int), cudaMemcpyDeviceToDevice, st));
   CK(cudaGetLastError());
