@@ -258,6 +258,38 @@ int neat_encodels(const float* lines, int input_height, int input_width, int hei
 int neat_point_line_attraction(const float* lines, int num_lines, int height, int width, float distance,
                                uint8_t* mask, long long* labels, float* proj_points, void* stream);
 
+/* ---- dataset pixel sampling: SceneDataset.__getitem__, code/datasets/scene_hawp_dataset.py:148-194 ----
+ * The per-image tables stay on the device; one launch per step produces every per-ray input.
+ * neat_mask_compact: `mask.nonzero()` (:173), once per image: out_idx [<= n] = ascending indices of the non-zero bytes of
+ * mask [n], *n_out (device int) = how many.
+ * neat_sample_pixels: R rays.  masked != NULL: pixel = masked[pos_j] with pos_j = perm[j] when perm != NULL (the prefix
+ * of the reference's CPU `torch.randperm(n_masked)`, :176 -- same seed, same rays) or else the j-th value of a keyed
+ * bijection of [0, n_masked) (seed, step): R distinct positions with no n-sized work (neat_pixel_permutation evaluates
+ * the same bijection on the host).  masked == NULL: pixel = first + j (the full-image branch, sampling_idx None).
+ * Outputs: uv [R,2] = (column, row) (:149-151), uv_proj [R,2] = att_points[pixel], rgb [R,3], labels_out [R],
+ * lines2d [R,5] = lines[labels[pixel]] (NULL to skip), index_out [R] = pixel (NULL to skip).                        */
+size_t neat_mask_compact_workspace_bytes(long long n);
+int neat_mask_compact(const uint8_t* mask, long long n, void* workspace, int* out_idx, int* n_out, void* stream);
+typedef struct {
+  int R, W;
+  long long first;
+  const int* masked;
+  int n_masked;
+  const long long* perm;
+  unsigned long long seed, step;
+  const float* rgb_image;    /* [HW,3] */
+  const long long* labels;   /* [HW]   */
+  const float* att_points;   /* [HW,2] */
+  const float* lines;        /* [n_lines,5] */
+  int n_lines;
+  float *uv, *uv_proj, *rgb, *lines2d;
+  long long *labels_out, *index_out;
+} neat_pixel_args;
+int neat_sample_pixels(const neat_pixel_args* a, void* stream);
+/* host function: out[i] = position drawn for ray first + i, i < count, of the (n, seed, step) bijection */
+int neat_pixel_permutation(unsigned n, unsigned long long seed, unsigned long long step, unsigned first, unsigned count,
+                           unsigned* out);
+
 /* ---- backward (replaces loss.backward() through the model, code/training/volsdf_train.py:373) ---- */
 /* Adjoint of neat_composite_forward for the outputs the reference losses consume (rgb_values, lines3d;
  * lines3d uses detached weights, neat_wfr_rend_a.py:410).  rgb_pre_bar [R,S,3] = dL/d(pre-sigmoid rgb),

@@ -49,6 +49,10 @@ SIGNATURES = {
     "neat_line_geometry": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "neat_encodels": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "neat_point_line_attraction": (_I, [_P, _I, _I, _I, ctypes.c_float, _P, _P, _P, _P]),
+    "neat_mask_compact_workspace_bytes": (ctypes.c_size_t, [ctypes.c_longlong]),
+    "neat_mask_compact": (_I, [_P, ctypes.c_longlong, _P, _P, _P, _P]),
+    "neat_sample_pixels": (_I, [_P, _P]),
+    "neat_pixel_permutation": (_I, [ctypes.c_uint, ctypes.c_ulonglong, ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_uint, _P]),
     "neat_linear_sum_assignment": (_I, [_P, _I, _I, _P, _P]),
     "neat_junction_match": (_I, [_P, _I, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "neat_project_points": (_I, [_I, _P, _P, _I, _P, _P, _P, _P]),
@@ -77,6 +81,13 @@ SIGNATURES = {
 
 class AdamTensor(ctypes.Structure):
     _fields_ = [("param", _P), ("grad", _P), ("exp_avg", _P), ("exp_avg_sq", _P), ("numel", ctypes.c_longlong)]
+
+
+class PixelArgs(ctypes.Structure):
+    _fields_ = [("R", _I), ("W", _I), ("first", ctypes.c_longlong), ("masked", _P), ("n_masked", _I), ("perm", _P),
+                ("seed", ctypes.c_ulonglong), ("step", ctypes.c_ulonglong), ("rgb_image", _P), ("labels", _P),
+                ("att_points", _P), ("lines", _P), ("n_lines", _I), ("uv", _P), ("uv_proj", _P), ("rgb", _P),
+                ("lines2d", _P), ("labels_out", _P), ("index_out", _P)]
 
 
 class CompositeBwdArgs(ctypes.Structure):

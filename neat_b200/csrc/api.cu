@@ -26,6 +26,7 @@
 #include "junction.cuh"
 #include "adam.cuh"
 #include "parsing.cuh"
+#include "pixels.cuh"
 
 using namespace neat;
 
@@ -642,6 +643,55 @@ int neat_point_line_attraction(const float* lines, int num_lines, int height, in
       lines, num_lines, height, width, distance, mask, labels, proj_points);
   ++g_launches;
   CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+// ---------------------------------------------------------------- dataset pixel sampling
+size_t neat_mask_compact_workspace_bytes(long long n) {
+  if (n <= 0) return 0;
+  return al256(sizeof(int) * static_cast<size_t>((n + PX_BLOCK - 1) / PX_BLOCK));
+}
+
+int neat_mask_compact(const uint8_t* mask, long long n, void* workspace, int* out_idx, int* n_out, void* stream) {
+  if (!mask || n <= 0 || n > 0x7fffffffLL || !workspace || !out_idx || !n_out) return fail(NEAT_EINVAL, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nb = static_cast<int>((n + PX_BLOCK - 1) / PX_BLOCK);
+  int* block = static_cast<int*>(workspace);
+  mask_count_kernel<<<nb, PX_BLOCK, 0, st>>>(mask, n, block);
+  ++g_launches;
+  mask_scan_kernel<<<1, PX_BLOCK, 0, st>>>(block, nb, n_out);
+  ++g_launches;
+  mask_scatter_kernel<<<nb, PX_BLOCK, 0, st>>>(mask, n, block, out_idx);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+int neat_sample_pixels(const neat_pixel_args* a, void* stream) {
+  if (!a || a->R < 0 || a->W <= 0 || !a->rgb_image || !a->labels || !a->att_points || !a->uv || !a->uv_proj || !a->rgb ||
+      !a->labels_out || (a->lines2d && (!a->lines || a->n_lines <= 0)) || a->first < 0)
+    return fail(NEAT_EINVAL, "bad argument");
+  if (a->masked && (a->n_masked <= 0 || (!a->perm && a->R > a->n_masked)))
+    return fail(NEAT_EINVAL, "sample_pixels: more rays than masked pixels");
+  if (a->R == 0) return NEAT_OK;
+  PixelParams p{};
+  p.R = a->R; p.W = a->W; p.first = a->first; p.masked = a->masked; p.perm = a->perm;
+  if (a->masked && !a->perm) p.draw = make_pixel_perm(static_cast<uint32_t>(a->n_masked), a->seed, a->step);
+  p.rgb_image = a->rgb_image; p.labels = a->labels; p.att_points = a->att_points; p.lines = a->lines; p.n_lines = a->n_lines;
+  p.uv = a->uv; p.uv_proj = a->uv_proj; p.rgb = a->rgb; p.lines2d = a->lines2d; p.labels_out = a->labels_out;
+  p.index_out = a->index_out;
+  sample_pixels_kernel<<<(a->R + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+int neat_pixel_permutation(unsigned n, unsigned long long seed, unsigned long long step, unsigned first, unsigned count,
+                           unsigned* out) {
+  if (n == 0 || n > 0x7fffffffu || !out || static_cast<unsigned long long>(first) + count > n)
+    return fail(NEAT_EINVAL, "bad argument");
+  const PixelPerm P = make_pixel_perm(n, seed, step);
+  for (unsigned i = 0; i < count; ++i) out[i] = px_permute(P, first + i);
   return NEAT_OK;
 }
 
