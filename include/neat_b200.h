@@ -348,6 +348,14 @@ int neat_line_vote(const float* lines2d, const float* lines3d, const float* poin
 int neat_line_visibility(const float* lines3d, int L, const float* pose_inv, const float* K, int k_ld, const float* gt_lines,
                          int G, float dis_threshold, uint8_t* visible, float* mindis, void* stream);
 
+/* get_wireframe_from_lines_and_junctions (code/neat-final-parsing.py:128-157): lines3d [N,2,3], junctions [J,3].
+ * midx [N,2] = nearest junction of each end point, matched [N] = 1 when max(snap distances) < line length (and
+ * rel_threshold <= 0: with a positive threshold the reference's `is_matched *= is_matched < thr` clears every match),
+ * graph [J,J] f32 = symmetric adjacency (overwritten), upper [J,J] u8 = its upper triangle incl. the diagonal
+ * (graph.triu() != 0; neat_mask_compact of it lists the wireframe's junction pairs in the reference's order).      */
+int neat_line_junction_graph(const float* lines3d, int N, const float* junctions, int J, float rel_threshold, int* midx,
+                             uint8_t* matched, float* graph, uint8_t* upper, void* stream);
+
 /* ---- optimizer step: torch.optim.Adam(lr) of code/training/volsdf_train.py:178,374 ----
  * One launch for every parameter tensor: param -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps)
  * with m, v updated in place (torch's default Adam: no amsgrad, L2 weight decay added to the gradient).  grad is

@@ -62,6 +62,7 @@ SIGNATURES = {
     "neat_line_vote_workspace_bytes": (ctypes.c_size_t, [_I, _I]),
     "neat_line_vote": (_I, [_P, _P, _P, _I, _P, _I, ctypes.c_float, _P, _P, _P, _P, _P]),
     "neat_line_visibility": (_I, [_P, _I, _P, _P, _I, _P, _I, ctypes.c_float, _P, _P, _P]),
+    "neat_line_junction_graph": (_I, [_P, _I, _P, _I, ctypes.c_float, _P, _P, _P, _P, _P]),
     "neat_adam_step": (_I, [_P, _I, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _I,
                            ctypes.c_float, _P]),
     "neat_loss_forward_backward": (_I, [_P, _P]),

@@ -824,6 +824,21 @@ int neat_line_visibility(const float* lines3d, int L, const float* pose_inv, con
   return NEAT_OK;
 }
 
+int neat_line_junction_graph(const float* lines3d, int N, const float* junctions, int J, float rel_threshold, int* midx,
+                             uint8_t* matched, float* graph, uint8_t* upper, void* stream) {
+  if (N < 0 || J <= 0 || !junctions || !graph || !upper || (N && (!lines3d || !midx || !matched)))
+    return fail(NEAT_EINVAL, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CK(cudaMemsetAsync(graph, 0, sizeof(float) * static_cast<size_t>(J) * J, st));
+  CK(cudaMemsetAsync(upper, 0, static_cast<size_t>(J) * J, st));
+  if (N == 0) return NEAT_OK;
+  line_junction_graph_kernel<<<(N + 255) / 256, 256, 0, st>>>(lines3d, N, junctions, J, rel_threshold > 0.f ? 1 : 0, midx,
+                                                             matched, graph, upper);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
 // ---------------------------------------------------------------- optimizer step
 namespace {
 struct AdamCache {  // one table per device: re-uploaded only when the tensor list changes (it never does in training)

@@ -142,4 +142,55 @@ __global__ void __launch_bounds__(256) line_visibility_kernel(const float* __res
   if (best < thr) visible[i] = 1;
 }
 
+// get_wireframe_from_lines_and_junctions (code/neat-final-parsing.py:128-157): every 3D line's two end points snap to
+// their nearest junction (first minimum, Euclidean); the line is matched when the larger of the two snap distances is
+// smaller than the line's own length; matched lines set graph[a][b] = graph[b][a] = 1 and upper[min(a,b)][max(a,b)] = 1
+// (the diagonal included, as graph.triu() keeps it).  Junctions are staged in shared memory, one thread per line.
+constexpr int GRAPH_J_TILE = 1024;  // 12 KB
+
+__global__ void __launch_bounds__(256) line_junction_graph_kernel(const float* __restrict__ lines3d, int N,
+                                                                  const float* __restrict__ junctions, int J, int clear_all,
+                                                                  int* __restrict__ midx, uint8_t* __restrict__ matched,
+                                                                  float* __restrict__ graph, uint8_t* __restrict__ upper) {
+  __shared__ float sj[3 * GRAPH_J_TILE];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < N;
+  float a[3] = {0.f, 0.f, 0.f}, b[3] = {0.f, 0.f, 0.f};
+  if (live) {
+    const float* p = lines3d + 6 * static_cast<size_t>(i);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { a[c] = p[c]; b[c] = p[3 + c]; }
+  }
+  float best_a = INFINITY, best_b = INFINITY;
+  int arg_a = 0, arg_b = 0;
+  for (int j0 = 0; j0 < J; j0 += GRAPH_J_TILE) {
+    const int n = min(GRAPH_J_TILE, J - j0);
+    __syncthreads();
+    for (int k = threadIdx.x; k < 3 * n; k += blockDim.x) sj[k] = junctions[3 * static_cast<size_t>(j0) + k];
+    __syncthreads();
+    if (live) {
+      for (int k = 0; k < n; ++k) {
+        const float x = sj[3 * k], y = sj[3 * k + 1], z = sj[3 * k + 2];
+        const float da = ((a[0] - x) * (a[0] - x) + (a[1] - y) * (a[1] - y)) + (a[2] - z) * (a[2] - z);
+        const float db = ((b[0] - x) * (b[0] - x) + (b[1] - y) * (b[1] - y)) + (b[2] - z) * (b[2] - z);
+        if (da < best_a) { best_a = da; arg_a = j0 + k; }
+        if (db < best_b) { best_b = db; arg_b = j0 + k; }
+      }
+    }
+  }
+  if (!live) return;
+  const float len = sqrtf(((a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1])) + (a[2] - b[2]) * (a[2] - b[2]));
+  bool ok = J > 0 && fmaxf(sqrtf(best_a), sqrtf(best_b)) < len;
+  if (clear_all) ok = false;  // rel_matching_distance_threshold > 0: `is_matched *= is_matched < thr` (:140) clears every match
+  midx[2 * i] = arg_a;
+  midx[2 * i + 1] = arg_b;
+  matched[i] = ok ? 1 : 0;
+  if (ok) {
+    const int lo = min(arg_a, arg_b), hi = max(arg_a, arg_b);
+    graph[static_cast<size_t>(lo) * J + hi] = 1.f;
+    graph[static_cast<size_t>(hi) * J + lo] = 1.f;
+    upper[static_cast<size_t>(lo) * J + hi] = 1;
+  }
+}
+
 }  // namespace neat

@@ -86,3 +86,97 @@ def line_visibility(lines3d, pose, intrinsics, gt_lines, mindis_th=25.0):
                                                 _P(gt.data_ptr()), Gn, float(mindis_th), _P(vis.data_ptr()),
                                                 _P(mind.data_ptr()), _P(torch.cuda.current_stream(dev).cuda_stream)))
     return vis.bool(), mind
+
+
+def wireframe_from_lines_and_junctions(lines, junctions, rel_matching_distance_threshold=0.01):
+    """get_wireframe_from_lines_and_junctions (neat-final-parsing.py:128-157) on the GPU: lines [N,2,3], junctions [J,3]
+    -> (graph [J,J] float, lines3d_wf [E,2,3] = junctions[graph.triu().nonzero()])."""
+    from . import dataset
+    lib = _lib.load()
+    dev = junctions.device
+    if dev.type != "cuda":
+        raise _lib.NeatError("neat_b200.parsing runs on CUDA tensors only (no CPU path)")
+    l3 = lines.detach().to(dev, torch.float32).reshape(-1, 6).contiguous()
+    jn = junctions.detach().to(dev, torch.float32).reshape(-1, 3).contiguous()
+    N, J = l3.shape[0], jn.shape[0]
+    if J == 0:
+        return torch.zeros(0, 0, device=dev), torch.zeros(0, 2, 3, device=dev)
+    midx = torch.empty(max(N, 1), 2, dtype=torch.int32, device=dev)
+    matched = torch.empty(max(N, 1), dtype=torch.uint8, device=dev)
+    graph = torch.empty(J, J, device=dev)
+    upper = torch.empty(J, J, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.neat_line_junction_graph(_P(l3.data_ptr()), N, _P(jn.data_ptr()), J,
+                                                float(rel_matching_distance_threshold), _P(midx.data_ptr()),
+                                                _P(matched.data_ptr()), _P(graph.data_ptr()), _P(upper.data_ptr()),
+                                                _P(torch.cuda.current_stream(dev).cuda_stream)))
+        pairs = dataset.nonzero_mask(upper).long()            # row-major, like graph.triu().nonzero()
+    return graph, jn[torch.stack((pairs // J, pairs % J), dim=1)]
+
+
+@torch.no_grad()
+def initial_recon(model, eval_dataloader, chunksize, *, line_dis_threshold=10, line_score_threshold=0.01,
+                  junc_match_threshold=0.05, sdf_junction_refine=True, device="cuda", **kwargs):
+    """initial_recon of code/neat-final-parsing.py:159-295, same arguments and result dict.  `eval_dataloader` yields the
+    reference's (indices, model_input, ground_truth) items (full image + `mask`; a neat_b200.dataset.DeviceScene with
+    change_sampling_idx(-1) works); the forward over the masked pixels runs in chunks of `chunksize` through `model`
+    (the plugin in eval mode), voting / scoring / graph construction in the kernels of csrc/parsing.cuh, the end-point /
+    junction assignment in the native host solver."""
+    model.eval()
+    dev = torch.device(device)
+    if sdf_junction_refine:
+        global_junctions, _, _ = refine_global_junctions(model)
+    else:
+        global_junctions = model.ffn(model.latents).detach()
+    global_junctions = global_junctions.to(dev)
+    votes = {}                                  # junction index -> number of matched end points, in first-seen order
+    lines3d_all, scores_all = [], []
+    for indices, model_input, ground_truth in eval_dataloader:
+        mask = model_input["mask"][0].to(dev)
+        uv = model_input["uv"].to(dev)[:, mask]                                        # :203
+        uv_proj = model_input["uv_proj"].to(dev)[:, mask]
+        l3, l2, p3 = [], [], []
+        for a in range(0, uv.shape[1], chunksize):                                     # utils.split_input, :210
+            s = dict(model_input)
+            s["intrinsics"], s["pose"] = model_input["intrinsics"].to(dev), model_input["pose"].to(dev)
+            s["uv"], s["uv_proj"] = uv[:, a:a + chunksize], uv_proj[:, a:a + chunksize]
+            out = model(s)
+            l3.append(out["lines3d"].detach().reshape(-1, 2, 3))
+            l2.append(out["lines2d"].detach().reshape(-1, 4))
+            p3.append(out["l3d"].detach().reshape(-1, 3))
+        if not l3:
+            continue
+        gt_lines = model_input["wireframe"][0].line_segments(0.01).to(dev)[:, :-1]        # :232
+        _, lines3d, scores, _ = vote_lines(torch.cat(l2), torch.cat(l3), torch.cat(p3), gt_lines, line_dis_threshold)
+        if lines3d.shape[0] > 0:
+            for ai, _ in match_endpoints(global_junctions, lines3d, junc_match_threshold):   # :262-268
+                votes[ai] = votes.get(ai, 0) + 1
+            lines3d_all.append(lines3d)
+            scores_all.append(scores)
+    if not lines3d_all:
+        raise _lib.NeatError("initial_recon: no view produced a line vote")
+    lines3d_all, scores_all = torch.cat(lines3d_all, dim=0), torch.cat(scores_all, dim=0)
+    lines3d_all = lines3d_all[scores_all < line_score_threshold]                        # :276
+    keep = [k for k, n in votes.items() if n > 1]                                        # :288
+    if not keep:
+        raise _lib.NeatError("initial_recon: no global junction received two end-point votes")
+    junctions3d_initial = global_junctions[torch.tensor(keep, device=dev)]
+    graph_initial, lines3d_wfi = wireframe_from_lines_and_junctions(lines3d_all, junctions3d_initial,
+                                                                    rel_matching_distance_threshold=0)
+    return {"junctions3d_initial": junctions3d_initial, "lines3d_all": lines3d_all, "graph_initial": graph_initial,
+            "lines3d_wfi": lines3d_wfi}
+
+
+@torch.no_grad()
+def visibility_checking(lines3d_all, eval_dataloader, model=None, *, mindis_th=25, min_visible_views=1, device="cuda"):
+    """visibility_checking of code/neat-final-parsing.py:305-337: keep the 3D lines whose projection lies within
+    `mindis_th` (squared pixels, either end-point order) of a detected 2D line in at least `min_visible_views` views.
+    One fused launch per view; `model` is accepted for signature compatibility (the projection is in the kernel)."""
+    dev = torch.device(device)
+    lines3d_all = lines3d_all.to(dev)
+    seen = torch.zeros(lines3d_all.shape[0], dtype=torch.int32, device=dev)
+    for indices, model_input, ground_truth in eval_dataloader:
+        gt = model_input["wireframe"][0].line_segments(0.05).to(dev)[:, :4]              # :311
+        vis, _ = line_visibility(lines3d_all, model_input["pose"][0].to(dev), model_input["intrinsics"][0].to(dev), gt, mindis_th)
+        seen += vis.int()
+    return lines3d_all[seen >= min_visible_views]

@@ -10,12 +10,19 @@ from .parallel import GradBucket
 
 
 class Wireframe:
-    """The two members of utils.hawp_util.WireframeGraph the path touches (code/utils/hawp_util.py:7-95)."""
+    """The members of utils.hawp_util.WireframeGraph the path touches (code/utils/hawp_util.py:7-95): `vertices` [J,2]
+    (the model's junction block, the loss) and `line_segments()` [E,5] (dataset lines, finalisation)."""
 
     def __init__(self, vertices, edges=None, weights=None):
         self.vertices = torch.as_tensor(vertices, dtype=torch.float32)
         self.edges = None if edges is None else torch.as_tensor(edges, dtype=torch.long)
         self.weights = None if weights is None else torch.as_tensor(weights, dtype=torch.float32)
+
+    def line_segments(self, threshold=0.05, device=None):
+        """(x1, y1, x2, y2, weight) of the edges with weight > threshold (hawp_util.py:56-69)."""
+        ok = self.weights > threshold
+        lines = torch.cat((self.vertices[self.edges[ok, 0]], self.vertices[self.edges[ok, 1]], self.weights[ok][:, None]), dim=-1)
+        return lines if device is None else lines.to(device)
 
 
 def host_batch(R, seed, pinned=True, camera_seed=1):
