@@ -786,7 +786,8 @@ int neat_junction_terms_backward(int n, int n_global, const float* j3d_local, co
 // ---------------------------------------------------------------- finalisation: per-image line voting
 size_t neat_line_vote_workspace_bytes(int N, int G) {
   if (N < 0 || G < 0) return 0;
-  return al256(sizeof(int) * 2 * static_cast<size_t>(N)) + al256(sizeof(float) * 8 * static_cast<size_t>(G));
+  return al256(sizeof(int) * 2 * static_cast<size_t>(N)) + al256(sizeof(float) * 8 * static_cast<size_t>(G)) +
+         al256(sizeof(int) * 4 * static_cast<size_t>(G));
 }
 
 int neat_line_vote(const float* lines2d, const float* lines3d, const float* points3d, int N, const float* gt_lines, int G,
@@ -799,14 +800,18 @@ int neat_line_vote(const float* lines2d, const float* lines3d, const float* poin
   b += al256(sizeof(int) * 2 * static_cast<size_t>(N));
   float* sums = reinterpret_cast<float*>(b);                 // [G,6]
   float* score_sums = sums + 6 * static_cast<size_t>(G);     // [G]
+  b += al256(sizeof(float) * 8 * static_cast<size_t>(G));
+  int* slot_count = reinterpret_cast<int*>(b);               // [G]   three-vote lines: their support points
+  int* slots = slot_count + G;                               // [G,3]
   CK(cudaMemsetAsync(sums, 0, sizeof(float) * 7 * static_cast<size_t>(G), st));
+  CK(cudaMemsetAsync(slot_count, 0, sizeof(int) * 4 * static_cast<size_t>(G), st));
   CK(cudaMemsetAsync(counts, 0, sizeof(float) * static_cast<size_t>(G), st));
   const int blocks = (2 * N + 255) / 256;
   line_vote_assign_kernel<<<blocks, 256, 0, st>>>(lines2d, lines3d, N, gt_lines, G, dis_threshold, assign, sums, counts);
   ++g_launches;
-  line_vote_score_kernel<<<blocks, 256, 0, st>>>(points3d, N, assign, sums, counts, score_sums);
+  line_vote_score_kernel<<<blocks, 256, 0, st>>>(points3d, N, assign, sums, counts, score_sums, slot_count, slots);
   ++g_launches;
-  line_vote_finish_kernel<<<(G + 127) / 128, 128, 0, st>>>(G, sums, counts, score_sums, lines3d_mean, scores);
+  line_vote_finish_kernel<<<(G + 127) / 128, 128, 0, st>>>(G, sums, counts, score_sums, points3d, slots, lines3d_mean, scores);
   ++g_launches;
   CK(cudaGetLastError());
   return NEAT_OK;

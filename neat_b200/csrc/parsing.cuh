@@ -61,15 +61,23 @@ __global__ void __launch_bounds__(256) line_vote_assign_kernel(const float* __re
   }
 }
 
-// pass 2: score_sums[g] += |(p - a) x (p - b)| / max(|b - a|, 1e-6) with (a, b) = sums[g] / counts[g], p = support point
+// pass 2: score_sums[g] += |(p - a) x (p - b)| / max(|b - a|, 1e-6) with (a, b) = sums[g] / counts[g], p = support point.
+// Lines with exactly three votes only record their three support points here (slots): the reference's torch.cross call
+// (:256) has no `dim`, and for a [3,3] input the legacy default is dimension 0 -- line_vote_finish_kernel reproduces that.
 __global__ void __launch_bounds__(256) line_vote_score_kernel(const float* __restrict__ points3d, int N, const int* __restrict__ assign,
                                                               const float* __restrict__ sums, const float* __restrict__ counts,
-                                                              float* __restrict__ score_sums) {
+                                                              float* __restrict__ score_sums, int* __restrict__ slot_count,
+                                                              int* __restrict__ slots) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= 2 * N) return;
   const int g = assign[e];
   if (g < 0) return;
   const int i = e < N ? e : e - N;
+  if (counts[g] == 3.0f) {
+    const int k = atomicAdd(slot_count + g, 1);
+    if (k < 3) slots[3 * g + k] = i;
+    return;
+  }
   const float inv = 1.0f / counts[g];
   float a[3], b[3], p[3];
 #pragma unroll
@@ -86,15 +94,49 @@ __global__ void __launch_bounds__(256) line_vote_score_kernel(const float* __res
 
 // finalise: lines3d_mean[g] = sums / counts, scores[g] = score_sums / counts (rows without votes: zeros)
 __global__ void line_vote_finish_kernel(int G, const float* __restrict__ sums, const float* __restrict__ counts,
-                                        const float* __restrict__ score_sums, float* __restrict__ lines3d_mean,
+                                        const float* __restrict__ score_sums, const float* __restrict__ points3d,
+                                        const int* __restrict__ slots, float* __restrict__ lines3d_mean,
                                         float* __restrict__ scores) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= G) return;
   const float n = counts[g];
   const float inv = n > 0.f ? 1.0f / n : 0.f;
+  float m[6];
 #pragma unroll
-  for (int c = 0; c < 6; ++c) lines3d_mean[6 * g + c] = sums[6 * g + c] * inv;
-  scores[g] = score_sums[g] * inv;
+  for (int c = 0; c < 6; ++c) {
+    m[c] = sums[6 * g + c] * inv;
+    lines3d_mean[6 * g + c] = m[c];
+  }
+  if (n != 3.0f) {
+    scores[g] = score_sums[g] * inv;
+    return;
+  }
+  // three votes: torch.cross(P - a, P - b) of [3,3] operands without `dim` crosses along dimension 0, i.e. per
+  // COORDINATE c the 3-vectors (u_0c, u_1c, u_2c) x (v_0c, v_1c, v_2c); the score is the mean over rows of the row norms
+  float u[3][3], v[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float* p = points3d + 3 * static_cast<size_t>(slots[3 * g + i]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      u[i][c] = p[c] - m[c];
+      v[i][c] = p[c] - m[3 + c];
+    }
+  }
+  const float len = sqrtf((m[3] - m[0]) * (m[3] - m[0]) + (m[4] - m[1]) * (m[4] - m[1]) + (m[5] - m[2]) * (m[5] - m[2]));
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int j = (i + 1) % 3, k = (i + 2) % 3;
+    float r2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float r = u[j][c] * v[k][c] - u[k][c] * v[j][c];
+      r2 += r * r;
+    }
+    acc += sqrtf(r2) / fmaxf(len, 1e-6f);
+  }
+  scores[g] = acc * (1.0f / 3.0f);
 }
 
 // visibility_checking (code/neat-final-parsing.py:305-337) for one view: project every 3D line with project2D(K, R, T),

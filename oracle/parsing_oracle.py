@@ -14,7 +14,7 @@ from scipy.optimize import linear_sum_assignment
 def _legacy_cross(a, b):
     """torch.cross(a, b) WITHOUT dim, as the reference calls it (:256): the deprecated default is the first dimension of
     size 3 -- the last one for [n,3] inputs unless n == 3, where it is dimension 0 (a reference quirk for labels with
-    exactly three votes; the CUDA path computes the intended per-point cross product)."""
+    exactly three votes; the CUDA path reproduces it, csrc/parsing.cuh line_vote_finish_kernel)."""
     dim = next(i for i, n in enumerate(a.shape) if n == 3)
     return torch.cross(a, b, dim=dim)
 

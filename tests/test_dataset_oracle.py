@@ -50,6 +50,13 @@ def test_pixel_permutation_is_a_bijection_and_matches_mirror(n):
         assert D.pixel_permutation(n, 1234, 7, 10, 20) == got[10:30]
 
 
+@pytest.mark.parametrize("seed,step", [(2 ** 63 + 12345, 2 ** 40 + 7), (0, 0), (2 ** 64 - 1, 2 ** 64 - 1)])
+def test_pixel_permutation_64bit_keys(seed, step):
+    from neat_b200 import dataset as D
+    got = np.asarray(D.pixel_permutation(100003, seed, step, 0, 5000))
+    assert np.array_equal(got, DO.pixel_permutation(100003, seed, step, 0, 5000)) and np.unique(got).size == 5000
+
+
 def test_pixel_permutation_prefix_is_unbiased():
     """The first 1024 of 1.92 M positions (one training step of a 1600x1200 image), over 64 steps: position deciles are
     hit uniformly (chi-square, 9 dof; 99.9 % quantile = 27.9) and no position repeats suspiciously often."""
@@ -188,6 +195,6 @@ def test_gpu_scene_feeds_the_train_step():
     losses = []
     for _ in range(4):
         _, mi, gt = next(iter(loader))           # a fresh subset of the image every step
-        losses.append(float(ts.step(mi, gt)))
+        losses.append(float(ts.step(mi, gt).detach()))
     assert all(np.isfinite(l) for l in losses) and bool(torch.isfinite(ts.bucket.flat).all())
     assert float((ts.model.implicit_network.lin0.weight_v.detach() - before).abs().max()) > 0
