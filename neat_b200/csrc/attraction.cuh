@@ -4,8 +4,11 @@
 //   point_line_attraction    == SceneDataset.compute_point_line_attraction (code/datasets/scene_hawp_dataset.py:92-146)
 //                               fused: no [num_lines, H, W] one-hot tensor is ever materialised.
 // One thread per pixel, line segments staged through shared memory, every result written exactly once (the reference
-// kernel rewrites its six output planes each time a closer segment is found).  Arithmetic uses explicit
-// round-to-nearest intrinsics (no FMA contraction) so that it is bit-identical to the scalar definition.
+// kernel rewrites its six output planes each time a closer segment is found).  Arithmetic is spelled out with explicit
+// round-to-nearest intrinsics in exactly the form nvcc gives the reference kernel at its default flags (-fmad=true):
+// every `a*a + b*b` is fma(a, a, rn(b*b)), `x1 + t*dx` is fma(t, dx, x1), the division runs in double.  That pattern was
+// read off the SASS of the reference kernel built for sm_100a (oracle/build_ref.py -> oracle/_ref/), and
+// tests/test_hawp_oracle.py::test_gpu_encodels_vs_reference_kernel checks bit-equality against that binary on the GPU.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -37,19 +40,19 @@ __device__ __forceinline__ NearestLine nearest_line(const float* __restrict__ li
     for (int i = 0; i < cnt; ++i) {
       const float x1 = sl[i].x, y1 = sl[i].y, x2 = sl[i].z, y2 = sl[i].w;
       const float dx = __fsub_rn(x2, x1), dy = __fsub_rn(y2, y1);
-      const float norm2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-      const float num_ = __fadd_rn(__fmul_rn(__fsub_rn(px, x1), dx), __fmul_rn(__fsub_rn(py, y1), dy));
+      const float norm2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
+      const float num_ = __fmaf_rn(__fsub_rn(px, x1), dx, __fmul_rn(__fsub_rn(py, y1), dy));
       float t = static_cast<float>(static_cast<double>(num_) / (static_cast<double>(norm2) + 1e-6));  // double, as the reference
       const bool flag = t <= 1.f && t >= 0.f;
       t = t < 0.f ? 0.f : t;
       t = t > 1.f ? 1.f : t;
-      const float ax = __fsub_rn(__fadd_rn(x1, __fmul_rn(t, dx)), px);
-      const float ay = __fsub_rn(__fadd_rn(y1, __fmul_rn(t, dy)), py);
-      const float dis = __fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay));
+      const float ax = __fsub_rn(__fmaf_rn(t, dx, x1), px);
+      const float ay = __fsub_rn(__fmaf_rn(t, dy, y1), py);
+      const float dis = __fmaf_rn(ax, ax, __fmul_rn(ay, ay));
       if (dis < b.dis) {
         b.dis = dis; b.ax = ax; b.ay = ay; b.t = t; b.idx = base + i; b.inside = flag;
         const float ux = __fsub_rn(x1, px), uy = __fsub_rn(y1, py), vx = __fsub_rn(x2, px), vy = __fsub_rn(y2, py);
-        const bool first = __fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)) < __fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy));
+        const bool first = __fmaf_rn(ux, ux, __fmul_rn(uy, uy)) < __fmaf_rn(vx, vx, __fmul_rn(vy, vy));
         b.ux = first ? ux : vx; b.uy = first ? uy : vy; b.vx = first ? vx : ux; b.vy = first ? vy : uy;
       }
     }

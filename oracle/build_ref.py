@@ -1,0 +1,53 @@
+"""TEST INFRASTRUCTURE ONLY -- builds the reference's own CUDA extension (`hawp.base._C`, the repo's one CUDA kernel:
+third-party/hawp/hawp/base/csrc/{binding.cpp,linesegment.cu}) from the sources WHERE THEY LIE under /root/reference,
+exactly as third-party/hawp/hawp/base/csrc/__init__.py does (torch.utils.cpp_extension.load of those two files), but
+cross-compiled for sm_100a and with the output in oracle/_ref/ (git-ignored, travels to the GPU box with the snapshot).
+The `-m gpu` test tests/test_hawp_oracle.py::test_gpu_encodels_vs_reference_kernel loads the built module on the B200
+and compares neat_encodels with the REAL reference kernel.  No reference source is copied into this repository.
+
+    python oracle/build_ref.py            # needs /root/reference; a no-op message otherwise"""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "_ref")
+NAME = "hawp_ref_C"
+REF_CSRC = os.path.join(os.environ.get("NEAT_REFERENCE_ROOT", "/root/reference"), "third-party", "hawp", "hawp", "base", "csrc")
+
+
+def built_path():
+    p = os.path.join(OUT, NAME + ".so")
+    return p if os.path.exists(p) else None
+
+
+def load_built():
+    """Import the prebuilt module (GPU box: /root/reference is absent, only oracle/_ref/ travelled)."""
+    import importlib.util
+    import torch  # noqa: F401  (the extension links against libtorch)
+    p = built_path()
+    if p is None:
+        return None
+    spec = importlib.util.spec_from_file_location(NAME, p)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def build(verbose=False):
+    srcs = [os.path.join(REF_CSRC, "binding.cpp"), os.path.join(REF_CSRC, "linesegment.cu")]
+    if not all(os.path.exists(s) for s in srcs):
+        print("reference sources not present (%s): nothing built" % REF_CSRC)
+        return built_path()
+    p = built_path()
+    if p and all(os.path.getmtime(p) >= os.path.getmtime(s) for s in srcs):
+        return p
+    os.makedirs(OUT, exist_ok=True)
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")          # no GPU here: name the target instead of probing
+    from torch.utils.cpp_extension import load
+    load(name=NAME, sources=srcs, build_directory=OUT, verbose=verbose,
+         extra_cuda_cflags=["-gencode", "arch=compute_100a,code=sm_100a"])
+    return built_path()
+
+
+if __name__ == "__main__":
+    print(build(verbose="-v" in sys.argv))

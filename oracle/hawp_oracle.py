@@ -5,13 +5,21 @@
   point_line_attraction(...)    restates SceneDataset.compute_point_line_attraction
                                 (code/datasets/scene_hawp_dataset.py:92-146).
 
-Parity status: `encode_kernel` itself is PARITY UNPINNED -- the reference kernel needs a GPU plus the hawp
-extension build, neither of which exists where the reference tree is available, and the reference ships no golden
-vectors for it.  It is a line-by-line restatement of 80 lines of scalar code (incl. the double-precision division
-caused by the `1e-6` literal).  `point_line_attraction` IS pinned: oracle/make_golden_hawp.py runs the UNMODIFIED
+Parity status: PINNED ON THE GPU BOX.  The reference kernel needs a GPU, so it cannot run where the reference tree
+lives; instead oracle/build_ref.py compiles the reference's own two source files for sm_100a into oracle/_ref/ (which
+travels to the B200 box) and tests/test_hawp_oracle.py::test_gpu_encodels_vs_reference_kernel compares this
+restatement -- and the product kernel -- with that binary bit for bit.  The restatement follows the arithmetic nvcc
+gives the kernel at its default flags, read off its SASS: `a*a + b*b` is fma(a, a, rn(b*b)), `x1 + t*dx` is
+fma(t, dx, x1), the division runs in double (the `1e-6` literal).  `point_line_attraction` is pinned here as well: oracle/make_golden_hawp.py runs the UNMODIFIED
 reference method with `_C.encodels` replaced by the restatement above and stores its outputs in
 tests/golden/hawp_abc.npz.  Only tests/ may import this module."""
 import numpy as np
+
+
+def _fma(a, b, c):
+    """float32 fma(a, b, c): the product of two float32 is exact in float64; the sum is rounded to float64 and then to
+    float32 (double rounding can differ from a true fma only when the float64 sum sits exactly on a float32 tie)."""
+    return (np.asarray(a, dtype=np.float64) * np.asarray(b, dtype=np.float64) + np.asarray(c, dtype=np.float64)).astype(np.float32)
 
 
 def encodels(lines, input_height, input_width, height, width, num_lines):
@@ -32,18 +40,18 @@ def encodels(lines, input_height, input_width, height, width, num_lines):
         x1, y1, x2, y2 = f32(lines[i, 0] * xs), f32(lines[i, 1] * ys), f32(lines[i, 2] * xs), f32(lines[i, 3] * ys)
         dx, dy = f32(x2 - x1), f32(y2 - y1)
         ux, uy, vx, vy = x1 - px, y1 - py, x2 - px, y2 - py
-        norm2 = f32(dx * dx + dy * dy)
-        num = ((px - x1) * dx + (py - y1) * dy).astype(np.float32)
+        norm2 = f32(_fma(dx, dx, f32(dy * dy)))
+        num = _fma((px - x1).astype(np.float32), dx, ((py - y1).astype(np.float32) * dy).astype(np.float32))
         t = (num.astype(np.float64) / (np.float64(norm2) + 1e-6)).astype(np.float32)   # `1e-6` is a double literal
         flag = (t <= 1) & (t >= 0.0)
         t = np.clip(t, 0.0, 1.0).astype(np.float32)
-        ax = (x1 + t * (x2 - x1) - px).astype(np.float32)
-        ay = (y1 + t * (y2 - y1) - py).astype(np.float32)
-        dis = (ax * ax + ay * ay).astype(np.float32)
+        ax = (_fma(t, dx, x1) - px).astype(np.float32)
+        ay = (_fma(t, dy, y1) - py).astype(np.float32)
+        dis = _fma(ax, ax, (ay * ay).astype(np.float32))
         upd = dis < min_dis
         min_dis = np.where(upd, dis, min_dis)
-        nu2 = (ux * ux + uy * uy).astype(np.float32)
-        nv2 = (vx * vx + vy * vy).astype(np.float32)
+        nu2 = _fma(ux, ux, (uy * uy).astype(np.float32))
+        nv2 = _fma(vx, vx, (vy * vy).astype(np.float32))
         first = nu2 < nv2
         mp[0] = np.where(upd, ax, mp[0])
         mp[1] = np.where(upd, ay, mp[1])

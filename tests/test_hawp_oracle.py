@@ -61,3 +61,26 @@ def test_gpu_encodels_bit_exact(n, H, W, ih, iw):
     assert np.array_equal(mp.cpu().numpy(), om)
     assert np.array_equal(label.cpu().numpy(), ol)
     assert np.array_equal(tmap.cpu().numpy(), ot)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,H,W,ih,iw", [(9, 512, 512, 512, 512), (1500, 96, 130, 192, 260), (1, 7, 5, 7, 5), (40, 300, 400, 1200, 1600)])
+def test_gpu_encodels_vs_reference_kernel(n, H, W, ih, iw):
+    """The REAL reference kernel (hawp.base._C.encodels, built from the reference's own two source files for sm_100a by
+    oracle/build_ref.py into oracle/_ref/) against the product kernel and against the numpy restatement, on the same
+    inputs, bit for bit.  This is what pins `encode_kernel`."""
+    from neat_b200 import attraction as A
+    from oracle import build_ref
+    ref = build_ref.load_built()
+    if ref is None:
+        pytest.skip("oracle/_ref/hawp_ref_C.so is not built (python oracle/build_ref.py needs the reference tree)")
+    rs = np.random.RandomState(100 + n)
+    lines = np.stack([rs.uniform(0, iw, n), rs.uniform(0, ih, n), rs.uniform(0, iw, n), rs.uniform(0, ih, n)], -1).astype(np.float32)
+    if n == 9:                                            # the in-repo ABC wireframe (incl. pixels equidistant to two lines)
+        lines = np.load(GOLD)["lines"][:, :4].astype(np.float32)
+    rm, rl, rt = ref.encodels(torch.from_numpy(lines).cuda(), ih, iw, H, W, n)
+    torch.cuda.synchronize()
+    mp, label, tmap = A.encodels(torch.from_numpy(lines).cuda(), ih, iw, H, W, n)
+    assert torch.equal(mp, rm) and torch.equal(label, rl) and torch.equal(tmap, rt)
+    om, ol, ot = HO.encodels(lines, ih, iw, H, W, n)
+    assert np.array_equal(rm.cpu().numpy(), om) and np.array_equal(rl.cpu().numpy(), ol) and np.array_equal(rt.cpu().numpy(), ot)
