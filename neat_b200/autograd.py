@@ -37,6 +37,10 @@ class NeatStepFunction(torch.autograd.Function):
         ctx = renderer.ctx
         lib = ctx.lib
         dev = ctx.device
+        # the save records live in named, reused workspaces (render.WorkspacePool): one step in flight at a time.
+        # backward() checks that no later forward has overwritten them instead of silently using the wrong records.
+        renderer.generation += 1
+        st.generation = renderer.generation
         layers = [tuple(None if t is None else t.detach() for t in lay) for lay in st.param_layers]
         st.wn_layers = layers
         renderer.effective_weights(layers)
@@ -106,6 +110,10 @@ class NeatStepFunction(torch.autograd.Function):
     @staticmethod
     def backward(fctx, rgb_values_bar, lines3d_bar, grad_theta_bar):
         renderer, st = fctx.renderer, fctx.st
+        if st.generation != renderer.generation:
+            raise _lib.NeatError("backward() of a training forward whose saved activations were overwritten by a later "
+                                 "forward of the same module: call loss.backward() before the next model(...) call "
+                                 "(one step in flight at a time, as in code/training/volsdf_train.py:366-374)")
         ctx = renderer.ctx
         lib, dev = ctx.lib, ctx.device
         R, S = st.R, st.S

@@ -66,6 +66,7 @@ class Renderer:
         self.pool = WorkspacePool(ctx.device)
         self._pinned = {}
         self.timers = None  # bench.py: dict name -> [(start, end) CUDA events] on the launching stream
+        self.generation = 0  # bumped by every forward that reuses the named workspaces (autograd.py checks it in backward)
 
     def timed(self, name):
         return _Timed(self, name)
@@ -141,6 +142,8 @@ class Renderer:
 
     def head_forward(self, head, pts, M, normals, feat, training=False):
         ctx = self.ctx
+        if not training:
+            self.generation += 1  # "head%d.out" is also what a pending training step's backward reads (st.rgb / st.lines)
         out = self.pool.get("head%d.out" % head, M * (3 if head == 0 else 6)).view(M, 3 if head == 0 else 6)
         save = (self.pool.get("head%d.save" % head, int(ctx.lib.neat_head_save_bytes(ctx._h, M)), torch.uint8)
                 if training else None)
@@ -303,6 +306,7 @@ class Renderer:
     def forward_eval(self, uv, pose, K, uv_proj, beta_param):
         """uv [R,2], pose [4,4], K [4,4], uv_proj [R,2] (device fp32).  Mirrors the eval branch of
         VolSDFNetwork.forward; returns the reference's output dict entries computed on device."""
+        self.generation += 1  # shares the "render" / head workspaces with a pending training step, if any
         dirs, cam = self.camera_rays(uv, pose, K)
         z, z_eik, n_it = self.sampler.get_z_vals(cam, dirs, beta_param, training=False)
         R, S = z.shape

@@ -564,3 +564,24 @@ def test_ragged_ray_counts_forward_backward_vs_oracle(conf_name, R):
         norm = max(np.sqrt((ref * ref).sum()), 1e-12)
         tol = 5e-2 if n == "density.beta" else 2e-3
         assert np.abs(got - ref).max() <= tol * norm + 1e-9, (n, np.abs(got - ref).max() / norm)
+
+
+def test_backward_after_a_later_forward_is_refused():
+    """The save records live in reused workspaces (one step in flight, as in the reference trainer): a backward whose
+    records were overwritten by a later forward raises instead of producing wrong gradients."""
+    from neat_b200 import _lib, trainer as TR
+    ts = TR.TrainStep(synth.toy_conf(), device="cuda:0", seed=0, beta=0.1, rng="device")
+    inp, gt = TR.to_device(TR.host_batch(128, seed=5), "cuda:0")
+    first = ts.loss_fn(ts.model(inp), gt)["loss"]
+    second = ts.loss_fn(ts.model(inp), gt)["loss"]
+    with pytest.raises(_lib.NeatError):
+        first.backward()
+    second.backward()                                   # the latest step is intact
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in ts.model.implicit_network.parameters())
+    third = ts.loss_fn(ts.model(inp), gt)["loss"]
+    ts.model.eval()
+    with torch.no_grad():
+        ts.model(inp)                                   # an eval forward shares the workspaces as well
+    ts.model.train()
+    with pytest.raises(_lib.NeatError):
+        third.backward()
