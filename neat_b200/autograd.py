@@ -86,7 +86,11 @@ class NeatStepFunction(torch.autograd.Function):
         w, lines3d, depth, points3d = renderer.composite_lines(z, st.sdf, st.lines, cam, dirs, beta)
         st.weights, st.depth, st.points3d = w, depth, points3d
         if st.junction_inputs is not None:
-            cent_d, n_d = renderer.dbscan_async(lines3d.view(-1, 3), 0.01)
+            if st.dbscan_enabled:
+                cent_d, n_d = renderer.dbscan_async(lines3d.view(-1, 3), 0.01)
+            else:  # abc-neat-a.conf: every attraction end point is a junction candidate (neat_wfr_rend_a.py:465-466)
+                cent_d = lines3d.view(-1, 3)
+                n_d = torch.full((1,), 2 * R, dtype=torch.int32, device=dev)
             st.junction_event, st.junction_host = renderer.to_host_async([n_d, cent_d] + list(st.junction_inputs))
         lines_done = torch.cuda.Event()
         lines_done.record(main)

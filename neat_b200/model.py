@@ -249,8 +249,9 @@ class VolSDFNetwork(nn.Module):
         self.use_median = bool(c.get("use_median", False))
         self.junction_eikonal = bool(c.get("junction_eikonal", False))
         self.use_l3d = bool(c.get("use_l3d", False))
-        if not self.dbscan_enabled or self.junction_eikonal:
-            raise _lib.NeatError("only dbscan_enabled=True, junction_eikonal=False are supported (the shipped confs)")
+        if self.junction_eikonal or (self.use_l3d and not self.dbscan_enabled):
+            raise _lib.NeatError("junction_eikonal=True and use_l3d=True (without DBSCAN) are not supported: no shipped "
+                                 "conf enables them (dtu.conf / bmvs.conf: DBSCAN; abc-neat-a.conf: every end point)")
         import weakref
         ref = weakref.ref(self)
         for m in (self.implicit_network, self.rendering_network, self.attraction_network):
@@ -373,6 +374,7 @@ class VolSDFNetwork(nn.Module):
         # single device->host transfer
         glob = self.ffn(self.latents)
         st.junction_inputs = (glob.detach(), pose, K4)
+        st.dbscan_enabled = self.dbscan_enabled
         st.param_layers = self._wn_layers()
         self._packed_version = None  # the step packs its own copy
         # RNG order of the reference: the sampler's draws, then the eikonal uniform_ (neat_wfr_rend_a.py:518); the junction

@@ -34,6 +34,15 @@ def dtu_conf():
     }
 
 
+def abc_conf():
+    """model{} of code/confs/abc-neat-a.conf:28-87: the DTU nets and sampler, but every attraction end point is a
+    junction candidate (dbscan_enabled = False), the match filter is the median cost, and 64 global junctions."""
+    c = dtu_conf()
+    c.update(dbscan_enabled=False, use_l3d=False, use_median=True)
+    c["global_junctions"] = {"num_junctions": 64, "num_layers": 2, "dim_out": 3, "dim_hidden": 256}
+    return c
+
+
 def toy_conf():
     c = dtu_conf()
     c["feature_vector_size"] = 128

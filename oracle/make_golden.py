@@ -170,6 +170,8 @@ def run_case(name, conf, R, seed_w, beta, cam, perturb=0.15):
               "j2d_local", "j3d_local", "j3d_global", "j2d_global", "j2d_local_calib", "j2d_global_calib",
               "grad_theta", "points"):
         gold["train_" + k] = to_np(out[k])
+    if "median" in out:
+        gold["train_median"] = to_np(out["median"])
     for k, v in lo.items():
         gold["loss_" + k] = np.asarray(to_np(v), dtype=np.float64)
     # parameter gradients: full for small tensors, (sum, abs-sum, 256 sampled entries) for all
@@ -194,6 +196,13 @@ def main():
     torch.set_num_threads(8)
     cams = np.load(os.path.join(ref_shim.REF_ROOT, "data/abc/00075213/cameras.npz"))
     abc_pose = cams["extrinsics"][0].astype(np.float32)
+    only = sys.argv[1:]
+    if "abc" in only or not only:
+        # abc-neat-a.conf's model block (no DBSCAN: all end points are junction candidates; median match filter;
+        # 64 global junctions), ABC camera 0
+        run_case("abc_beta0.1", synth.abc_conf(), 128, seed_w=3, beta=0.1, cam=(512, 512, 560.0, abc_pose))
+        if only:
+            return
     # toy: ABC camera 0 (f=560, 512x512), 256 rays x 64 samples, 4x128 nets
     run_case("toy_beta0.1", synth.toy_conf(), 256, seed_w=0, beta=0.1, cam=(512, 512, 560.0, abc_pose))
     # DTU nets (8x256 / 4x256), 98 samples, small ray count; two density settings (k=2.. and k=5)

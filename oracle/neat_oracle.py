@@ -50,6 +50,8 @@ class NeatParams:
     ffn_W: List[torch.Tensor] = field(default_factory=list)
     ffn_b: List[torch.Tensor] = field(default_factory=list)
     latents: Optional[torch.Tensor] = None
+    dbscan_enabled: bool = True              # neat_wfr_rend_a.py:312-315 (model conf)
+    use_median: bool = False
 
     def beta(self):
         # code/model/density.py:28-30
@@ -61,7 +63,7 @@ class NeatParams:
                           cv(self.att_W), cv(self.att_b), self.beta_param.to(dtype),
                           self.beta_min, tuple(self.skip_in), self.multires, self.multires_view,
                           self.sphere_radius, self.sphere_scale, cv(self.ffn_W), cv(self.ffn_b),
-                          None if self.latents is None else self.latents.to(dtype))
+                          None if self.latents is None else self.latents.to(dtype), self.dbscan_enabled, self.use_median)
 
 
 def weight_norm_effective(g, v):
@@ -730,24 +732,36 @@ class TrainRandoms:
 
 
 def junction_block(P: NeatParams, K, pose, lines3d, gt_vertices):
-    """neat_wfr_rend_a.py:457-496 (dbscan_enabled=True, use_median=False)."""
+    """neat_wfr_rend_a.py:457-496: candidates = DBSCAN centroids (dbscan_enabled, :459-460) or every attraction end
+    point (:465-466; use_l3d is not restated), match filter < 10 px or < median matched cost (use_median, :475-482)."""
     from scipy.optimize import linear_sum_assignment
     dt = lines3d.dtype
     Rm, T = pose_inverse_rt(pose)
     K3 = K[:3, :3]
     I3 = torch.eye(3, dtype=dt)
-    cent = dbscan_centroids(lines3d.detach().cpu().numpy().reshape(-1, 3), eps=0.01, min_samples=2)
-    j3d = torch.tensor(cent).float().to(dt).reshape(-1, 3)
+    if P.dbscan_enabled:
+        cent = dbscan_centroids(lines3d.detach().cpu().numpy().reshape(-1, 3), eps=0.01, min_samples=2)
+        j3d = torch.tensor(cent).float().to(dt).reshape(-1, 3)
+    else:
+        j3d = lines3d.detach().reshape(-1, 3)
     j2d = project2d(K3, Rm, T, j3d)
     j2d_cal = project2d(I3, Rm, T, j3d)
     gt = gt_vertices.to(dt)
     cost = ((j2d[None] - gt[:, None]) ** 2).sum(-1).sqrt()
     a0, a1 = linear_sum_assignment(cost.detach().cpu().numpy())
-    ok = cost[a0, a1] < 10
+    extra = {}
+    if P.use_median:
+        median = cost[a0, a1].detach().median()
+        if torch.isnan(median):
+            median = torch.tensor(10, dtype=torch.float32)
+        ok = cost[a0, a1] < median
+        extra["median"] = median
+    else:
+        ok = cost[a0, a1] < 10
     glob = junction_ffn(P)
     return dict(j3d_local=j3d[a1][ok], j2d_local=j2d[a1][ok], j2d_local_calib=j2d_cal[a1][ok],
                 j3d_global=glob, j2d_global=project2d(K3, Rm, T, glob),
-                j2d_global_calib=project2d(I3, Rm, T, glob))
+                j2d_global_calib=project2d(I3, Rm, T, glob), **extra)
 
 
 def neat_forward(P: NeatParams, sconf: SamplerConf, K, pose, uv, uv_proj, gt_vertices=None,

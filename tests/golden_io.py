@@ -8,7 +8,8 @@ from neat_b200 import synth
 from oracle import neat_oracle as O
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = {"toy_beta0.1": synth.toy_conf, "dtu_beta0.1": synth.dtu_conf, "dtu_beta0.01": synth.dtu_conf}
+CASES = {"toy_beta0.1": synth.toy_conf, "dtu_beta0.1": synth.dtu_conf, "dtu_beta0.01": synth.dtu_conf,
+         "abc_beta0.1": synth.abc_conf}
 
 
 def load(name):
@@ -28,6 +29,7 @@ def oracle_params(conf, sd_np, dtype=torch.float32, track=False):
                                  multires_view=conf["rendering_network"]["multires_view"],
                                  sphere_radius=conf["scene_bounding_sphere"], sphere_scale=ci["sphere_scale"],
                                  beta_min=conf["density"]["beta_min"], track=track)
+    P.dbscan_enabled, P.use_median = bool(conf.get("dbscan_enabled", True)), bool(conf.get("use_median", False))
     return P, sd
 
 
