@@ -10,8 +10,10 @@ the per-step CPU `mask.nonzero()`, `randperm`, fancy-index gathers and host-to-d
 
 File loading (images, cameras.npz, the HAWP json files, `SceneDataset.__init__` :18-91) stays with the reference's loaders:
 pass their arrays to `add_image`.  `rng = "reference"` (default) draws the subset with the same CPU-generator call as
-the reference (`torch.randperm(n_masked)[:R]`, :176), so the same seed gives the same rays; `rng = "device"` draws R
-distinct masked pixels inside the gather kernel (keyed bijection, csrc/pixels.cuh) with no host work at all."""
+the reference (`torch.randperm(n_masked)[:R]`, :176), so the same seed gives the same rays; `rng = "reference-numpy"` is
+BlenderDataset's draw (`np.random.choice(sampling_idx, R)`, WITH replacement, numpy's global generator;
+code/datasets/blender_hawp_dataset.py:43 -- the dataset class of abc-neat-a.conf); `rng = "device"` draws R distinct masked
+pixels inside the gather kernel (keyed bijection, csrc/pixels.cuh) with no host work at all."""
 import ctypes
 
 import torch
@@ -49,6 +51,13 @@ def pixel_permutation(n, seed, step, first, count):
     out = (ctypes.c_uint * count)()
     _lib.check(lib.neat_pixel_permutation(n, seed, step, first, count, out))
     return list(out)
+
+
+def reference_numpy_positions(n, R):
+    """Positions into the masked-pixel list that `np.random.choice(sampling_idx, R)` (blender_hawp_dataset.py:43) picks:
+    the legacy generator draws `randint(0, n, R)` and indexes the array, so choosing positions consumes the same stream."""
+    import numpy as np
+    return np.random.choice(n, R).astype(np.int64)
 
 
 class _Image:
@@ -105,7 +114,7 @@ class DeviceScene(torch.utils.data.Dataset):
             self.sampling_size = None
         else:
             self.sampling_size = int(sampling_size)
-            if self.rng == "reference":
+            if self.rng in ("reference", "reference-numpy"):
                 torch.randperm(self.total_pixels)
 
     # ------------------------------------------------------------------ one item
@@ -141,6 +150,13 @@ class DeviceScene(torch.utils.data.Dataset):
             sample.update(uv=uv, uv_proj=uvp, labels=lab, lines=l2d)
             return i, sample, {"rgb": rgb}
         R, n = self.sampling_size, int(im.masked.numel())
+        if self.rng == "reference-numpy":
+            if n == 0:
+                raise _lib.NeatError("image %d has no masked pixel" % i)
+            perm = torch.from_numpy(reference_numpy_positions(n, R)).pin_memory().to(self.device, non_blocking=True)
+            uv, uvp, rgb, l2d, lab, idx = self._gather(im, R, perm=perm)
+            sample.update(uv=uv, uv_proj=uvp, labels=lab, lines=l2d, sampling_idx=idx)
+            return i, sample, {"rgb": rgb, "lines2d": l2d}
         if R > n:
             raise _lib.NeatError("image %d has %d masked pixels, fewer than the %d requested" % (i, n, R))
         if self.rng == "reference":
@@ -150,7 +166,7 @@ class DeviceScene(torch.utils.data.Dataset):
             self.draws += 1
             uv, uvp, rgb, l2d, lab, idx = self._gather(im, R, draw=(self.seed, self.draws))
         else:
-            raise _lib.NeatError("rng must be 'reference' or 'device'")
+            raise _lib.NeatError("rng must be 'reference', 'reference-numpy' or 'device'")
         sample.update(uv=uv, uv_proj=uvp, labels=lab, lines=l2d, sampling_idx=idx)
         return i, sample, {"rgb": rgb, "lines2d": l2d}
 

@@ -78,6 +78,18 @@ def test_pixel_permutation_rejects_bad_arguments():
         D.pixel_permutation(0, 0, 0, 0, 0)
 
 
+def test_reference_numpy_positions_consume_the_stream_like_blender_dataset():
+    """BlenderDataset draws `np.random.choice(sampling_idx, R)` (with replacement); drawing POSITIONS with the same seed
+    selects the same pixels."""
+    from neat_b200 import dataset as D
+    masked = np.sort(np.random.RandomState(0).permutation(512 * 512)[:15030])
+    np.random.seed(123)
+    ref = np.random.choice(torch.from_numpy(masked), 1024)              # the reference call, on its tensor argument
+    np.random.seed(123)
+    pos = D.reference_numpy_positions(masked.size, 1024)
+    assert np.array_equal(masked[pos], np.asarray(ref)) and np.unique(pos).size < 1024   # with replacement
+
+
 def test_device_scene_has_no_cpu_path():
     from neat_b200 import _lib, dataset as D
     with pytest.raises(_lib.NeatError):
