@@ -6,12 +6,18 @@
 
 A "step" is what code/training/volsdf_train.py:361-374 does for one image: model(input) -> loss -> zero_grad ->
 backward -> (all-reduce of the flat gradient bucket for N>1) -> Adam step.  Rank 0 prints ONE JSON line.
-  value : whole-job rays/s with the batch already resident in HBM (device-timed, max over ranks)
-  e2e   : the same step driven from HOST buffers (pinned H2D of the batch and a D2H read of the loss every step)
-  roofline     : the dominant kernel, timed live with CUDA events on the launching stream
-  cpu_baseline : the CPU port of the reference algorithm (oracle/) on this box's host cores, bounded sample
-`--impl reference` times that CPU path alone (the reference itself is Python under /root/reference, which does not
-exist on the GPU box; the oracle is its line-by-line restatement pinned against the reference's outputs)."""
+  value   : whole-job rays/s with the batch already resident in HBM (device-timed, max over ranks); BASELINE configs[1]
+  e2e     : the same step driven from HOST buffers (pinned H2D of the batch and a D2H read of the loss every step)
+  roofline: the dominant kernel, timed live with CUDA events on the launching stream; `frac` is the TENSOR fraction
+            (SURVEY 8d names the tensor cores as the bound of the MLP kernels), `hbm_frac` sits beside it
+  cpu_baseline       : the UNMODIFIED reference classes on this box's host cores (bounded: 1 + 1 steps of the full batch)
+  gpu_eager_baseline : the UNMODIFIED reference classes on this B200 (fp32 eager PyTorch + cuBLAS) -- what a NEAT user
+                       runs today; `vs_gpu_eager` = value / that
+  configs : the other BASELINE configs measured in the same run (steady-state beta = 0.01, 8192 rays/GPU, eval chunks)
+  dp_check: (N > 1) all-reduced bucket == mean over ranks of the per-rank gradients, through the real plugin
+`--impl reference` runs the reference arm alone: the unmodified reference's training loop on the host CPU (all threads)
+at the FULL ray count, from oracle/_ref/neat_ref_code.zip (oracle/build_ref.py archives the reference's own files there;
+/root/reference does not exist on the GPU box).  If that archive is missing the oracle port is timed and labelled "port"."""
 import argparse
 import json
 import os
@@ -23,17 +29,18 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-F_SDF, F_REND, F_ATT = 1049088.0, 542720.0, 531968.0  # FLOP per point (BASELINE.md section 2)
+F_SDF, F_REND, F_ATT = 1049088.0, 542720.0, 531968.0  # FLOP per point (SURVEY.md section 8d)
 S = 98
-# ncu DRAM bytes (read + write) of one launch at 1024 rays (profiles/r01_v5_ncu_full_summary.csv)
-NCU_DRAM_BYTES_1024 = {"wgrad": 6.165e9, "sdf_bwd": 5.809e9, "sdf_render": 3.073e9}
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch at 1024 rays (ncu --set full; profiles/*_ncu_full_summary.csv)
+NCU_DRAM_BYTES_1024 = json.load(open(os.path.join(ROOT, "profiles", "ncu_dram_bytes_1024.json"))) \
+    if os.path.exists(os.path.join(ROOT, "profiles", "ncu_dram_bytes_1024.json")) else \
+    {"wgrad": 6.165e9, "sdf_bwd": 5.809e9, "sdf_render": 3.073e9, "source": "profiles/r01_v5_ncu_full_summary.csv"}
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        d = json.load(open(p))
-        return d, "measured"
+        return json.load(open(p)), "measured"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
@@ -47,7 +54,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -81,8 +88,9 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_baseline(R_cpu, beta, steps, threads):
-    """The CPU port (oracle/) of one train step: forward + loss + autograd backward on `threads` host threads."""
+# ------------------------------------------------------------------------------------------------ reference legs
+def cpu_port(R_cpu, beta, steps, threads):
+    """Fallback only (no reference archive): the CPU port (oracle/) of one train step."""
     import numpy as np
     import torch
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -92,15 +100,13 @@ def cpu_baseline(R_cpu, beta, steps, threads):
     conf = synth.dtu_conf()
     sd_np = synth.make_state_dict(conf, seed=1, perturb=0.15, beta=beta)
     sd = {k: torch.from_numpy(v.copy()).requires_grad_(True) for k, v in sd_np.items()}
-    ci = conf["implicit_network"]
-    c = conf["ray_sampler"]
+    ci, c = conf["implicit_network"], conf["ray_sampler"]
     sconf = O.SamplerConf(near=c["near"], N_samples=c["N_samples"], N_samples_eval=c["N_samples_eval"],
                           N_samples_extra=c["N_samples_extra"], eps=c["eps"], beta_iters=c["beta_iters"],
                           max_total_iters=c["max_total_iters"])
     b = synth.make_batch(R_cpu, seed=1)
     T = lambda a: torch.from_numpy(np.asarray(a))
-    times = []
-    k = 0
+    times, k = [], 0
     for it in range(steps + 1):
         t0 = time.perf_counter()
         P = O.params_from_state_dict(sd, skip_in=tuple(ci["skip_in"]), multires=ci["multires"],
@@ -108,7 +114,6 @@ def cpu_baseline(R_cpu, beta, steps, threads):
                                      sphere_radius=conf["scene_bounding_sphere"], sphere_scale=ci["sphere_scale"],
                                      beta_min=conf["density"]["beta_min"], track=True)
         g = torch.Generator().manual_seed(it)
-        L_guess = sconf.N_samples_eval * sconf.max_total_iters
         rnd = O.TrainRandoms(O.SamplerRandoms(torch.rand(R_cpu, sconf.N_samples_eval, generator=g),
                                               torch.rand(R_cpu, sconf.N_samples, generator=g),
                                               torch.randperm(sconf.N_samples_eval, generator=g)[:sconf.N_samples_extra],
@@ -124,12 +129,141 @@ def cpu_baseline(R_cpu, beta, steps, threads):
         if it > 0:
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
-    return R_cpu / sec, sec, k
+    return {"rays_per_s": R_cpu / sec, "ms_per_step": sec * 1e3, "steps": steps, "warmup": 1, "rays": R_cpu,
+            "threads": threads, "device": "cpu", "k": k}
 
 
-def eval_mode(args, rank, world, dev, lib):
-    """Extra, informational: the eval-mode forward (sampler + SDF with normals + both heads + compositing + geometry,
-    no backward) over a chunk of rays per GPU; rays shard over ranks with no collective."""
+def reference_cpu(rays, beta, steps, warmup, budget_s):
+    """The reference's CPU path on this box's host cores: (result dict, kind)."""
+    threads = os.cpu_count() or 1
+    try:
+        from oracle import ref_bench
+        if ref_bench.available():
+            return ref_bench.train_steps(rays, steps, warmup, beta=beta, device="cpu", threads=threads,
+                                         budget_s=budget_s), "reference"
+    except Exception as e:  # never lose the whole line to the baseline leg
+        sys.stderr.write("reference CPU leg failed (%s: %s); timing the oracle port instead\n" % (type(e).__name__, e))
+    return cpu_port(min(rays, 256), beta, max(1, min(steps, 2)), threads), "port"
+
+
+def reference_config(r, kind, beta):
+    what = ("UNMODIFIED reference classes (model.networks.neat_wfr_rend_a.VolSDFNetwork + loss_wfr.VolSDFLoss, "
+            "oracle/_ref/neat_ref_code.zip)" if kind == "reference" else "oracle/neat_oracle.py (CPU port of the reference)")
+    return {"workload": "DTU-shaped synthetic batch: %d rays x 98 samples, 8x256 SDF + 4x256 rendering/attraction MLPs, "
+                        "ErrorBoundSampler; train step = fwd+loss+zero_grad+backward+torch.optim.Adam, as "
+                        "code/training/volsdf_train.py:361-374" % r["rays"],
+            "implementation": what, "device": "host CPU, torch fp32 eager + autograd (double backward via create_graph)",
+            "threads": r["threads"], "rays_per_step": r["rays"], "samples_per_ray": S, "beta": beta, "parallelism": "none"}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def train_config(rays, beta, steps, warmup, rank, world, dev, lib, e2e=True, timers=True, clocks=None):
+    """Times `steps` training steps at `rays` rays per GPU.  Returns a dict of raw measurements (max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    from neat_b200 import synth
+    from neat_b200 import trainer as TR
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ts = TR.TrainStep(synth.dtu_conf(), device=dev, seed=42, beta=beta)
+    hb = TR.host_batch(rays, seed=1 + rank)
+    inp, gt = TR.to_device(hb, dev)
+    rn = ts.model._get_renderer()
+    for _ in range(warmup):
+        ts.step(inp, gt)
+    barrier()
+    if clocks is not None:
+        clocks.start()
+    rn.timers = {} if timers else None
+    l0 = lib.neat_launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    k_acc = torch.zeros(1, dtype=torch.int32, device=dev)  # the sampler's k is data dependent and drifts as beta trains
+    for _ in range(steps):
+        ts.step(inp, gt)
+        k_acc += ts.model.last_step.n_iters
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = lib.neat_launch_count() - l0
+    tm = rn.timer_ms() if timers else {}
+    rn.timers = None
+    r = {"rays": rays, "beta": beta, "steps": steps, "warmup": warmup, "ms_total": ms_total, "launches": int(launches),
+         "timers": tm, "k_last": int(ts.model.last_step.n_iters.item()), "k_mean": float(k_acc.item()) / steps,
+         "host_junction_block": getattr(ts.model, "last_host_ms", None), "h2d": TR.h2d_bytes(hb)}
+    if e2e:
+        # end to end from host buffers (same initial state and trajectory as the loop above)
+        del ts
+        ts = TR.TrainStep(synth.dtu_conf(), device=dev, seed=42, beta=beta)
+        for _ in range(warmup):
+            ts.step(inp, gt)
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        loss_host = 0.0
+        for _ in range(steps):
+            i2, g2 = TR.to_device(hb, dev)
+            loss_host = float(ts.step(i2, g2).item())
+        e3.record()
+        barrier()
+        r["ms_e2e"] = e2.elapsed_time(e3)
+        r["last_loss"] = loss_host
+    if clocks is not None:
+        r["clocks"] = clocks.stop()
+    t = torch.tensor([r["ms_total"], r.get("ms_e2e", 0.0)], device=dev, dtype=torch.float64)
+    if world > 1:
+        mine = torch.tensor([r["ms_total"] / steps, float(r["k_last"]), sum(v[1] for v in tm.values()) / steps,
+                             r.get("last_loss", 0.0)], device=dev, dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        r["per_rank"] = [{"ms_per_step": round(float(a[0]), 3), "sampler_k": int(a[1]), "mlp_kernel_ms": round(float(a[2]), 3),
+                          "last_loss": round(float(a[3]), 5)} for a in allr]
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    r["ms_total"], r["ms_e2e"] = float(t[0]), float(t[1])
+    del ts
+    torch.cuda.empty_cache()
+    return r
+
+
+def kernel_fractions(r, pk):
+    """Per-kernel algorithmic TFLOP/s and GB/s (and their fractions of the measured peaks) from the live CUDA-event timers."""
+    rays, M, tm = r["rays"], r["rays"] * S, r["timers"]
+    # Tensor work per point: forward F + normal pass F (sdf_render); tangent F + reverse F (sdf_bwd); the two
+    # outer-product accumulations 2 F plus the heads' (wgrad) -- SURVEY.md Appendix A, 6 F_sdf per render point.
+    flops = {"sdf_bwd_M%d" % M: 2 * F_SDF * M, "sdf_render_M%d" % M: 2 * F_SDF * M,
+             "sampler": 128.0 * r["k_mean"] * rays * F_SDF,
+             "head_fwd": 0.5 * (F_REND + F_ATT) * M, "head_bwd": 0.5 * (F_REND + F_ATT) * M,  # per launch (one head)
+             "wgrad": (2 * F_SDF + F_REND + F_ATT) * M + 2 * F_SDF * 2 * rays}
+    # Algorithmic bytes = compulsory HBM traffic per 128-point tile of the save-record design (DESIGN.md section 2.1)
+    MAIN, AUX = 131072.0, 24576.0
+    WG_SDF_B, WG_HEAD_B = (33 * MAIN + 5 * AUX) / 128.0, 2 * (9 * MAIN + 2 * AUX) / 128.0
+    BWD_B = (16 * MAIN + 8 * MAIN + MAIN + (8 * MAIN + AUX) + (9 * MAIN + AUX)) / 128.0 + 20.0
+    REND_B = (8 * MAIN + 8 * MAIN + 8 * MAIN + AUX + MAIN) / 128.0 + 20.0
+    hbm_bytes = {"wgrad": (WG_SDF_B + WG_HEAD_B) * M + WG_SDF_B * 2 * rays, "sdf_bwd_M%d" % M: BWD_B * M,
+                 "sdf_render_M%d" % M: REND_B * M}
+    out = {}
+    for k, (n_l, ms) in tm.items():
+        if k not in flops or n_l == 0:
+            continue
+        sec = ms / n_l * 1e-3
+        d = {"ms_per_launch": round(ms / n_l, 4), "tensor_tflops": round(flops[k] / sec / 1e12, 1),
+             "tensor_frac": round(flops[k] / sec / 1e12 / pk["bf16_tflops_sustained"], 4)}
+        if k in hbm_bytes:
+            d["hbm_gbs"] = round(hbm_bytes[k] / sec / 1e9, 1)
+            d["hbm_frac"] = round(hbm_bytes[k] / sec / 1e9 / pk["hbm_gbs"], 4)
+        out[k] = d
+    return out
+
+
+def eval_config(rays, beta, steps, warmup, rank, world, dev, lib):
+    """The eval-mode forward (sampler + SDF with normals + both heads + compositing + geometry, no backward) over a chunk
+    of `rays` rays per GPU -- BASELINE configs[4], chunked as code/utils/general.py:23-36 / neat-final-parsing.py:205-213
+    do; rays shard over ranks with no collective."""
     import torch
     import torch.distributed as dist
     from neat_b200 import synth
@@ -138,9 +272,9 @@ def eval_mode(args, rank, world, dev, lib):
     torch.manual_seed(42)
     model = VolSDFNetwork(synth.dtu_conf())
     with torch.no_grad():
-        model.density.beta.fill_(args.beta)
+        model.density.beta.fill_(beta)
     model = model.to(dev).eval()
-    hb = TR.host_batch(args.rays, seed=1 + rank)
+    hb = TR.host_batch(rays, seed=1 + rank)
     inp, _ = TR.to_device(hb, dev)
 
     def barrier():
@@ -148,43 +282,70 @@ def eval_mode(args, rank, world, dev, lib):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        model(inp)
+    for _ in range(warmup):
+        out = model(inp)
     barrier()
     l0 = lib.neat_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         out = model(inp)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    launches = lib.neat_launch_count() - l0
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         i2, _ = TR.to_device(hb, dev)
         o = model(i2)
         host = o["lines3d"].cpu()  # the result a caller keeps (neat-final-parsing.py:213)
     e3.record()
     barrier()
-    ms_e2e = e2.elapsed_time(e3)
-    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms, e2.elapsed_time(e3)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        ms, ms_e2e = float(t[0]), float(t[1])
-        print(json.dumps({"metric": "eval_forward_rays_per_sec", "value": world * args.rays * args.steps / (ms * 1e-3),
-                          "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                          "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                          "dtype": "bf16x3->f32", "data": "synthetic",
-                          "config": {"workload": "eval-mode forward, %d rays/GPU per call x 98 samples, DTU nets" % args.rays,
-                                     "beta": args.beta, "parallelism": "dp%d" % world},
-                          "e2e": {"value": world * args.rays * args.steps / (ms_e2e * 1e-3), "unit": "rays/s",
-                                  "h2d_bytes_per_step": sum(hb[k].numel() * 4 for k in ("intrinsics", "pose", "uv", "uv_proj")),
-                                  "d2h_bytes_per_step": int(host.numel() * 4)},
-                          "gpu_launches": int(lib.neat_launch_count() - l0)}))
-    if world > 1:
-        dist.destroy_process_group()
+    ms, ms_e2e = float(t[0]), float(t[1])
+    k = int(model._get_renderer().last_n_iters.item())
+    r = {"metric": "eval_forward_rays_per_sec", "value": world * rays * steps / (ms * 1e-3), "unit": "rays/s",
+         "rays_per_gpu": rays, "beta": beta, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "sampler_k": k,
+         "e2e": {"value": world * rays * steps / (ms_e2e * 1e-3), "unit": "rays/s",
+                 "h2d_bytes_per_step": sum(hb[kk].numel() * 4 for kk in ("intrinsics", "pose", "uv", "uv_proj")),
+                 "d2h_bytes_per_step": int(host.numel() * 4)},
+         "gpu_launches": int(launches),
+         "full_image_1600x1200_seconds_at_this_rate": round(1600 * 1200 / (world * rays * steps / (ms * 1e-3)), 3)}
+    del model
+    torch.cuda.empty_cache()
+    return r
+
+
+def dp_check(rank, world, dev):
+    """N > 1: one step through the real plugin; the all-reduced flat bucket times 1/world must equal the mean of the
+    per-rank gradients (gathered before the reduction)."""
+    import torch
+    import torch.distributed as dist
+    from neat_b200 import synth
+    from neat_b200 import trainer as TR
+    ts = TR.TrainStep(synth.dtu_conf(), device=dev, seed=42, beta=0.1)
+    inp, gt = TR.to_device(TR.host_batch(256, seed=1 + rank), dev)
+    lo = ts.loss_fn(ts.model(inp), gt)
+    ts.bucket.zero()
+    lo["loss"].backward()
+    mine = ts.bucket.flat.clone()
+    allg = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allg, mine)
+    mean = torch.stack(allg).double().mean(0)
+    scale = ts.bucket.all_reduce_sum()
+    red = ts.bucket.flat.double() * scale
+    err = float((red - mean).abs().max() / mean.abs().max().clamp_min(1e-30))
+    t = torch.tensor([err], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    losses = [torch.zeros(1, device=dev) for _ in range(world)]
+    dist.all_gather(losses, lo["loss"].detach().reshape(1).float())
+    del ts
+    torch.cuda.empty_cache()
+    return {"allreduce_vs_mean_of_rank_gradients_rel_err": float(t[0]), "ok": bool(float(t[0]) < 1e-5),
+            "rank_losses": [round(float(x), 5) for x in losses], "rays_per_rank": 256}
 
 
 def main():
@@ -195,42 +356,38 @@ def main():
     ap.add_argument("--rays", type=int, default=1024, help="rays per GPU per step (weak scaling)")
     ap.add_argument("--beta", type=float, default=0.1, help="density.beta (0.1 = init, k~2; 0.01 = trained-like, k=5)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-rays", type=int, default=256)
+    ap.add_argument("--cpu-rays", type=int, default=0, help="reference legs: rays per step (0 = the full --rays)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true")
     ap.add_argument("--mode", default="train", choices=["train", "eval"],
-                    help="train: the headline train step; eval: the eval-mode forward over a chunk of `--rays` rays "
-                         "(BASELINE configs[4]: full-image inference, chunked as neat-final-parsing.py / eval.py do)")
+                    help="train: the headline train step; eval: only the eval-mode forward over chunks of `--rays` rays")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": "DTU-shaped synthetic batch: %d rays/GPU x 98 samples, 8x256 SDF + 4x256 rendering/attraction "
-                          "MLPs, ErrorBoundSampler (<=5 x 128 SDF queries/ray), train step = fwd+loss+bwd+Adam" % args.rays,
-              "optimizer": "Adam(lr=5e-4), all parameter tensors in one launch (neat_b200.optim.Adam)",
-              "rays_per_gpu": args.rays, "samples_per_ray": S, "beta": args.beta, "parallelism": "dp%d" % world,
-              "rng": "training draws (stratified jitter, inverse-CDF u, extra columns, eikonal points) made on the device",
-              "precision_mode": "bf16x3 (hi/lo split operands, fp32 accumulate) on tcgen05",
-              "l2": "no explicit flush: the per-step working set (~5 GB of saved activations at 1024 rays) is >> the 126 MB L2"}
+    warm = max(args.warmup, 3)
 
     if args.impl == "reference":
         if rank != 0:
             return
-        threads = os.cpu_count() or 1
-        steps = max(1, min(args.steps, 2))
-        val, sec, k = cpu_baseline(args.cpu_rays, args.beta, steps, threads)
-        sample = "%d rays (of %d) per step, %d timed step(s) after 1 untimed, sampler k=%d" % (args.cpu_rays, args.rays, steps, k)
+        rays = args.cpu_rays or args.rays
+        r, kind = reference_cpu(rays, args.beta, args.steps, max(args.warmup, 1), budget_s=200.0)
+        sample = ("the full batch: %d rays per step, %d timed step(s) after %d untimed (requested %d + %d; bounded to ~200 s "
+                  "of host time), %d host threads" % (r["rays"], r["steps"], r["warmup"], args.steps, args.warmup, r["threads"]))
+        val = r["rays_per_s"]
         print(json.dumps({"impl": "reference", "metric": "train_step_rays_per_sec", "value": val, "unit": "rays/s",
-                          "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": sec * 1e3,
+                          "n_gpus": args.gpus, "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"],
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                          "data": "synthetic", "config": config,
-                          "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample},
-                          "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                          "data": "synthetic", "config": reference_config(r, kind, args.beta),
+                          "cpu_baseline": {"value": val, "unit": "rays/s", "cores": r["threads"], "kind": kind, "sample": sample},
+                          "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "last_loss": r.get("loss")}))
         return
 
     import torch
     import torch.distributed as dist
-    from neat_b200 import _lib, synth
-    from neat_b200 import trainer as TR
+    from neat_b200 import _lib
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
@@ -239,144 +396,111 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     if args.mode == "eval":
-        return eval_mode(args, rank, world, dev, lib)
-    ts = TR.TrainStep(synth.dtu_conf(), device=dev, seed=42, beta=args.beta)
-    hb = TR.host_batch(args.rays, seed=1 + rank)
-    inp, gt = TR.to_device(hb, dev)
-    rn = ts.model._get_renderer()
-
-    def barrier():
+        r = eval_config(args.rays, args.beta, args.steps, warm, rank, world, dev, lib)
+        if rank == 0:
+            r.update(n_gpus=world, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16x3->f32", data="synthetic",
+                     config={"workload": "eval-mode forward, %d rays/GPU per call x 98 samples, DTU nets" % args.rays,
+                             "beta": args.beta, "parallelism": "dp%d" % world})
+            print(json.dumps(r))
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+            dist.destroy_process_group()
+        return
 
-    for _ in range(max(args.warmup, 3)):
-        ts.step(inp, gt)
-    barrier()
+    config = {"workload": "DTU-shaped synthetic batch: %d rays/GPU x 98 samples, 8x256 SDF + 4x256 rendering/attraction "
+                          "MLPs, ErrorBoundSampler (<=5 x 128 SDF queries/ray), train step = fwd+loss+bwd+Adam "
+                          "(BASELINE configs[1])" % args.rays,
+              "optimizer": "Adam(lr=5e-4), all parameter tensors in one launch (neat_b200.optim.Adam)",
+              "rays_per_gpu": args.rays, "samples_per_ray": S, "beta": args.beta, "parallelism": "dp%d" % world,
+              "rng": "training draws (stratified jitter, inverse-CDF u, extra columns, eikonal points) made on the device",
+              "precision_mode": "bf16x3 (hi/lo split operands, fp32 accumulate) on tcgen05",
+              "l2": "no explicit flush: the per-step working set (GBs of saved activations at 1024 rays) is >> the 126 MB L2"}
+    check = dp_check(rank, world, dev) if world > 1 else None
+    clocks = ClockSampler(local) if rank == 0 else None
+    r = train_config(args.rays, args.beta, args.steps, warm, rank, world, dev, lib, clocks=clocks)
 
-    # ---- device-resident inputs ------------------------------------------------------------------
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    rn.timers = {}
-    l0 = lib.neat_launch_count()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    k_acc = torch.zeros(1, dtype=torch.int32, device=dev)  # the sampler's k is data dependent and drifts as beta trains
-    for _ in range(args.steps):
-        ts.step(inp, gt)
-        k_acc += ts.model.last_step.n_iters
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    launches = lib.neat_launch_count() - l0
-    timers = rn.timer_ms()
-    rn.timers = None
-    k_iters = int(ts.model.last_step.n_iters.item())
-    k_mean = float(k_acc.item()) / args.steps
+    extras = []
+    if not args.no_extra_configs:
+        # the other BASELINE configs, same run, each with its own ms/step, sampler k and kernel fractions
+        plan = [("configs[1] at the steady-state density: 1024 rays/GPU, beta=0.01 (sampler k=5)", 1024, 0.01, 30),
+                ("configs[1], 100 timed steps (beta trains away from 0.1: k drifts)", 1024, 0.1, 100),
+                ("configs[2]/[3]: 8192 rays/GPU, beta=0.1", 8192, 0.1, 10),
+                ("configs[2]/[3]: 8192 rays/GPU, beta=0.01 (k=5)", 8192, 0.01, 10)]
+        pk0, _ = peaks()
+        for name, rays, beta, steps in plan:
+            if rays == args.rays and beta == args.beta and steps == args.steps:
+                continue
+            x = train_config(rays, beta, steps, 3, rank, world, dev, lib, e2e=False)
+            extras.append({"name": name, "rays_per_gpu": rays, "beta": beta, "steps": steps, "warmup": 3,
+                           "value": world * rays * steps / (x["ms_total"] * 1e-3), "unit": "rays/s",
+                           "ms_per_step": x["ms_total"] / steps, "sampler_k_last": x["k_last"],
+                           "sampler_k_mean": round(x["k_mean"], 3), "gpu_launches_per_step": x["launches"] / steps,
+                           "kernel_ms_per_step": {k: round(v[1] / steps, 4) for k, v in x["timers"].items()},
+                           "kernels": kernel_fractions(x, pk0)})
+        e = eval_config(65536, 0.01, 5, 3, rank, world, dev, lib)
+        e["name"] = "configs[4]: eval-mode forward in 65536-ray chunks per GPU (full 1600x1200 image = 30 chunks), beta=0.01"
+        extras.append(e)
 
-    # ---- end to end from host buffers (same initial state and trajectory as the loop above) ----------------
-    del ts
-    ts = TR.TrainStep(synth.dtu_conf(), device=dev, seed=42, beta=args.beta)
-    for _ in range(max(args.warmup, 3)):
-        ts.step(inp, gt)
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    loss_host = 0.0
-    for _ in range(args.steps):
-        i2, g2 = TR.to_device(hb, dev)
-        loss_host = float(ts.step(i2, g2).item())
-    e3.record()
-    barrier()
-    ms_e2e = e2.elapsed_time(e3)
-    clk = clocks.stop() if rank == 0 else None
-
-    t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
-    per_rank = None
-    if world > 1:
-        mine = torch.tensor([ms_total / args.steps, float(k_iters), sum(v[1] for v in timers.values()) / args.steps],
-                            device=dev, dtype=torch.float64)
-        allr = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(allr, mine)
-        per_rank = [{"ms_per_step": round(float(a[0]), 3), "sampler_k": int(a[1]), "mlp_kernel_ms": round(float(a[2]), 3)}
-                    for a in allr]
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = float(t[0]), float(t[1])
     if rank == 0:
         pk, pk_kind = peaks()
-        ms_step = ms_total / args.steps
-        value = world * args.rays * args.steps / (ms_total * 1e-3)
-        e2e = world * args.rays * args.steps / (ms_e2e * 1e-3)
+        steps = args.steps
+        ms_total, ms_e2e, timers = r["ms_total"], r["ms_e2e"], r["timers"]
+        value = world * args.rays * steps / (ms_total * 1e-3)
+        e2e = world * args.rays * steps / (ms_e2e * 1e-3)
         M = args.rays * S
-        # Tensor work per point: forward F, normal pass F (sdf_render); tangent F + reverse F (sdf_bwd); the two
-        # outer-product accumulations 2 F plus the heads' (wgrad) -- SURVEY.md Appendix A, 6 F_sdf per render point.
-        flops = {"sdf_bwd_M%d" % M: 2 * F_SDF * M, "sdf_render_M%d" % M: 2 * F_SDF * M,
-                 "sampler": 128.0 * k_mean * args.rays * F_SDF,
-                 "head_fwd": 0.5 * (F_REND + F_ATT) * M, "head_bwd": 0.5 * (F_REND + F_ATT) * M,  # per launch (one head)
-                 "wgrad": (2 * F_SDF + F_REND + F_ATT) * M + 2 * F_SDF * 2 * args.rays}
-        # The training kernels are bound by HBM at least as much as by the tensor pipe (ncu: wgrad DRAM 62 % / tensor
-        # 27 %, sdf_bwd 58 % / 20 %, sdf_render 35 % / 24 % of peak), so each of them gets BOTH fractions and the larger one
-        # names the bound.  Algorithmic bytes = compulsory HBM traffic per 128-point tile:
-        #   wgrad      reads every saved operand tile once: 33 main (128 KB: 256 columns x 128 points x bf16 hi + lo) + 5
-        #              aux (24 KB) for the SDF net, 2 x (9 main + 2 aux) for the heads = 52.7 KB per render point
-        #   sdf_bwd    reads sigma' twice (tangent + reverse sweep, 8 x 128 KB each) + a_l (8 main) + feat_bar (128 KB),
-        #              writes p (8 main + aux) and z_bar (9 main + aux) = 42.4 KB per point (the zhat scratch is L2 traffic)
-        #   sdf_render writes sigma' (8 x 128 KB), u (8 main), a (8 main), PE (aux), the feature tile = 25.2 KB per point
-        MAIN, AUX = 131072.0, 24576.0
-        WG_SDF_B, WG_HEAD_B = (33 * MAIN + 5 * AUX) / 128.0, 2 * (9 * MAIN + 2 * AUX) / 128.0
-        BWD_B = (16 * MAIN + 8 * MAIN + MAIN + (8 * MAIN + AUX) + (9 * MAIN + AUX)) / 128.0 + 20.0
-        REND_B = (8 * MAIN + 8 * MAIN + 8 * MAIN + AUX + MAIN) / 128.0 + 20.0
-        hbm_bytes = {"wgrad": (WG_SDF_B + WG_HEAD_B) * M + WG_SDF_B * 2 * args.rays,
-                     "sdf_bwd_M%d" % M: BWD_B * M, "sdf_render_M%d" % M: REND_B * M}
-        shares = {k: v[1] / ms_total for k, v in timers.items()}
+        kf = kernel_fractions(r, pk)
         # dominant KERNEL = longest single launch ("sampler" is a group of up to 5 query launches + the per-ray kernels)
-        dom = max((k for k in timers if k in flops and k != "sampler"), key=lambda k: timers[k][1] / timers[k][0])
-        n_l, ms_dom = timers[dom]
-        sec_dom = ms_dom / n_l * 1e-3
-        tensor_tflops = flops[dom] / sec_dom / 1e12
-        tensor_frac = tensor_tflops / pk["bf16_tflops_sustained"]
-        hbm_gbs = hbm_bytes[dom] / sec_dom / 1e9 if dom in hbm_bytes else 0.0
-        hbm_frac = hbm_gbs / pk["hbm_gbs"]
-        if hbm_frac >= tensor_frac:
-            achieved, peak, unit, bound = hbm_gbs, pk["hbm_gbs"], "GB/s", "hbm"
-            peak_kind = pk_kind + " copy bandwidth (read + write)"
-            note = ("achieved = ALGORITHMIC bytes (compulsory HBM traffic of the kernel, each saved tile moved once) / "
-                    "CUDA-event time; `traffic` = DRAM bytes of one launch from ncu.  The same launch does %.1f algorithmic "
-                    "TFLOP/s = %.3f of the sustained bf16 tensor rate (x3 issued: bf16x3)" % (tensor_tflops, tensor_frac))
-        else:
-            achieved, peak, unit, bound = tensor_tflops, pk["bf16_tflops_sustained"], "TFLOP/s", "tensor"
-            peak_kind = pk_kind + " sustained bf16 (cuBLAS)"
-            note = ("achieved = ALGORITHMIC fp32-equivalent FLOPs (2*MAC) / CUDA-event time; the kernel issues 3 bf16 MMAs "
-                    "per algorithmic MAC (hi*hi + hi*lo + lo*hi) to meet the 1e-4 parity bound, so the tensor pipe does 3x this")
+        dom = max((k for k in kf if k != "sampler"), key=lambda k: kf[k]["ms_per_launch"])
+        d = kf[dom]
         ncu_traffic = NCU_DRAM_BYTES_1024.get(dom.split("_M")[0]) if args.rays == 1024 else None
-        line = {"metric": "train_step_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        big = sum(v[1] for k, v in timers.items()) / steps
+        line = {"metric": "train_step_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": steps,
+                "warmup": warm, "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16x3->f32", "data": "synthetic", "config": config,
-                "sampler_iters_k": k_iters, "sampler_iters_k_mean": round(k_mean, 3),
-                "mlp_samples_per_sec": world * (M + 128 * k_mean * args.rays + 3 * args.rays) * args.steps / (ms_total * 1e-3),
-                "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": TR.h2d_bytes(hb), "d2h_bytes_per_step": 4,
-                        "ms_per_step": ms_e2e / args.steps, "last_loss": loss_host},
-                "gpu_launches": int(launches), "clocks": clk,
-                "roofline": {"bound": bound, "kernel": dom, "achieved": achieved, "peak": peak, "unit": unit,
-                             "frac": achieved / peak,
-                             # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at 1024 rays,
-                             # from the ncu --set full capture summarised in profiles/r01_v5_ncu_full_summary.csv
-                             "traffic": ncu_traffic,
-                             "other_bound": {"tensor_frac": round(tensor_frac, 4), "hbm_frac": round(hbm_frac, 4)},
-                             "peak_kind": peak_kind, "note": note,
-                             "tensor_tflops_algorithmic": {k: round(flops[k] / (timers[k][1] / timers[k][0] * 1e-3) / 1e12, 1)
-                                                           for k in timers if k in flops}},
-                "kernel_time_share": {k: round(v, 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1])},
-                "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in timers.items()},
-                "host_junction_block": getattr(ts.model, "last_host_ms", None), "per_rank": per_rank}
-        if not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            val, sec, kc = cpu_baseline(args.cpu_rays, args.beta, 1, threads)
-            line["cpu_baseline"] = {"value": val, "unit": "rays/s", "cores": threads, "kind": "port",
-                                    "sample": "%d rays (of %d) per step, 1 timed step after 1 untimed, sampler k=%d, "
-                                              "torch CPU fp32, all host threads" % (args.cpu_rays, args.rays, kc)}
+                "sampler_iters_k": r["k_last"], "sampler_iters_k_mean": round(r["k_mean"], 3),
+                "mlp_samples_per_sec": world * (M + 128 * r["k_mean"] * args.rays + 3 * args.rays) * steps / (ms_total * 1e-3),
+                "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e / steps, "last_loss": r["last_loss"]},
+                "gpu_launches": r["launches"], "clocks": r.get("clocks"),
+                "roofline": {"bound": "tensor", "kernel": dom, "achieved": d["tensor_tflops"], "peak": pk["bf16_tflops_sustained"],
+                             "unit": "TFLOP/s", "frac": d["tensor_tflops"] / pk["bf16_tflops_sustained"],
+                             "hbm_frac": d.get("hbm_frac"), "hbm_gbs_algorithmic": d.get("hbm_gbs"),
+                             # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at 1024 rays (ncu --set full)
+                             "traffic": ncu_traffic, "traffic_source": NCU_DRAM_BYTES_1024.get("source"),
+                             "peak_kind": pk_kind + " sustained bf16 (cuBLAS) / " + pk_kind + " copy bandwidth for hbm_frac",
+                             "note": "achieved = ALGORITHMIC fp32-equivalent FLOPs (2*MAC, SURVEY 8d) / CUDA-event time of the "
+                                     "longest single launch; the kernel issues 3 bf16 MMAs per algorithmic MAC (hi*hi + hi*lo + "
+                                     "lo*hi) to meet the 1e-4 parity bound, so the tensor pipe does 3x this.  hbm_frac = the "
+                                     "kernel's compulsory save-record bytes / time / copy bandwidth.",
+                             "step_tensor_frac": round((947.5e6 + 134.3e6 * r["k_mean"]) * value / world / 1e12
+                                                       / pk["bf16_tflops_sustained"], 4),
+                             "kernels": kf},
+                "kernel_ms_per_step": {k: round(v[1] / steps, 4) for k, v in timers.items()},
+                "step_minus_big_kernels_ms": round(ms_total / steps - big, 4),
+                "host_junction_block": r["host_junction_block"], "per_rank": r.get("per_rank"), "dp_check": check,
+                "configs": extras}
+        if world == 1 and not args.no_eager_baseline:
+            try:
+                from oracle import ref_bench
+                if ref_bench.available():
+                    g = ref_bench.train_steps(args.cpu_rays or args.rays, 10, 3, beta=args.beta, device="cuda:%d" % local)
+                    line["gpu_eager_baseline"] = {
+                        "value": g["rays_per_s"], "unit": "rays/s", "ms_per_step": g["ms_per_step"], "steps": g["steps"],
+                        "warmup": g["warmup"], "rays": g["rays"], "kind": "reference",
+                        "what": "the UNMODIFIED reference classes on this B200: fp32 eager PyTorch + cuBLAS, torch.optim.Adam, "
+                                "the loop of volsdf_train.py:361-374 (host sync per sampler iteration, sklearn DBSCAN and scipy "
+                                "assignment on the host, as shipped)"}
+                    line["vs_gpu_eager"] = value / g["rays_per_s"]
+                else:
+                    line["gpu_eager_baseline"] = {"unavailable": "oracle/_ref/neat_ref_code.zip not built (oracle/build_ref.py)"}
+            except Exception as ex:
+                line["gpu_eager_baseline"] = {"unavailable": "%s: %s" % (type(ex).__name__, ex)}
+        if world == 1 and not args.no_cpu_baseline:
+            c, kind = reference_cpu(args.cpu_rays or args.rays, args.beta, 1, 1, budget_s=30.0)
+            line["cpu_baseline"] = {"value": c["rays_per_s"], "unit": "rays/s", "cores": c["threads"], "kind": kind,
+                                    "sample": "%d rays (of %d) per step, %d timed step after %d untimed, torch CPU fp32, all "
+                                              "host threads; %s" % (c["rays"], args.rays, c["steps"], c["warmup"],
+                                                                    "the unmodified reference classes" if kind == "reference"
+                                                                    else "oracle port")}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

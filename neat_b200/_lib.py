@@ -149,6 +149,10 @@ def load():
         fn.argtypes = args
     lib.neat_debug_set_l2_prefetch.restype = _I
     lib.neat_debug_set_l2_prefetch.argtypes = [_I]
+    lib.neat_debug_set_grid_cap.restype = _I
+    lib.neat_debug_set_grid_cap.argtypes = [_P, _I]
+    lib.neat_debug_set_wgrad_split.restype = _I
+    lib.neat_debug_set_wgrad_split.argtypes = [_P, _I, _I]
     _lib = lib
     return lib
 

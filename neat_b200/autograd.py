@@ -41,6 +41,13 @@ class NeatStepFunction(torch.autograd.Function):
         # backward() checks that no later forward has overwritten them instead of silently using the wrong records.
         renderer.generation += 1
         st.generation = renderer.generation
+        for lay in st.param_layers:
+            for t in lay:
+                # the MLP parameters are not autograd inputs of this Function (backward() writes their .grad itself), so
+                # tensor hooks on them would silently never fire: refuse instead ("autograd contract")
+                if t is not None and (t._backward_hooks or getattr(t, "_post_accumulate_grad_hooks", None)):
+                    raise _lib.NeatError("hooks on the MLP parameters are not supported: the step writes p.grad directly "
+                                         "(use neat_b200.parallel.GradBucket for data parallelism, not DDP hooks)")
         layers = [tuple(None if t is None else t.detach() for t in lay) for lay in st.param_layers]
         st.wn_layers = layers
         renderer.effective_weights(layers)
@@ -48,7 +55,12 @@ class NeatStepFunction(torch.autograd.Function):
         st.beta = beta
         uv, pose, K = st.uv, st.pose, st.K
         dirs, cam = renderer.camera_rays(uv, pose, K)
-        z, z_eik, n_it = renderer.sampler.get_z_vals(cam, dirs, beta, training=True, randoms=st.sampler_randoms)
+        if getattr(st, "samples_override", None) is not None:
+            # tests: (z_vals [R,S], z_eik [R,1]) handed in, e.g. to replay one batch in ray chunks at identical samples
+            z, z_eik = (t.to(dev, torch.float32).contiguous() for t in st.samples_override)
+            n_it = torch.zeros(1, dtype=torch.int32, device=dev)
+        else:
+            z, z_eik, n_it = renderer.sampler.get_z_vals(cam, dirs, beta, training=True, randoms=st.sampler_randoms)
         R, S = z.shape
         M = R * S
         st.R, st.S, st.dirs, st.cam, st.z, st.n_iters = R, S, dirs, cam, z, n_it

@@ -60,6 +60,17 @@ class Context:
         if h:
             self.lib.neat_destroy(h)
 
+    # ------------------------------------------------------------------ test knobs
+    def debug_grid_cap(self, max_ctas):
+        """Tests: at most `max_ctas` persistent CTAs per tile-MLP launch (0 = one per SM), so that a small point count
+        exercises the several-tiles-per-CTA loops the full-size step runs."""
+        _lib.check(self.lib.neat_debug_set_grid_cap(self._h, int(max_ctas)))
+
+    def debug_wgrad_split(self, max_split, tiles_per_split):
+        """Tests: split every weight-gradient GEMM's tile range into up to `max_split` pieces of >= `tiles_per_split`
+        tiles (0, 0 = the defaults 32 / 48)."""
+        _lib.check(self.lib.neat_debug_set_wgrad_split(self._h, int(max_split), int(tiles_per_split)))
+
     # ------------------------------------------------------------------ helpers
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -112,6 +123,13 @@ class Context:
 
 def sampler_config_from_conf(conf):
     c = conf["ray_sampler"]
+    # options of ErrorBoundSampler (code/model/ray_sampler.py:101-128) the kernels do not implement: refuse, never ignore
+    if float(c.get("add_tiny", 0.0)) != 0.0:
+        raise _lib.NeatError("ray_sampler.add_tiny != 0 is not supported (the kernels hard-code add_tiny = 0, the value "
+                             "of every shipped conf)")
+    if bool(c.get("inverse_sphere_bg", False)) or int(c.get("N_samples_inverse_sphere", 0)) > 0:
+        raise _lib.NeatError("ray_sampler.inverse_sphere_bg / N_samples_inverse_sphere are not supported (no shipped conf "
+                             "enables the inverse-sphere background, ray_sampler.py:261-263)")
     return _lib.SamplerConfig(
         n_eval=int(c["N_samples_eval"]), n_final=int(c["N_samples"]), n_extra=int(c.get("N_samples_extra", 0)),
         beta_iters=int(c["beta_iters"]), max_iters=int(c["max_total_iters"]), near_=float(c["near"]),

@@ -85,6 +85,10 @@ struct neat_ctx {
   Program prog_query{}, prog_render{}, prog_head[2]{}, prog_head_bwd[2]{}, prog_sdf_bwd{};  // zero: pf_base = nullptr
   uint8_t* ones_tile = nullptr;  // X operand with column 0 = 1 (aux-plane sized, hi then lo)
   int epilogue_prefetch = 0;  // NEAT_EPILOGUE_PREFETCH=1: producer-warp L2 hints for the backward epilogues (experiment)
+  int grid_cap = 0;           // neat_debug_set_grid_cap: at most this many persistent CTAs per tile-MLP launch (tests force
+                              // several tiles per CTA at small sizes with it); 0 = one CTA per SM
+  int wgrad_max_split = 32;   // neat_debug_set_wgrad_split / NEAT_WGRAD_SPLIT: cap of the tile-range splits per GEMM
+  int wgrad_tiles_per_split = 48;
   WJob* jobs_dev = nullptr;
   std::vector<WJob> jobs_last;  // what jobs_dev holds
   int jobs_cap = 0;
@@ -92,6 +96,13 @@ struct neat_ctx {
   WnTable wn_host{};
   bool wn_valid = false;
 };
+
+// persistent grid of a tile-MLP launch: one CTA per SM (or the debug cap), never more CTAs than tiles
+static inline int grid_for(const neat_ctx* c, int M) {
+  const int n_tiles = (M + TILE_M - 1) / TILE_M;
+  const int cap = c->grid_cap > 0 && c->grid_cap < c->num_sms ? c->grid_cap : c->num_sms;
+  return n_tiles < cap ? n_tiles : cap;
+}
 
 // ---------------------------------------------------------------- packing kernels
 __global__ void pack_bf16_kernel(const float* __restrict__ flat, const int32_t* __restrict__ src,
@@ -126,6 +137,7 @@ static int init_ctx(neat_ctx* c, const neat_net_config* cfg) {
     return fail(NEAT_EUNSUPPORTED, e.what());
   }
   if (const char* e = std::getenv("NEAT_EPILOGUE_PREFETCH")) c->epilogue_prefetch = std::atoi(e);
+  if (const char* e = std::getenv("NEAT_WGRAD_SPLIT")) c->wgrad_max_split = std::max(1, std::atoi(e));
   CK(cudaGetDevice(&c->device));
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, c->device));
@@ -337,8 +349,7 @@ static int launch_query(neat_ctx* c, SdfQueryParams& p, void* stream) {
   p.multires = c->plan.cfg.multires;
   p.sphere_r = p.sphere_r < 0.f ? 0.f : c->plan.cfg.sphere_radius;  // < 0 on entry: no sphere clamp (raw network sdf)
   p.sphere_scale = c->plan.cfg.sphere_scale;
-  const int n_tiles = (p.M + TILE_M - 1) / TILE_M;
-  const int grid = n_tiles < c->num_sms ? n_tiles : c->num_sms;
+  const int grid = grid_for(c, p.M);
   sdf_query_kernel<QUERY_STAGES>
       <<<grid, NUM_THREADS, engine_smem_bytes(QUERY_STAGES), static_cast<cudaStream_t>(stream)>>>(p);
   ++g_launches;
@@ -508,10 +519,6 @@ int fill_points(const neat_ctx* c, const neat_points* pts, SdfQueryParams& q) {
   q.sphere_r = c->plan.cfg.sphere_radius;
   q.sphere_scale = c->plan.cfg.sphere_scale;
   return NEAT_OK;
-}
-inline int grid_for(const neat_ctx* c, int M) {
-  const int n_tiles = (M + TILE_M - 1) / TILE_M;
-  return n_tiles < c->num_sms ? n_tiles : c->num_sms;
 }
 }  // namespace
 
@@ -846,11 +853,12 @@ int neat_line_junction_graph(const float* lines3d, int N, const float* junctions
 
 // ---------------------------------------------------------------- optimizer step
 namespace {
-struct AdamCache {  // one table per device: re-uploaded only when the tensor list changes (it never does in training)
-  AdamTable host{};
-  AdamTable* dev = nullptr;
-  int device = -1;
-  bool valid = false;
+struct AdamCache {  // device copies of the tensor tables seen so far on one device (param groups, > 128 tensors: one
+  // table per chunk); a table is uploaded once, the first time its tensor list is seen -- no synchronisation afterwards
+  static constexpr int MAX = 16;
+  AdamTable* host[MAX] = {};
+  AdamTable* dev[MAX] = {};
+  int n = 0, next = 0;
 };
 AdamCache g_adam[16];
 }  // namespace
@@ -864,7 +872,8 @@ int neat_adam_step(const neat_adam_tensor* tensors, int n, float lr, float beta1
   if (dev < 0 || dev >= 16) return fail(NEAT_EINVAL, "device index out of range");
   AdamCache& c = g_adam[dev];
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  AdamTable t{};
+  static thread_local AdamTable t;
+  std::memset(&t, 0, sizeof(t));
   t.n = n;
   int blocks = 0;
   for (int i = 0; i < n; ++i) {
@@ -875,18 +884,22 @@ int neat_adam_step(const neat_adam_tensor* tensors, int n, float lr, float beta1
     blocks += static_cast<int>((tensors[i].numel + ADAM_BLOCK_ELEMS - 1) / ADAM_BLOCK_ELEMS);
   }
   for (int i = n; i <= ADAM_MAX_TENSORS; ++i) t.blk_start[i] = blocks;
-  if (!c.dev) CK(cudaMalloc(&c.dev, sizeof(AdamTable)));
-  if (!c.valid || std::memcmp(&c.host, &t, sizeof(AdamTable)) != 0) {
+  int hit = -1;
+  for (int i = 0; i < c.n && hit < 0; ++i)
+    if (std::memcmp(c.host[i], &t, sizeof(AdamTable)) == 0) hit = i;
+  if (hit < 0) {  // first sight of this tensor list: one synchronous upload (the slot's previous table may still be read)
+    hit = c.n < AdamCache::MAX ? c.n++ : (c.next++ % AdamCache::MAX);
+    if (!c.host[hit]) c.host[hit] = new AdamTable();
+    if (!c.dev[hit]) CK(cudaMalloc(&c.dev[hit], sizeof(AdamTable)));
     CK(cudaStreamSynchronize(st));
-    CK(cudaMemcpyAsync(c.dev, &t, sizeof(AdamTable), cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));  // `t` is a stack object
-    c.host = t;
-    c.valid = true;
+    *c.host[hit] = t;
+    CK(cudaMemcpyAsync(c.dev[hit], c.host[hit], sizeof(AdamTable), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
   }
   if (blocks == 0) return NEAT_OK;
   const double bc1 = 1.0 - std::pow(static_cast<double>(beta1), step);
   const double bc2 = 1.0 - std::pow(static_cast<double>(beta2), step);
-  adam_step_kernel<<<blocks, 256, 0, st>>>(c.dev, lr, beta1, beta2, eps, weight_decay, static_cast<float>(bc1),
+  adam_step_kernel<<<blocks, 256, 0, st>>>(c.dev[hit], lr, beta1, beta2, eps, weight_decay, static_cast<float>(bc1),
                                           static_cast<float>(1.0 / std::sqrt(bc2)), grad_scale);
   ++g_launches;
   CK(cudaGetLastError());
@@ -1083,8 +1096,7 @@ int neat_weight_gradients(neat_ctx* c, const neat_grad_group* groups, int n_grou
     const int nt = (G.M + TILE_M - 1) / TILE_M;
     // tile-range splits per GEMM: ~48 tiles per CTA, at most 32 (measured: 784 tiles -> 16 splits 1.29 -> 1.22 ms vs 8;
     // 6272 tiles -> 32 splits 10.9 -> 9.6..10.1 ms; more splits only add flush traffic).  NEAT_WGRAD_SPLIT overrides the cap.
-    static const int max_split = [] { const char* e = std::getenv("NEAT_WGRAD_SPLIT"); return e ? std::atoi(e) : 32; }();
-    const int ns = std::max(1, std::min(max_split, nt / 48));
+    const int ns = std::max(1, std::min(c->wgrad_max_split, nt / std::max(1, c->wgrad_tiles_per_split)));
     if (G.sdf_fwd_save && G.sdf_bwd_save) {
       const Planes pe = aux_planes(G.sdf_fwd_save, fl.total, fl.pe, c16(E));
       const Planes p0 = aux_planes(G.sdf_bwd_save, bl.total, bl.p_aux, c16(E));
@@ -1220,6 +1232,21 @@ int neat_set_precision(neat_ctx* c, int fast) {
 }
 
 // ---------------------------------------------------------------- debug / bring-up
+
+// Tests only: cap the persistent grid (several tiles per CTA at small point counts) and force the wgrad tile-range
+// splitting (max_split pieces of >= tiles_per_split tiles); 0 restores the defaults.  Scratch sizes depend on the grid:
+// set the cap before the first launch that sizes a workspace.
+int neat_debug_set_grid_cap(neat_ctx* c, int max_ctas) {
+  if (!c || max_ctas < 0) return fail(NEAT_EINVAL, "bad argument");
+  c->grid_cap = max_ctas;
+  return NEAT_OK;
+}
+int neat_debug_set_wgrad_split(neat_ctx* c, int max_split, int tiles_per_split) {
+  if (!c || max_split < 0 || tiles_per_split < 0) return fail(NEAT_EINVAL, "bad argument");
+  c->wgrad_max_split = max_split > 0 ? max_split : 32;
+  c->wgrad_tiles_per_split = tiles_per_split > 0 ? tiles_per_split : 48;
+  return NEAT_OK;
+}
 
 int neat_debug_set_l2_prefetch(int on) {
   CK(cudaMemcpyToSymbol(g_l2_prefetch, &on, sizeof(int)));

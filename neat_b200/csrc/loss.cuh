@@ -161,7 +161,8 @@ __global__ void __launch_bounds__(256) loss_grads_kernel(LossParams p) {
   if (p.grad_theta && r < p.n_eik) {
     const float gx = p.grad_theta[3 * r], gy = p.grad_theta[3 * r + 1], gz = p.grad_theta[3 * r + 2];
     const float n = sqrtf(gx * gx + gy * gy + gz * gz);
-    const float k = p.eikonal_weight * 2.f * (n - 1.f) / (n * p.n_eik);
+    // |grad_theta| = 0: torch's norm backward yields the zero subgradient there (no 0/0)
+    const float k = n > 0.f ? p.eikonal_weight * 2.f * (n - 1.f) / (n * p.n_eik) : 0.f;
     p.g_theta[3 * r] = k * gx; p.g_theta[3 * r + 1] = k * gy; p.g_theta[3 * r + 2] = k * gz;
   }
 }

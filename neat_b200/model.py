@@ -258,7 +258,7 @@ class VolSDFNetwork(nn.Module):
             m._owner = ref
         self._renderer = None
         self._packed_version = None
-        self.replay = None  # tests: dict(sampler=..., eik_uniform=...) recorded draws to replay
+        self.replay = None  # tests: dict(sampler=..., eik_uniform=..., samples=(z, z_eik)) recorded draws to replay
         # "reference": the training-mode random draws replay the reference's CPU-generator calls in order (same seed =>
         # same samples; costs pageable H2D copies and one device->host read of the sampler's iteration count);
         # "device": the same distributions drawn on the GPU, fully asynchronous.
@@ -368,8 +368,9 @@ class VolSDFNetwork(nn.Module):
         st = StepState()
         st.uv, st.pose, st.K, st.uv_proj = uv, pose, K4, uv_proj
         rn.sampler.rng = self.rng
-        st.sampler_randoms = self.replay["sampler"] if self.replay else None
+        st.sampler_randoms = self.replay.get("sampler") if self.replay else None
         st.eik_uniform = self.replay["eik_uniform"] if self.replay else None
+        st.samples_override = self.replay.get("samples") if self.replay else None
         # global junctions (independent of the render step): enqueue first so that their host copy rides in the step's
         # single device->host transfer
         glob = self.ffn(self.latents)

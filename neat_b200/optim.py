@@ -71,4 +71,8 @@ class Adam(torch.optim.Optimizer):
                     _lib.check(lib.neat_adam_step(arr, len(chunk), float(group["lr"]), float(b1), float(b2),
                                                   float(group["eps"]), float(group["weight_decay"]), step,
                                                   self.grad_scale, _P(torch.cuda.current_stream(dev).cuda_stream)))
+            # the kernel wrote through raw pointers: tell autograd / version-keyed caches (VolSDFNetwork._sync_weights
+            # decides from p._version whether the packed tcgen05 weight slabs are stale) that the parameters changed
+            for p in plist:
+                torch.autograd.graph.increment_version(p)
         return loss

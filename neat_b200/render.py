@@ -309,6 +309,7 @@ class Renderer:
         self.generation += 1  # shares the "render" / head workspaces with a pending training step, if any
         dirs, cam = self.camera_rays(uv, pose, K)
         z, z_eik, n_it = self.sampler.get_z_vals(cam, dirs, beta_param, training=False)
+        self.last_n_iters = n_it
         R, S = z.shape
         M = R * S
         pts = self.ray_points(cam, dirs, z)

@@ -5,6 +5,12 @@ cross-compiled for sm_100a and with the output in oracle/_ref/ (git-ignored, tra
 The `-m gpu` test tests/test_hawp_oracle.py::test_gpu_encodels_vs_reference_kernel loads the built module on the B200
 and compares neat_encodels with the REAL reference kernel.  No reference source is copied into this repository.
 
+Second artefact (round 2): the reference's own PYTHON path for the step -- the seven unmodified files VolSDFNetwork /
+VolSDFLoss import (code/model/{density,embedder,ray_sampler}.py, code/model/networks/{neat_wfr_rend_a,loss_wfr}.py,
+code/utils/{rend_util,general}.py) -- archived byte for byte into oracle/_ref/neat_ref_code.zip (git-ignored build output,
+like the .so; imported through zipimport by oracle/ref_shim.py).  It is what `bench.py --impl reference`, `cpu_baseline`
+and `gpu_eager_baseline` time on the GPU box, where /root/reference does not exist: the UNMODIFIED reference, not a port.
+
     python oracle/build_ref.py            # needs /root/reference; a no-op message otherwise"""
 import os
 import sys
@@ -13,6 +19,29 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_ref")
 NAME = "hawp_ref_C"
 REF_CSRC = os.path.join(os.environ.get("NEAT_REFERENCE_ROOT", "/root/reference"), "third-party", "hawp", "hawp", "base", "csrc")
+
+
+REF_CODE = os.path.join(os.environ.get("NEAT_REFERENCE_ROOT", "/root/reference"), "code")
+CODE_ZIP = os.path.join(OUT, "neat_ref_code.zip")
+CODE_FILES = ["model/density.py", "model/embedder.py", "model/ray_sampler.py", "model/networks/neat_wfr_rend_a.py",
+              "model/networks/loss_wfr.py", "utils/rend_util.py", "utils/general.py"]
+
+
+def stage_code():
+    """Archive the reference's step files (unmodified) into oracle/_ref/neat_ref_code.zip; returns the path or None."""
+    import zipfile
+    srcs = [os.path.join(REF_CODE, f) for f in CODE_FILES]
+    if not all(os.path.exists(s) for s in srcs):
+        return CODE_ZIP if os.path.exists(CODE_ZIP) else None
+    if os.path.exists(CODE_ZIP) and all(os.path.getmtime(CODE_ZIP) >= os.path.getmtime(s) for s in srcs):
+        return CODE_ZIP
+    os.makedirs(OUT, exist_ok=True)
+    with zipfile.ZipFile(CODE_ZIP, "w", zipfile.ZIP_DEFLATED) as z:
+        for d in ("model/", "model/networks/", "utils/"):     # explicit directory entries: namespace packages in a zip
+            z.writestr(zipfile.ZipInfo(d), "")
+        for f, s in zip(CODE_FILES, srcs):
+            z.write(s, f)
+    return CODE_ZIP
 
 
 def built_path():
@@ -38,6 +67,7 @@ def load_built():
 
 
 def build(verbose=False):
+    stage_code()
     srcs = [os.path.join(REF_CSRC, "binding.cpp"), os.path.join(REF_CSRC, "linesegment.cu")]
     if not all(os.path.exists(s) for s in srcs):
         print("reference sources not present (%s): nothing built" % REF_CSRC)

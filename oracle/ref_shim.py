@@ -5,8 +5,10 @@ Loads ``model.networks.neat_wfr_rend_a.VolSDFNetwork`` and
 golden vectors can be generated from the reference itself (``oracle/make_golden.py``)
 and so that the CPU restatement in ``oracle/neat_oracle.py`` can be pinned against it.
 
-It exists only in the build container: ``/root/reference`` is absent on the GPU box, so
-nothing under ``-m gpu``, ``smoke()`` or ``bench.py`` may import this file.
+``/root/reference`` is absent on the GPU box; there the same seven files are imported from
+``oracle/_ref/neat_ref_code.zip`` (built, unmodified, by ``oracle/build_ref.py``).  Only ``bench.py``'s
+reference legs (``--impl reference``, ``cpu_baseline``, ``gpu_eager_baseline``) and tests may import this file --
+never the product path.
 
 What the shim does:
   * stubs the third-party imports the hot path never calls
@@ -24,10 +26,17 @@ import torch
 
 REF_ROOT = os.environ.get("NEAT_REFERENCE_ROOT", "/root/reference")
 REF_CODE = os.path.join(REF_ROOT, "code")
+# the same seven files, archived unmodified by oracle/build_ref.py (travels to the GPU box, where REF_ROOT is absent)
+REF_ZIP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "neat_ref_code.zip")
 
 
 def available() -> bool:
-    return os.path.isdir(os.path.join(REF_CODE, "model", "networks"))
+    return os.path.isdir(os.path.join(REF_CODE, "model", "networks")) or os.path.exists(REF_ZIP)
+
+
+def code_location() -> str:
+    """Where `import model...` resolves: the reference tree when present, else the archive built from it."""
+    return REF_CODE if os.path.isdir(os.path.join(REF_CODE, "model", "networks")) else REF_ZIP
 
 
 class ConfigTree(dict):
@@ -100,12 +109,26 @@ def install():
     stub("pyhocon", ConfigTree=ConfigTree, ConfigFactory=object)
 
     if not torch.cuda.is_available():
+        force_cpu(True)
+
+    loc = code_location()
+    if loc not in sys.path:
+        sys.path.insert(0, loc)
+    _installed = True
+
+
+_orig_cuda = (torch.Tensor.cuda, torch.nn.Module.cuda)
+
+
+def force_cpu(on: bool):
+    """The reference hard-codes `.cuda()` (e.g. code/model/ray_sampler.py:71).  on=True makes Tensor.cuda / Module.cuda
+    the identity so that the unmodified classes run on the host CPU (always the case without a GPU; on the GPU box this is
+    how bench.py times the reference's CPU path); on=False restores torch's own methods (the reference on the B200)."""
+    if on:
         torch.Tensor.cuda = lambda self, *a, **k: self
         torch.nn.Module.cuda = lambda self, *a, **k: self
-
-    if REF_CODE not in sys.path:
-        sys.path.insert(0, REF_CODE)
-    _installed = True
+    else:
+        torch.Tensor.cuda, torch.nn.Module.cuda = _orig_cuda
 
 
 def load_classes():
@@ -115,7 +138,7 @@ def load_classes():
 
     net = importlib.import_module("model.networks.neat_wfr_rend_a")
     loss = importlib.import_module("model.networks.loss_wfr")
-    assert net.__file__.startswith(REF_CODE), net.__file__
+    assert net.__file__.startswith(code_location()), net.__file__
     return net.VolSDFNetwork, loss.VolSDFLoss, net, loss
 
 

@@ -1,5 +1,6 @@
-"""CPU: the reference arm of bench.py (`--impl reference`: the CPU port of the reference algorithm, no GPU needed)
-prints ONE JSON line with the keys the driver's contract names."""
+"""CPU: the reference arm of bench.py (`--impl reference`: the UNMODIFIED reference classes on the host CPU, imported from
+/root/reference or from the archive oracle/build_ref.py makes of them; no GPU needed) prints ONE JSON line with the keys
+the driver's contract names.  The test shrinks the batch (--cpu-rays) to keep the CPU suite short."""
 import json
 import os
 import subprocess
@@ -9,7 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_the_contract_line():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-rays", "64"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
@@ -21,6 +23,8 @@ def test_reference_arm_prints_the_contract_line():
         assert k in d, k
     assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None and d["data"] == "synthetic"
     assert "workload" in d["config"] and "model" not in d["config"]
+    assert "64 rays" in d["config"]["workload"] and d["config"]["rays_per_step"] == 64    # says what it ran
+    assert "bf16" not in json.dumps(d["config"])                                          # ... and not our arm's config
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
     e = d["e2e"]
