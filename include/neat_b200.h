@@ -371,6 +371,34 @@ typedef struct {
 int neat_adam_step(const neat_adam_tensor* tensors, int n, float lr, float beta1, float beta2, float eps,
                    float weight_decay, int step, float grad_scale, void* stream);
 
+/* ---- the training step without the host in it (round 2): everything below exists so that one step can be replayed as
+ * CUDA graphs (neat_b200.trainer.FusedTrainStep): no eager PyTorch kernels, no host-side counters. -------------------- */
+/* Every random draw of one training forward in ONE launch (Philox4x32-10 keyed by seed and a device-resident draw counter
+ * that the kernel bumps itself: counter_dev = 2 x uint64, zero-initialised).  Same DISTRIBUTIONS as the reference's CPU
+ * draws: t_rand [R,n_eval] ~ U[0,1) (code/model/ray_sampler.py:87), u_final [R,n_final] ~ U[0,1) (:234), extra_idx
+ * [max_iters,n_extra] row k-1 = the first n_extra entries of a uniform random permutation of [0, n_eval*k) (:265),
+ * eik_idx [R] ~ U{0..n_final+2+n_extra-1} (:275), eik_uniform [R,3] ~ U(-radius, radius)
+ * (code/model/networks/neat_wfr_rend_a.py:518).                                                                    */
+int neat_train_draws(const neat_sampler_config* cfg, int R, float radius, unsigned long long seed,
+                     unsigned long long* counter_dev, float* t_rand, float* u_final, int64_t* extra_idx, int64_t* eik_idx,
+                     float* eik_uniform, void* stream);
+/* fp32 GEMM C[M,N] (+)= op(A) op(B) for the junction `ffn` (nn.Sequential of 3 Linear layers on the 1024 latents,
+ * neat_wfr_rend_a.py:274-303, 488) and its backward: row-major with leading dimensions; ta: A stored [K,M]; tb: B stored
+ * [N,K] (a Linear weight); optional bias [N], ReLU, ReLU-adjoint mask (C = mask > 0 ? C : 0), accumulate.          */
+int neat_gemm_f32(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc, int ta, int tb,
+                  const float* bias, int relu, const float* mask, int ldm, int accumulate, void* stream);
+/* out[n] (+)= sum_m X[m,n] (bias gradients) */
+int neat_colsum_f32(const float* X, int M, int N, int ldx, float* out, int accumulate, void* stream);
+/* neat_junction_terms + _backward with the pair count read from DEVICE memory (it changes every step): packed = [n | rows
+ * [cap] | cols [cap] (int32) | local [cap,7] (float: xyz, uv, uv_calib)], the one host->device copy of the step.  out[3] =
+ * j3d_loss, j2d_loss, j2d_stat; g_* = d (w3 out[0] + w2 out[1]) / d (global junctions [G,3], calibrated projections [G,2]). */
+int neat_junction_step(const int* packed_dev, int cap, int n_global, const float* j3d_global, const float* j2d_global_calib,
+                       const float* j2d_global, float w3, float w2, float* out, float* g_j3d_global,
+                       float* g_j2d_global_calib, void* stream);
+/* neat_adam_step with the step count and hyper-parameters in device memory: hyper_dev[6] = lr, beta1, beta2, eps,
+ * weight_decay, grad_scale; state_dev[3] = step count (bumped here), 1 - beta1^step, 1/sqrt(1 - beta2^step).        */
+int neat_adam_step_device(const neat_adam_tensor* tensors, int n, const float* hyper_dev, float* state_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

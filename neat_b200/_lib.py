@@ -77,6 +77,11 @@ SIGNATURES = {
     "neat_sdf_bwd_scratch_bytes": (ctypes.c_size_t, [_P, _I]),
     "neat_sdf_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "neat_weight_gradients": (_I, [_P, _P, _I, _P, _P]),
+    "neat_train_draws": (_I, [_P, _I, ctypes.c_float, ctypes.c_ulonglong, _P, _P, _P, _P, _P, _P, _P]),
+    "neat_gemm_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P]),
+    "neat_colsum_f32": (_I, [_P, _I, _I, _I, _P, _I, _P]),
+    "neat_junction_step": (_I, [_P, _I, _I, _P, _P, _P, ctypes.c_float, ctypes.c_float, _P, _P, _P, _P]),
+    "neat_adam_step_device": (_I, [_P, _I, _P, _P, _P]),
 }
 
 

@@ -25,6 +25,7 @@
 #include "wgrad.cuh"
 #include "junction.cuh"
 #include "adam.cuh"
+#include "train_aux.cuh"
 #include "parsing.cuh"
 #include "pixels.cuh"
 
@@ -68,6 +69,7 @@ Step mk_step(const PLayer& w, int buf, int wait_a, int wait_aux, int commit_d) {
   s.wait_a = static_cast<uint8_t>(wait_a);
   s.wait_aux = static_cast<uint8_t>(wait_aux);
   s.commit_d = static_cast<uint8_t>(commit_d);
+  s.comp = 1.0f + 0.35f * 3.0f * static_cast<float>(w.nk_main + w.nk_aux) * 5.9604645e-08f;  // 3 MMAs per k-step
   return s;
 }
 }  // namespace
@@ -76,7 +78,8 @@ struct neat_ctx {
   Plan plan;
   int device = 0;
   int num_sms = 0;
-  uint8_t* packed = nullptr;
+  uint8_t* packed = nullptr;      // weight slabs as fp16 pairs + fp32 biases: the forward programs
+  uint8_t* packed_bf = nullptr;   // the same layout with bf16 pairs: the backward programs
   int32_t* g_src = nullptr;
   uint32_t *g_dst_hi = nullptr, *g_dst_lo = nullptr;
   float* g_scale = nullptr;
@@ -105,24 +108,34 @@ static inline int grid_for(const neat_ctx* c, int M) {
 }
 
 // ---------------------------------------------------------------- packing kernels
-__global__ void pack_bf16_kernel(const float* __restrict__ flat, const int32_t* __restrict__ src,
-                                 const uint32_t* __restrict__ dst_hi, const uint32_t* __restrict__ dst_lo,
-                                 const float* __restrict__ scale, int n, __nv_bfloat16* __restrict__ packed) {
+// weights -> hi / lo operand slabs: fp16 pairs (packed_f16: ~2^-22 relative, the forward programs) and bf16 pairs
+// (packed_bf16: the backward programs, whose activations are bf16 pairs)
+__global__ void pack_pairs_kernel(const float* __restrict__ flat, const int32_t* __restrict__ src,
+                                  const uint32_t* __restrict__ dst_hi, const uint32_t* __restrict__ dst_lo,
+                                  const float* __restrict__ scale, int n, uint16_t* __restrict__ packed_f16,
+                                  uint16_t* __restrict__ packed_bf16) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int s = src[i];
   const float v = s >= 0 ? flat[s] * scale[i] : 0.f;
   __nv_bfloat16 hi, lo;
   split_bf16(v, hi, lo);
-  packed[dst_hi[i]] = hi;
-  packed[dst_lo[i]] = lo;
+  packed_bf16[dst_hi[i]] = __bfloat16_as_ushort(hi);
+  packed_bf16[dst_lo[i]] = __bfloat16_as_ushort(lo);
+  const float vc = fminf(fmaxf(v, -65504.f), 65504.f);
+  const __half h = __float2half_rn(vc);
+  const __half l = __float2half_rn(vc - __half2float(h));
+  packed_f16[dst_hi[i]] = __half_as_ushort(h);
+  packed_f16[dst_lo[i]] = __half_as_ushort(l);
 }
 __global__ void pack_f32_kernel(const float* __restrict__ flat, const int32_t* __restrict__ src,
-                                const uint32_t* __restrict__ dst, int n, float* __restrict__ packed) {
+                                const uint32_t* __restrict__ dst, int n, float* __restrict__ packed, float* __restrict__ packed2) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int s = src[i];
-  packed[dst[i]] = s >= 0 ? flat[s] : 0.f;
+  const float v = s >= 0 ? flat[s] : 0.f;
+  packed[dst[i]] = v;
+  packed2[dst[i]] = v;
 }
 
 extern "C" {
@@ -146,6 +159,9 @@ static int init_ctx(neat_ctx* c, const neat_net_config* cfg) {
   const GatherTables& g = c->plan.g;
   CK(cudaMalloc(&c->packed, c->plan.packed_bytes));
   CK(cudaMemset(c->packed, 0, c->plan.packed_bytes));
+  CK(cudaMalloc(&c->packed_bf, c->plan.packed_bytes));
+  CK(cudaMemset(c->packed_bf, 0, c->plan.packed_bytes));
+
   CK(upload(g.src, &c->g_src));
   CK(upload(g.dst_hi, &c->g_dst_hi));
   CK(upload(g.dst_lo, &c->g_dst_lo));
@@ -211,6 +227,10 @@ static int init_ctx(neat_ctx* c, const neat_net_config* cfg) {
     CK(cudaMalloc(&c->ones_tile, TILE_AUX_BYTES));
     CK(cudaMemcpy(c->ones_tile, ones.data(), TILE_AUX_BYTES, cudaMemcpyHostToDevice));
   }
+  // operand formats (umma.cuh): the forward programs multiply fp16 x fp16 pairs, the backward ones bf16 x bf16 (the
+  // hardware rejects mixed formats; backward tensors need bf16's range), each from its own copy of the weight slabs
+  for (Program* p : {&c->prog_query, &c->prog_render, &c->prog_head[0], &c->prog_head[1]}) p->a_f16 = p->b_f16 = 1;
+  for (Program* p : {&c->prog_head_bwd[0], &c->prog_head_bwd[1], &c->prog_sdf_bwd}) p->a_f16 = p->b_f16 = 0;
   CK(cudaFuncSetAttribute(head_bwd_kernel<RENDER_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           static_cast<int>(engine_smem_bytes(RENDER_STAGES))));
   CK(cudaFuncSetAttribute(sdf_bwd_kernel<RENDER_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -242,6 +262,7 @@ int neat_create(const neat_net_config* cfg, neat_ctx** out) {
 void neat_destroy(neat_ctx* c) {
   if (!c) return;
   cudaFree(c->packed);
+  cudaFree(c->packed_bf);
   cudaFree(c->g_src);
   cudaFree(c->g_dst_hi);
   cudaFree(c->g_dst_lo);
@@ -333,10 +354,12 @@ int neat_pack_weights(neat_ctx* c, const float* flat, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int n = static_cast<int>(c->plan.g.src.size());
   const int nf = static_cast<int>(c->plan.g.fsrc.size());
-  pack_bf16_kernel<<<(n + 255) / 256, 256, 0, st>>>(flat, c->g_src, c->g_dst_hi, c->g_dst_lo, c->g_scale, n,
-                                                   reinterpret_cast<__nv_bfloat16*>(c->packed));
+  pack_pairs_kernel<<<(n + 255) / 256, 256, 0, st>>>(flat, c->g_src, c->g_dst_hi, c->g_dst_lo, c->g_scale, n,
+                                                    reinterpret_cast<uint16_t*>(c->packed),
+                                                    reinterpret_cast<uint16_t*>(c->packed_bf));
   ++g_launches;
-  pack_f32_kernel<<<(nf + 255) / 256, 256, 0, st>>>(flat, c->g_fsrc, c->g_fdst, nf, reinterpret_cast<float*>(c->packed));
+  pack_f32_kernel<<<(nf + 255) / 256, 256, 0, st>>>(flat, c->g_fsrc, c->g_fdst, nf, reinterpret_cast<float*>(c->packed),
+                                                   reinterpret_cast<float*>(c->packed_bf));
   ++g_launches;
   CK(cudaGetLastError());
   return NEAT_OK;
@@ -906,6 +929,104 @@ int neat_adam_step(const neat_adam_tensor* tensors, int n, float lr, float beta1
   return NEAT_OK;
 }
 
+// graph-replayable variant: step count, bias corrections and hyper-parameters live in device memory (train_aux.cuh)
+int neat_adam_step_device(const neat_adam_tensor* tensors, int n, const float* hyper_dev, float* state_dev, void* stream) {
+  if (n <= 0 || n > ADAM_MAX_TENSORS || !tensors || !hyper_dev || !state_dev) return fail(NEAT_EINVAL, "bad argument");
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) return fail(NEAT_EINVAL, "device index out of range");
+  AdamCache& c = g_adam[dev];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static thread_local AdamTable t;
+  std::memset(&t, 0, sizeof(t));
+  t.n = n;
+  int blocks = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!tensors[i].param || !tensors[i].grad || !tensors[i].exp_avg || !tensors[i].exp_avg_sq || tensors[i].numel < 0)
+      return fail(NEAT_EINVAL, "adam: null tensor");
+    t.t[i] = tensors[i];
+    t.blk_start[i] = blocks;
+    blocks += static_cast<int>((tensors[i].numel + ADAM_BLOCK_ELEMS - 1) / ADAM_BLOCK_ELEMS);
+  }
+  for (int i = n; i <= ADAM_MAX_TENSORS; ++i) t.blk_start[i] = blocks;
+  int hit = -1;
+  for (int i = 0; i < c.n && hit < 0; ++i)
+    if (std::memcmp(c.host[i], &t, sizeof(AdamTable)) == 0) hit = i;
+  if (hit < 0) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    if (cs != cudaStreamCaptureStatusNone)
+      return fail(NEAT_EINVAL, "adam: a new tensor list cannot be uploaded during stream capture (run one eager step first)");
+    hit = c.n < AdamCache::MAX ? c.n++ : (c.next++ % AdamCache::MAX);
+    if (!c.host[hit]) c.host[hit] = new AdamTable();
+    if (!c.dev[hit]) CK(cudaMalloc(&c.dev[hit], sizeof(AdamTable)));
+    CK(cudaStreamSynchronize(st));
+    *c.host[hit] = t;
+    CK(cudaMemcpyAsync(c.dev[hit], c.host[hit], sizeof(AdamTable), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  if (blocks == 0) return NEAT_OK;
+  adam_prepare_kernel<<<1, 32, 0, st>>>(hyper_dev, state_dev);
+  ++g_launches;
+  adam_graph_kernel<<<blocks, 256, 0, st>>>(c.dev[hit], hyper_dev, state_dev);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+// ---------------------------------------------------------------- training-step helpers (train_aux.cuh)
+int neat_train_draws(const neat_sampler_config* s, int R, float radius, unsigned long long seed,
+                     unsigned long long* counter_dev, float* t_rand, float* u_final, int64_t* extra_idx, int64_t* eik_idx,
+                     float* eik_uniform, void* stream) {
+  if (!s || R <= 0 || !counter_dev || !t_rand || !u_final || !eik_idx || !eik_uniform || (s->n_extra > 0 && !extra_idx))
+    return fail(NEAT_EINVAL, "bad argument");
+  if (int e = check_sampler_cfg(s)) return e;
+  DrawParams p{};
+  p.R = R; p.n_eval = s->n_eval; p.n_final = s->n_final; p.n_extra = s->n_extra; p.max_iters = s->max_iters;
+  p.n_out = s->n_final + 2 + s->n_extra;
+  p.radius = radius; p.seed = seed; p.counter = counter_dev;
+  p.t_rand = t_rand; p.u_final = u_final; p.extra_idx = reinterpret_cast<long long*>(extra_idx);
+  p.eik_idx = reinterpret_cast<long long*>(eik_idx); p.eik_uniform = eik_uniform;
+  const long long quads = (static_cast<long long>(R) * (s->n_eval + s->n_final + 4) + 3) / 4 + s->max_iters * s->n_extra;
+  const int grid = static_cast<int>(std::min<long long>((quads + 255) / 256, 148 * 8));
+  train_draws_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+int neat_gemm_f32(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc, int ta, int tb,
+                  const float* bias, int relu, const float* mask, int ldm, int accumulate, void* stream) {
+  if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) return fail(NEAT_EINVAL, "bad argument");
+  GemmParams p{A, B, C, M, N, K, lda, ldb, ldc, ta, tb, bias, relu, mask, ldm, accumulate};
+  gemm_f32_kernel<<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+int neat_colsum_f32(const float* X, int M, int N, int ldx, float* out, int accumulate, void* stream) {
+  if (!X || !out || M <= 0 || N <= 0) return fail(NEAT_EINVAL, "bad argument");
+  colsum_f32_kernel<<<(N + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(X, M, N, ldx, out, accumulate);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
+int neat_junction_step(const int* packed_dev, int cap, int n_global, const float* j3d_global, const float* j2d_global_calib,
+                       const float* j2d_global, float w3, float w2, float* out, float* g_j3d_global,
+                       float* g_j2d_global_calib, void* stream) {
+  if (!packed_dev || cap <= 0 || n_global <= 0 || !j3d_global || !j2d_global_calib || !j2d_global || !out || !g_j3d_global ||
+      !g_j2d_global_calib)
+    return fail(NEAT_EINVAL, "bad argument");
+  JunctionStepParams p{packed_dev, cap, n_global, j3d_global, j2d_global_calib, j2d_global, w3, w2, out, g_j3d_global,
+                       g_j2d_global_calib};
+  junction_step_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
 // ---------------------------------------------------------------- junction clustering
 namespace {
 int db_table_size(int N) {
@@ -993,7 +1114,7 @@ int neat_head_backward(neat_ctx* c, int head, int M, const float* out_bar, const
     p.prog.pf_base = static_cast<const uint8_t*>(fwd_save);
     p.prog.pf_stride = head_save_layout(c->plan.cfg.head_layers).total;
   }
-  p.packed = c->packed;
+  p.packed = c->packed_bf;
   p.M = M; p.HL = c->plan.cfg.head_layers; p.out_dim = head == 0 ? 3 : 6;
   p.out_bar = out_bar;
   p.fwd_save = static_cast<const uint8_t*>(fwd_save);
@@ -1026,7 +1147,7 @@ int neat_sdf_backward(neat_ctx* c, const neat_points* pts, const float* n_bar, c
     p.prog.pf_base = static_cast<const uint8_t*>(fwd_save);
     p.prog.pf_stride = sdf_save_layout(g.sdf_layers, true).total;
   }
-  p.packed = c->packed;
+  p.packed = c->packed_bf;
   p.L = g.sdf_layers; p.skip = g.sdf_skip; p.H = g.sdf_hidden; p.E = c->plan.E; p.F = g.feat;
   p.n_bar = n_bar; p.s_bar = s_bar; p.feat_bar = feat_bar; p.act = act;
   p.fwd_save = static_cast<const uint8_t*>(fwd_save);
@@ -1040,17 +1161,18 @@ int neat_sdf_backward(neat_ctx* c, const neat_points* pts, const float* n_bar, c
 }
 
 namespace {
-struct Planes {  // an operand: per-tile base + stride, offsets of the hi / lo planes, columns available
+struct Planes {  // an operand: per-tile base + stride, offsets of the hi / lo planes, columns available, format
   const uint8_t* base;
   uint64_t stride;
   uint32_t hi, lo;
   int cols;
+  int f16;  // 1: fp16 pairs (written by a forward kernel), 0: bf16 pairs (written by a backward kernel)
 };
-Planes main_planes(const void* base, uint64_t stride, uint32_t off, int cols) {
-  return Planes{static_cast<const uint8_t*>(base), stride, off, off + PLANE_MAIN_BYTES, cols};
+Planes main_planes(const void* base, uint64_t stride, uint32_t off, int cols, int f16) {
+  return Planes{static_cast<const uint8_t*>(base), stride, off, off + PLANE_MAIN_BYTES, cols, f16};
 }
-Planes aux_planes(const void* base, uint64_t stride, uint32_t off, int cols) {
-  return Planes{static_cast<const uint8_t*>(base), stride, off, off + PLANE_AUX_BYTES, cols};
+Planes aux_planes(const void* base, uint64_t stride, uint32_t off, int cols, int f16) {
+  return Planes{static_cast<const uint8_t*>(base), stride, off, off + PLANE_AUX_BYTES, cols, f16};
 }
 inline int c16(int x) { return (x + 15) / 16 * 16; }
 inline int c8(int x) { return (x + 7) / 8 * 8; }
@@ -1073,6 +1195,7 @@ void add_gemm(std::vector<WJob>& jobs, const Planes& X, int x_valid, const Plane
       j.out = out; j.ld = ld; j.row0 = row0 + m0; j.col0 = col0; j.scale = scale;
       j.bias = bias;
       j.n_tiles = n_tiles; j.split = sp; j.n_split = n_split;
+      j.x_f16 = X.f16; j.y_f16 = Y.f16;
       jobs.push_back(j);
     }
   }
@@ -1098,9 +1221,9 @@ int neat_weight_gradients(neat_ctx* c, const neat_grad_group* groups, int n_grou
     // 6272 tiles -> 32 splits 10.9 -> 9.6..10.1 ms; more splits only add flush traffic).  NEAT_WGRAD_SPLIT overrides the cap.
     const int ns = std::max(1, std::min(c->wgrad_max_split, nt / std::max(1, c->wgrad_tiles_per_split)));
     if (G.sdf_fwd_save && G.sdf_bwd_save) {
-      const Planes pe = aux_planes(G.sdf_fwd_save, fl.total, fl.pe, c16(E));
-      const Planes p0 = aux_planes(G.sdf_bwd_save, bl.total, bl.p_aux, c16(E));
-      const Planes ones = aux_planes(c->ones_tile, 0, 0, 16);
+      const Planes pe = aux_planes(G.sdf_fwd_save, fl.total, fl.pe, c16(E), 0);
+      const Planes p0 = aux_planes(G.sdf_bwd_save, bl.total, bl.p_aux, c16(E), 0);
+      const Planes ones = aux_planes(c->ones_tile, 0, 0, 16, 0);
       for (int l = 0; l < L; ++l) {
         const LinearDims d = P.sdf[l];
         float* Wg = flat + d.w_off;
@@ -1108,10 +1231,10 @@ int neat_weight_gradients(neat_ctx* c, const neat_grad_group* groups, int n_grou
         // ---- reverse-sweep term: z_bar_l^T u_l
         std::vector<std::pair<Planes, std::pair<int, int>>> xs;  // (planes, (rows valid, row0))
         if (l < L - 1) {
-          xs.push_back({main_planes(G.sdf_bwd_save, bl.total, bl.zb + l * TILE_MAIN_BYTES, P.sdf_f[l].npad), {d.out, 0}});
+          xs.push_back({main_planes(G.sdf_bwd_save, bl.total, bl.zb + l * TILE_MAIN_BYTES, P.sdf_f[l].npad, 0), {d.out, 0}});
         } else {
-          xs.push_back({aux_planes(G.sdf_bwd_save, bl.total, bl.zb_aux, 16), {1, 0}});
-          xs.push_back({main_planes(G.sdf_bwd_save, bl.total, bl.zb + l * TILE_MAIN_BYTES, F), {F, 1}});
+          xs.push_back({aux_planes(G.sdf_bwd_save, bl.total, bl.zb_aux, 16, 0), {1, 0}});
+          xs.push_back({main_planes(G.sdf_bwd_save, bl.total, bl.zb + l * TILE_MAIN_BYTES, F, 0), {F, 1}});
         }
         for (auto& xe : xs) {
           const Planes& X = xe.first;
@@ -1119,27 +1242,27 @@ int neat_weight_gradients(neat_ctx* c, const neat_grad_group* groups, int n_grou
           if (l == 0) {
             add_gemm(jobs, X, xv, pe, E, Wg, d.in, r0, 0, 1.f, bg, nt, ns);
           } else if (l == S) {
-            const Planes um = main_planes(G.sdf_fwd_save, fl.total, fl.u + (l - 1) * TILE_MAIN_BYTES, H - E);
+            const Planes um = main_planes(G.sdf_fwd_save, fl.total, fl.u + (l - 1) * TILE_MAIN_BYTES, H - E, 0);
             add_gemm(jobs, X, xv, um, H - E, Wg, d.in, r0, 0, rs2, nullptr, nt, ns);
             add_gemm(jobs, X, xv, pe, E, Wg, d.in, r0, H - E, rs2, nullptr, nt, ns);
             // bias gradient is unscaled: a separate ones-only job through the aux planes (E columns, none written)
             add_gemm(jobs, X, xv, pe, 0, Wg, d.in, r0, 0, 1.f, bg, nt, ns);
           } else {
-            const Planes um = main_planes(G.sdf_fwd_save, fl.total, fl.u + (l - 1) * TILE_MAIN_BYTES, d.in);
+            const Planes um = main_planes(G.sdf_fwd_save, fl.total, fl.u + (l - 1) * TILE_MAIN_BYTES, d.in, 0);
             add_gemm(jobs, X, xv, um, d.in, Wg, d.in, r0, 0, 1.f, bg, nt, ns);
           }
         }
         // ---- tangent term: a_l^T p_in
-        const Planes A = l < L - 1 ? main_planes(G.sdf_fwd_save, fl.total, fl.a + l * TILE_MAIN_BYTES, P.sdf_f[l].npad) : ones;
+        const Planes A = l < L - 1 ? main_planes(G.sdf_fwd_save, fl.total, fl.a + l * TILE_MAIN_BYTES, P.sdf_f[l].npad, 0) : ones;
         const int av = l < L - 1 ? d.out : 1;
         if (l == 0) {
           add_gemm(jobs, A, av, p0, E, Wg, d.in, 0, 0, 1.f, nullptr, nt, ns);
         } else if (l == S) {
-          const Planes pm = main_planes(G.sdf_bwd_save, bl.total, bl.p + (l - 1) * TILE_MAIN_BYTES, H - E);
+          const Planes pm = main_planes(G.sdf_bwd_save, bl.total, bl.p + (l - 1) * TILE_MAIN_BYTES, H - E, 0);
           add_gemm(jobs, A, av, pm, H - E, Wg, d.in, 0, 0, rs2, nullptr, nt, ns);
           add_gemm(jobs, A, av, p0, E, Wg, d.in, 0, H - E, rs2, nullptr, nt, ns);
         } else {
-          const Planes pm = main_planes(G.sdf_bwd_save, bl.total, bl.p + (l - 1) * TILE_MAIN_BYTES, d.in);
+          const Planes pm = main_planes(G.sdf_bwd_save, bl.total, bl.p + (l - 1) * TILE_MAIN_BYTES, d.in, 0);
           add_gemm(jobs, A, av, pm, d.in, Wg, d.in, 0, 0, 1.f, nullptr, nt, ns);
         }
       }
@@ -1152,15 +1275,15 @@ int neat_weight_gradients(neat_ctx* c, const neat_grad_group* groups, int n_grou
         const LinearDims d = net[l];
         float* Wg = flat + d.w_off;
         float* bg = flat + d.b_off;
-        const Planes X = l < HL - 1 ? main_planes(G.head_bwd_save[h], hbl.total, hbl.zb + l * TILE_MAIN_BYTES, d.out)
-                                    : aux_planes(G.head_bwd_save[h], hbl.total, hbl.zb_aux, 16);
+        const Planes X = l < HL - 1 ? main_planes(G.head_bwd_save[h], hbl.total, hbl.zb + l * TILE_MAIN_BYTES, d.out, 0)
+                                    : aux_planes(G.head_bwd_save[h], hbl.total, hbl.zb_aux, 16, 0);
         if (l == 0) {
-          const Planes ft = main_planes(G.feat_tiles, TILE_MAIN_BYTES, 0, F);
-          const Planes ax = aux_planes(G.head_fwd_save[h], hfl.total, hfl.aux, c16(aux_in));
+          const Planes ft = main_planes(G.sdf_fwd_save, fl.total, fl.feat, F, 0);  // the bf16 copy in the save record
+          const Planes ax = aux_planes(G.head_fwd_save[h], hfl.total, hfl.aux, c16(aux_in), 0);
           add_gemm(jobs, X, d.out, ft, F, Wg, d.in, 0, aux_in, 1.f, bg, nt, ns);
           add_gemm(jobs, X, d.out, ax, aux_in, Wg, d.in, 0, 0, 1.f, nullptr, nt, ns);
         } else {
-          const Planes um = main_planes(G.head_fwd_save[h], hfl.total, hfl.u + (l - 1) * TILE_MAIN_BYTES, d.in);
+          const Planes um = main_planes(G.head_fwd_save[h], hfl.total, hfl.u + (l - 1) * TILE_MAIN_BYTES, d.in, 0);
           add_gemm(jobs, X, d.out, um, d.in, Wg, d.in, 0, 0, 1.f, bg, nt, ns);
         }
       }
@@ -1226,8 +1349,11 @@ long long neat_launch_count(void) { return g_launches.load(); }
 int neat_set_precision(neat_ctx* c, int fast) {
   if (!c) return fail(NEAT_EINVAL, "null context");
   for (Program* p : {&c->prog_query, &c->prog_render, &c->prog_head[0], &c->prog_head[1], &c->prog_head_bwd[0],
-                     &c->prog_head_bwd[1], &c->prog_sdf_bwd})
+                     &c->prog_head_bwd[1], &c->prog_sdf_bwd}) {
     p->fast = fast ? 1 : 0;
+    for (int i = 0; i < p->n; ++i)
+      p->s[i].comp = 1.0f + 0.35f * (fast ? 1.0f : 3.0f) * static_cast<float>(p->s[i].w.nk_main + p->s[i].w.nk_aux) * 5.9604645e-08f;
+  }
   return NEAT_OK;
 }
 

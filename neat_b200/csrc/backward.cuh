@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_bwd_kernel(const __grid_c
             if (c < p.out_dim) a[c] = p.out_bar[static_cast<size_t>(pt) * p.out_dim + c];
         }
 #pragma unroll
-        for (int i = 0; i < A_AUX_COLS / 8; ++i) store_a8(sm.a_hi, sm.a_lo, e.row, A_MAIN_COLS + 8 * i, a + 8 * i);
+        for (int i = 0; i < A_AUX_COLS / 8; ++i) store_a8<false>(sm.a_hi, sm.a_lo, e.row, A_MAIN_COLS + 8 * i, a + 8 * i);
         epi_publish_aux(sm);
       }
       epi_publish_all(sm);
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_bwd_kernel(const __grid_c
 #pragma unroll
             for (int k = 0; k < 16; ++k)
               if (!((m >> k) & 1u)) acc[k] = 0.f;
-            store_a16_save(sm.a_hi, sm.a_lo, zsave, e.row, c0, acc);  // (global stores after the publish: spills here)
+            store_a16_save<false>(sm.a_hi, sm.a_lo, zsave, e.row, c0, acc);  // (global stores after the publish: spills here)
           }
           epi_publish_group(sm, g);
         }
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
           }
         }
 #pragma unroll
-        for (int i = 0; i < A_AUX_COLS / 8; ++i) store_a8(sm.a_hi, sm.a_lo, e.row, A_MAIN_COLS + 8 * i, a + 8 * i);
+        for (int i = 0; i < A_AUX_COLS / 8; ++i) store_a8<false>(sm.a_hi, sm.a_lo, e.row, A_MAIN_COLS + 8 * i, a + 8 * i);
         epi_publish_aux(sm);
       }
       epi_publish_all(sm);
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
           if (c < npad) {
             float a[8], q[8];
             tmem_ld8(e.tm + st.d_col + c, q);
-            unpack_hilo8(ah, al, a);
+            unpack_hilo8<false>(ah, al, a);
             tmem_ld_wait();
             float zv[8];
 #pragma unroll
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
             }
             *f4_at(zh, c, e.row) = make_float4(zv[0], zv[1], zv[2], zv[3]);
             *f4_at(zh, c + 4, e.row) = make_float4(zv[4], zv[5], zv[6], zv[7]);
-            store_a8_save(sm.a_hi, sm.a_lo, psave, e.row, c, q);
+            store_a8_save<false>(sm.a_hi, sm.a_lo, psave, e.row, c, q);
           }
           if ((u & 1) && l < L - 2) epi_publish_group(sm, u >> 1);  // -> F_{l+1}
         }
@@ -340,15 +340,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
               v[4 * j] = valid ? t.x : 0.f; v[4 * j + 1] = valid ? t.y : 0.f;
               v[4 * j + 2] = valid ? t.z : 0.f; v[4 * j + 3] = valid ? t.w : 0.f;
             }
-            store_a16(sm.a_hi, sm.a_lo, e.row, c0, v);
+            store_a16<false>(sm.a_hi, sm.a_lo, e.row, c0, v);
           }
         }
         if (e.j == 0) {
           float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
           const float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
           if (valid && p.s_bar) a8[0] = p.s_bar[pt];  // already masked by act (composite_bwd)
-          store_a8(sm.a_hi, sm.a_lo, e.row, A_MAIN_COLS, a8);
-          store_a8(sm.a_hi, sm.a_lo, e.row, A_MAIN_COLS + 8, zero8);
+          store_a8<false>(sm.a_hi, sm.a_lo, e.row, A_MAIN_COLS, a8);
+          store_a8<false>(sm.a_hi, sm.a_lo, e.row, A_MAIN_COLS + 8, zero8);
           epi_publish_aux(sm);
         }
       }
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 8; ++j) gq[j] = s1[j] * gq[j] + zz[j];
-            store_a8_save(sm.a_hi, sm.a_lo, zsave, e.row, c, gq);
+            store_a8_save<false>(sm.a_hi, sm.a_lo, zsave, e.row, c, gq);
           }
           if ((u & 1) && l >= 2) epi_publish_group(sm, u >> 1);  // -> T_{l-1}
         }

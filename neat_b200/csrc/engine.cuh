@@ -144,7 +144,7 @@ __device__ __forceinline__ void mma_loop(EngineSmem<STAGES>& sm, const Program& 
     for (int i = 0; i < prog.n; ++i) {
       const Step st = prog.s[i];
       const uint32_t npad = st.w.npad;
-      const uint32_t idesc = make_idesc(TILE_M, npad, 0, 0);
+      const uint32_t idesc = make_idesc(TILE_M, npad, 0, 0, prog.a_f16, prog.b_f16);
       const uint32_t d = tmem + st.d_col;
       const uint64_t db0 = make_desc_k(w0, npad * 16, 128);  // stage 0, hi plane; lo plane = + npad * 32 bytes
       const uint32_t b_lo_off = (npad * 32) >> 4;
@@ -230,13 +230,17 @@ __device__ __forceinline__ int epi_col(const Epi& e, int g) { return g * GROUP_C
 constexpr int N_UNITS = 2 * N_GROUPS;
 __device__ __forceinline__ int epi_unit_col(const Epi& e, int u) { return (u >> 1) * GROUP_COLS + 16 * e.j + 8 * (u & 1); }
 __device__ __forceinline__ uint4 ldg128(const uint8_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
-// fp32 values of 8 columns from the raw hi / lo vectors of an operand tile row
+// fp32 values of 8 columns from the raw hi / lo vectors of an operand tile row (F16: the tile holds fp16 pairs)
+template <bool F16>
 __device__ __forceinline__ void unpack_hilo8(const uint4& h, const uint4& l, float* v) {
   const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    v[2 * i] = __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
-    v[2 * i + 1] = __uint_as_float(hw[i] & 0xFFFF0000u) + __uint_as_float(lw[i] & 0xFFFF0000u);
+    float h0, h1, l0, l1;
+    unpack2<F16>(hw[i], h0, h1);
+    unpack2<F16>(lw[i], l0, l1);
+    v[2 * i] = h0 + l0;
+    v[2 * i + 1] = h1 + l1;
   }
 }
 // fp32 per-tile tensors that only travel between epilogues (sigma', zhat, feat_bar) are stored [col / 4][row][4]: a thread's
@@ -314,13 +318,14 @@ __device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 // write 16 / 8 consecutive columns [c0, ...) of row `row` (c0 % 8 == 0) into the A tile
+template <bool F16>
 __device__ __forceinline__ void store_a16(uint8_t* a_hi, uint8_t* a_lo, int row, int c0, const float* v) {
   const uint32_t off = (c0 >> 3) * A_CHUNK_BYTES + row * 16;
   const uint32_t s_hi = smem_u32(a_hi) + off, s_lo = smem_u32(a_lo) + off;
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     uint4 hi, lo;
-    split8(v + 8 * j, hi, lo);
+    split8<F16>(v + 8 * j, hi, lo);
     sts128(s_hi + j * A_CHUNK_BYTES, hi);
     sts128(s_lo + j * A_CHUNK_BYTES, lo);
   }
@@ -331,13 +336,14 @@ __device__ __forceinline__ void store_a16(uint8_t* a_hi, uint8_t* a_lo, int row,
 // store had to fit into the ~3 us of the next layer's MMAs -- 40 GB/s per SM, the whole HBM write bandwidth in bursts.
 // Measured with the stores disabled: 20-27 % of every training kernel.  Written from registers (each warp stores 512
 // contiguous bytes per chunk, streaming hint) nothing waits for them.  gtile == nullptr: shared memory only.
+template <bool F16>
 __device__ __forceinline__ void store_a16_save(uint8_t* a_hi, uint8_t* a_lo, uint8_t* gtile, int row, int c0, const float* v) {
   const uint32_t off = (c0 >> 3) * A_CHUNK_BYTES + row * 16;
   const uint32_t s_hi = smem_u32(a_hi) + off, s_lo = smem_u32(a_lo) + off;
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     uint4 hi, lo;
-    split8(v + 8 * j, hi, lo);
+    split8<F16>(v + 8 * j, hi, lo);
     sts128(s_hi + j * A_CHUNK_BYTES, hi);
     sts128(s_lo + j * A_CHUNK_BYTES, lo);
     if (gtile) {
@@ -349,9 +355,10 @@ __device__ __forceinline__ void store_a16_save(uint8_t* a_hi, uint8_t* a_lo, uin
 // The three steps of store_a16_save as separate calls, so that a kernel can put the group's publish (fence.proxy.async =
 // MEMBAR + FENCE, then the mbarrier arrive the MMA warp is waiting for) BETWEEN the shared-memory stores and the global
 // ones: the fence then does not have to wait for the global stores' round trip.
+template <bool F16>
 __device__ __forceinline__ void split16(const float* v, uint4 hi[2], uint4 lo[2]) {
-  split8(v, hi[0], lo[0]);
-  split8(v + 8, hi[1], lo[1]);
+  split8<F16>(v, hi[0], lo[0]);
+  split8<F16>(v + 8, hi[1], lo[1]);
 }
 __device__ __forceinline__ void sts16(uint8_t* a_hi, uint8_t* a_lo, int row, int c0, const uint4 hi[2], const uint4 lo[2]) {
   const uint32_t off = (c0 >> 3) * A_CHUNK_BYTES + row * 16;
@@ -362,6 +369,17 @@ __device__ __forceinline__ void sts16(uint8_t* a_hi, uint8_t* a_lo, int row, int
     sts128(s_lo + j * A_CHUNK_BYTES, lo[j]);
   }
 }
+// The saved operand tiles (read by the backward kernels and by wgrad) hold bf16 pairs whatever the shared-memory tile
+// holds: tcgen05.mma kind::f16 faults ("illegal instruction", measured on B200) when A and B carry different 16-bit
+// formats, and the backward tensors need bf16's exponent range.  16 / 8 fp32 values -> bf16 hi / lo -> global tile.
+// lo_off: byte offset of the lo plane from the hi plane (main tile: PLANE_MAIN, aux tile: PLANE_AUX).
+__device__ __forceinline__ void stg_bf16_pairs8(uint8_t* gtile, uint32_t lo_off, int row, int chunk, const float* v) {
+  uint4 hi, lo;
+  split8<false>(v, hi, lo);
+  const uint32_t off = chunk * A_CHUNK_BYTES + row * 16;
+  __stcs(reinterpret_cast<uint4*>(gtile + off), hi);
+  __stcs(reinterpret_cast<uint4*>(gtile + lo_off + off), lo);
+}
 __device__ __forceinline__ void stg16(uint8_t* gtile, int row, int c0, const uint4 hi[2], const uint4 lo[2]) {
   const uint32_t off = (c0 >> 3) * A_CHUNK_BYTES + row * 16;
 #pragma unroll
@@ -370,9 +388,10 @@ __device__ __forceinline__ void stg16(uint8_t* gtile, int row, int c0, const uin
     __stcs(reinterpret_cast<uint4*>(gtile + (A_MAIN_COLS / 8) * A_CHUNK_BYTES + off + j * A_CHUNK_BYTES), lo[j]);
   }
 }
+template <bool F16>
 __device__ __forceinline__ void store_a8_save(uint8_t* a_hi, uint8_t* a_lo, uint8_t* gtile, int row, int c0, const float* v) {
   uint4 hi, lo;
-  split8(v, hi, lo);
+  split8<F16>(v, hi, lo);
   const uint32_t off = (c0 >> 3) * A_CHUNK_BYTES + row * 16;
   sts128(smem_u32(a_hi) + off, hi);
   sts128(smem_u32(a_lo) + off, lo);
@@ -381,9 +400,10 @@ __device__ __forceinline__ void store_a8_save(uint8_t* a_hi, uint8_t* a_lo, uint
     __stcs(reinterpret_cast<uint4*>(gtile + (A_MAIN_COLS / 8) * A_CHUNK_BYTES + off), lo);
   }
 }
+template <bool F16>
 __device__ __forceinline__ void store_a8(uint8_t* a_hi, uint8_t* a_lo, int row, int c0, const float* v) {
   uint4 hi, lo;
-  split8(v, hi, lo);
+  split8<F16>(v, hi, lo);
   const uint32_t off = (c0 >> 3) * A_CHUNK_BYTES + row * 16;
   sts128(smem_u32(a_hi) + off, hi);
   sts128(smem_u32(a_lo) + off, lo);

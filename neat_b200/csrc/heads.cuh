@@ -105,13 +105,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_fwd_kernel(const __grid_c
           if (i == 3 + nv) { a[i] = nrm[0]; a[i + 1] = nrm[1]; a[i + 2] = nrm[2]; }
         }
 #pragma unroll
-        for (int i = 0; i < A_AUX_COLS / 8; ++i) store_a8(sm.a_hi, sm.a_lo, e.row, A_MAIN_COLS + 8 * i, a + 8 * i);
+        for (int i = 0; i < A_AUX_COLS / 8; ++i) store_a8<true>(sm.a_hi, sm.a_lo, e.row, A_MAIN_COLS + 8 * i, a + 8 * i);
         epi_publish_aux(sm);
+        if (tr) {  // the aux part of u_0 for wgrad: bf16 pairs (engine.cuh), written from registers
+#pragma unroll
+          for (int i = 0; i < A_AUX_COLS / 8; ++i) stg_bf16_pairs8(rec + lay.aux, PLANE_AUX_BYTES, e.row, i, a + 8 * i);
+        }
       }
       mbar_wait(&sm.in_ready, in_phase);  // the feature planes have landed (every thread observes the TMA completion)
       in_phase ^= 1;
       epi_publish_all(sm);
-      if (tr) epi_store_main(sm, e, sm.a_hi + PLANE_MAIN_BYTES, sm.a_lo + PLANE_MAIN_BYTES, rec + lay.aux, PLANE_AUX_BYTES);
 
       for (int l = 0; l < p.HL - 1; ++l) {
         const Step st = p.prog.s[l];
@@ -129,22 +132,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_fwd_kernel(const __grid_c
 #pragma unroll
           for (int j = 0; j < 16; ++j) acc[j] = nxt[j];
           if (g + 1 < N_GROUPS) tmem_ld16(e.tm + st.d_col + epi_col(e, g + 1), nxt);
-          uint4 hi[2], lo[2];
           const bool has = c0 < st.w.npad;
           if (has) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float4 b = __ldg(bias + (c0 >> 2) + j);
-              acc[4 * j + 0] = fmaxf(acc[4 * j + 0] + b.x, 0.f);
-              acc[4 * j + 1] = fmaxf(acc[4 * j + 1] + b.y, 0.f);
-              acc[4 * j + 2] = fmaxf(acc[4 * j + 2] + b.z, 0.f);
-              acc[4 * j + 3] = fmaxf(acc[4 * j + 3] + b.w, 0.f);
+              acc[4 * j + 0] = fmaxf(fmaf(acc[4 * j + 0], st.comp, b.x), 0.f);   // comp: layout.h (RZ accumulation)
+              acc[4 * j + 1] = fmaxf(fmaf(acc[4 * j + 1], st.comp, b.y), 0.f);
+              acc[4 * j + 2] = fmaxf(fmaf(acc[4 * j + 2], st.comp, b.z), 0.f);
+              acc[4 * j + 3] = fmaxf(fmaf(acc[4 * j + 3], st.comp, b.w), 0.f);
             }
-            split16(acc, hi, lo);
-            sts16(sm.a_hi, sm.a_lo, e.row, c0, hi, lo);
+            store_a16<true>(sm.a_hi, sm.a_lo, e.row, c0, acc);
           }
           epi_publish_group(sm, g);
-          if (has && usave) stg16(usave, e.row, c0, hi, lo);  // after the publish: nothing waits for these
+          if (has && usave) {  // after the publish: nothing waits for the save record (bf16 pairs, see engine.cuh)
+            stg_bf16_pairs8(usave, PLANE_MAIN_BYTES, e.row, c0 >> 3, acc);
+            stg_bf16_pairs8(usave, PLANE_MAIN_BYTES, e.row, (c0 >> 3) + 1, acc + 8);
+          }
         }
       }
       {
@@ -159,12 +163,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_fwd_kernel(const __grid_c
             if (p.head == 0) {
 #pragma unroll
               for (int c = 0; c < 3; ++c) {
-                const float v = acc[c] + __ldg(bias + c);
+                const float v = fmaf(acc[c], st.comp, __ldg(bias + c));
                 p.out[3 * static_cast<size_t>(pt) + c] = 1.0f / (1.0f + expf(-v));
               }
             } else {
 #pragma unroll
-              for (int c = 0; c < 6; ++c) p.out[6 * static_cast<size_t>(pt) + c] = x[c % 3] + acc[c] + __ldg(bias + c);
+              for (int c = 0; c < 6; ++c) p.out[6 * static_cast<size_t>(pt) + c] = x[c % 3] + fmaf(acc[c], st.comp, __ldg(bias + c));
             }
           }
         }

@@ -32,6 +32,13 @@ struct Step {          // one GEMM of a kernel's program
   uint8_t wait_a;      // 1: wait (group by group) until the epilogue published the main columns of the A tile
   uint8_t wait_aux;    // 1: wait until the aux columns were published
   uint8_t commit_d;    // 1: signal the epilogue when this GEMM (and all before it) completed
+  // Accumulator bias compensation.  tcgen05.mma adds every K=16 block product into the fp32 accumulator with round-toward-
+  // zero (measured: making the operands 32x more precise left the SDF error at 1.6e-5; a numpy model of the MLP with RZ
+  // accumulation reproduces 1.69e-5, with round-to-nearest 1.0e-6 -- see DESIGN.md section 2.1).  n truncations shrink the
+  // sum by ~0.35 n 2^-24 relative (0.5 ulp each, ulp / |acc| = 0.72 x 2^-23 on average, partial sums smaller than the
+  // final one), so the forward epilogues read the accumulator as acc * comp, comp = 1 + 0.35 n 2^-24, folded into the
+  // bias FMA: SDF error 1.7e-5 -> 2.8e-6 in the model, for free.
+  float comp;
   // what the EPILOGUE of this step reads from the tile's read-only record (Program::pf_base + tile * pf_stride + off):
   // the weight-producer warp asks the L2 for it one step ahead, spread over the previous step's k-steps
   uint32_t pf_off[2];
@@ -40,7 +47,8 @@ struct Step {          // one GEMM of a kernel's program
 
 struct Program {
   int n;
-  int fast;  // 0: bf16x3 (hi*hi + hi*lo + lo*hi, the parity mode); 1: plain bf16 (hi*hi only; ~1e-2 accuracy)
+  int fast;  // 0: "x3" (hi*hi + hi*lo + lo*hi, the parity mode); 1: hi*hi only (~1e-2 .. 1e-3 accuracy)
+  int a_f16, b_f16;  // operand formats of the tcgen05 instruction descriptor: 1 = fp16 pairs, 0 = bf16 pairs (umma.cuh)
   const uint8_t* pf_base;   // per-tile records the epilogues read (nullptr: no prefetching)
   uint64_t pf_stride;
   Step s[MAX_STEPS];

@@ -29,7 +29,9 @@ struct SdfQueryParams {
 };
 
 // positional encoding of x into the aux columns of the A tile (zero padded to 48 columns)
-__device__ __forceinline__ void pe_to_aux(uint8_t* a_hi, uint8_t* a_lo, int row, const float x[3], int multires) {
+// gsave (training): the same 48 columns as bf16 pairs into the tile's save record (aux-tile layout)
+__device__ __forceinline__ void pe_to_aux(uint8_t* a_hi, uint8_t* a_lo, int row, const float x[3], int multires,
+                                          uint8_t* gsave = nullptr) {
   float e[A_AUX_COLS];
 #pragma unroll
   for (int i = 0; i < A_AUX_COLS; ++i) e[i] = 0.f;
@@ -48,7 +50,11 @@ __device__ __forceinline__ void pe_to_aux(uint8_t* a_hi, uint8_t* a_lo, int row,
     }
   }
 #pragma unroll
-  for (int i = 0; i < A_AUX_COLS / 8; ++i) store_a8(a_hi, a_lo, row, A_MAIN_COLS + 8 * i, e + 8 * i);
+  for (int i = 0; i < A_AUX_COLS / 8; ++i) store_a8<true>(a_hi, a_lo, row, A_MAIN_COLS + 8 * i, e + 8 * i);
+  if (gsave) {
+#pragma unroll
+    for (int i = 0; i < A_AUX_COLS / 8; ++i) stg_bf16_pairs8(gsave, (A_AUX_COLS / 8) * A_CHUNK_BYTES, row, i, e + 8 * i);
+  }
 }
 
 // the point handled by this thread: explicit, or o + z * d with the reference's rounding (mul, then add)
@@ -119,12 +125,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_query_kernel(const __grid_
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float4 b = __ldg(bias + (c0 >> 2) + j);
-              acc[4 * j + 0] = softplus100(acc[4 * j + 0] + b.x);
-              acc[4 * j + 1] = softplus100(acc[4 * j + 1] + b.y);
-              acc[4 * j + 2] = softplus100(acc[4 * j + 2] + b.z);
-              acc[4 * j + 3] = softplus100(acc[4 * j + 3] + b.w);
+              acc[4 * j + 0] = softplus100(fmaf(acc[4 * j + 0], st.comp, b.x));   // comp: layout.h (RZ accumulation)
+              acc[4 * j + 1] = softplus100(fmaf(acc[4 * j + 1], st.comp, b.y));
+              acc[4 * j + 2] = softplus100(fmaf(acc[4 * j + 2], st.comp, b.z));
+              acc[4 * j + 3] = softplus100(fmaf(acc[4 * j + 3], st.comp, b.w));
             }
-            store_a16(sm.a_hi, sm.a_lo, e.row, c0, acc);
+            store_a16<true>(sm.a_hi, sm.a_lo, e.row, c0, acc);
           }
           epi_publish_group(sm, g);
         }
@@ -136,7 +142,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_query_kernel(const __grid_
           float acc[16];
           tmem_ld16(e.tm + st.d_col, acc);
           tmem_ld_wait();
-          float s = acc[0] + __ldg(reinterpret_cast<const float*>(p.packed + st.w.bias_off));
+          float s = fmaf(acc[0], st.comp, __ldg(reinterpret_cast<const float*>(p.packed + st.w.bias_off)));
           if (p.sphere_r > 0.f) {
             const float nrm = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
             s = fminf(s, p.sphere_scale * (p.sphere_r - nrm));

@@ -27,6 +27,8 @@ struct SdfSaveLayout {
   uint32_t pe;     // TILE_AUX_BYTES   (u_0 and the aux part of u_skip)
   uint32_t u;      // [L-1] x TILE_MAIN_BYTES : u_1 .. u_{L-1}   (training only)
   uint32_t a;      // [L-1] x TILE_MAIN_BYTES : a_0 .. a_{L-2}   (training only)
+  uint32_t feat;   // TILE_MAIN_BYTES : the feature vectors as bf16 pairs for wgrad (training only; the heads read the
+                   // fp16 tile in SdfRenderParams::feat_tiles)
   uint32_t total;  // bytes per tile
 };
 __host__ __device__ inline SdfSaveLayout sdf_save_layout(int L, bool training) {
@@ -36,7 +38,8 @@ __host__ __device__ inline SdfSaveLayout sdf_save_layout(int L, bool training) {
   s.pe = s.rskip + RSKIP_BYTES;
   s.u = s.pe + TILE_AUX_BYTES;
   s.a = s.u + (training ? (L - 1) * TILE_MAIN_BYTES : 0);
-  s.total = s.a + (training ? (L - 1) * TILE_MAIN_BYTES : 0);
+  s.feat = s.a + (training ? (L - 1) * TILE_MAIN_BYTES : 0);
+  s.total = s.feat + (training ? TILE_MAIN_BYTES : 0);
   return s;
 }
 
@@ -88,11 +91,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
       // ------------------------------------------------------------ stage 0: positional encoding
       epi_planes_free(sm, e);
       if (e.j == 0) {
-        pe_to_aux(sm.a_hi, sm.a_lo, e.row, x, p.pts.multires);
+        pe_to_aux(sm.a_hi, sm.a_lo, e.row, x, p.pts.multires, tr ? rec + lay.pe : nullptr);
         epi_publish_aux(sm);
       }
       epi_publish_all(sm);
-      if (tr) epi_store_main(sm, e, sm.a_hi + PLANE_MAIN_BYTES, sm.a_lo + PLANE_MAIN_BYTES, rec + lay.pe, PLANE_AUX_BYTES);
 
       // ------------------------------------------------------------ forward pass, hidden layers
       for (int l = 0; l < L - 1; ++l) {
@@ -112,7 +114,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
 #pragma unroll
           for (int j = 0; j < 16; ++j) acc[j] = nxt[j];
           if (g + 1 < N_GROUPS) tmem_ld16(e.tm + st.d_col + epi_col(e, g + 1), nxt);
-          uint4 hi[2], lo[2];
           const bool has = c0 < st.w.npad;
           if (has) {
 #pragma unroll
@@ -123,16 +124,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 float hv;
-                softplus100_d1(acc[4 * j + k] + bb[k], hv, dd[k]);
+                softplus100_d1(fmaf(acc[4 * j + k], st.comp, bb[k]), hv, dd[k]);   // comp: layout.h (RZ accumulation)
                 acc[4 * j + k] = hv;
               }
               *f4_at(d1, c0 + 4 * j, e.row) = make_float4(dd[0], dd[1], dd[2], dd[3]);
             }
-            split16(acc, hi, lo);
-            sts16(sm.a_hi, sm.a_lo, e.row, c0, hi, lo);
+            store_a16<true>(sm.a_hi, sm.a_lo, e.row, c0, acc);
           }
           epi_publish_group(sm, g);
-          if (has && usave) stg16(usave, e.row, c0, hi, lo);  // after the publish: nothing waits for these
+          if (has && usave) {  // after the publish: nothing waits for the save record (bf16 pairs, see engine.cuh)
+            stg_bf16_pairs8(usave, PLANE_MAIN_BYTES, e.row, c0 >> 3, acc);
+            stg_bf16_pairs8(usave, PLANE_MAIN_BYTES, e.row, (c0 >> 3) + 1, acc + 8);
+          }
         }
       }
 
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
           float acc[16];
           tmem_ld16(e.tm + ss.d_col, acc);
           tmem_ld_wait();
-          s_raw = acc[0] + __ldg(reinterpret_cast<const float*>(p.packed + ss.w.bias_off));
+          s_raw = fmaf(acc[0], ss.comp, __ldg(reinterpret_cast<const float*>(p.packed + ss.w.bias_off)));
         }
         for (int g = 0; g < N_GROUPS; ++g) {
           const int c0 = epi_col(e, g);
@@ -157,9 +160,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float4 b = __ldg(bias + (c0 >> 2) + j);
-              acc[4 * j + 0] += b.x; acc[4 * j + 1] += b.y; acc[4 * j + 2] += b.z; acc[4 * j + 3] += b.w;
+              acc[4 * j + 0] = fmaf(acc[4 * j + 0], sf.comp, b.x); acc[4 * j + 1] = fmaf(acc[4 * j + 1], sf.comp, b.y);
+              acc[4 * j + 2] = fmaf(acc[4 * j + 2], sf.comp, b.z); acc[4 * j + 3] = fmaf(acc[4 * j + 3], sf.comp, b.w);
             }
-            store_a16(sm.a_hi, sm.a_lo, e.row, c0, acc);
+            store_a16<true>(sm.a_hi, sm.a_lo, e.row, c0, acc);
+            if (tr) {
+              uint8_t* fsave = rec + lay.feat;
+              stg_bf16_pairs8(fsave, PLANE_MAIN_BYTES, e.row, c0 >> 3, acc);
+              stg_bf16_pairs8(fsave, PLANE_MAIN_BYTES, e.row, (c0 >> 3) + 1, acc + 8);
+            }
           }
         }
         fence_proxy_async();
@@ -188,7 +197,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
             for (int j = 0; j < 4; ++j) f4_unpack(*f4_at(d1, c0 + 4 * j, e.row), a + 4 * j);
 #pragma unroll
             for (int j = 0; j < 16; ++j) a[j] *= __ldg(w_row + c0 + j);
-            store_a16_save(sm.a_hi, sm.a_lo, tr ? rec + lay.a + static_cast<size_t>(L - 2) * TILE_MAIN_BYTES : nullptr, e.row, c0, a);
+            store_a16<true>(sm.a_hi, sm.a_lo, e.row, c0, a);
+            if (tr) {
+              uint8_t* asave = rec + lay.a + static_cast<size_t>(L - 2) * TILE_MAIN_BYTES;
+              stg_bf16_pairs8(asave, PLANE_MAIN_BYTES, e.row, c0 >> 3, a);
+              stg_bf16_pairs8(asave, PLANE_MAIN_BYTES, e.row, (c0 >> 3) + 1, a + 8);
+            }
           }
           epi_publish_group(sm, g);
         }
@@ -221,6 +235,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
             float acc[8];
             tmem_ld8(e.tm + st.d_col + c, acc);
             tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] *= st.comp;
             if (l == p.skip) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -230,7 +246,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] *= s1[j];
-            store_a8_save(sm.a_hi, sm.a_lo, asave, e.row, c, acc);
+            store_a8<true>(sm.a_hi, sm.a_lo, e.row, c, acc);
+            if (asave) stg_bf16_pairs8(asave, PLANE_MAIN_BYTES, e.row, c >> 3, acc);
           }
           if (u & 1) epi_publish_group(sm, u >> 1);
         }
@@ -253,7 +270,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const int c = 16 * part + i;  // compile-time
-              float val = v[i];
+              float val = v[i] * st.comp;
               if (p.skip >= 0 && c < p.E) val += rskip[c * TILE_M + e.row];
               if (c < 3) {
                 n[c] += val;

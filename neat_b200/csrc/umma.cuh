@@ -3,6 +3,7 @@
 // Everything is inline PTX; there is no CUTLASS/CuTe dependency.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -115,13 +116,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
   return d;         // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
 }
 
-// Instruction descriptor, kind::f16: BF16 x BF16 -> FP32, dense.
-//   a_mn / b_mn : 0 = K-major operand, 1 = MN-major operand
-__device__ __forceinline__ uint32_t make_idesc(uint32_t M, uint32_t N, uint32_t a_mn, uint32_t b_mn) {
+// Instruction descriptor, kind::f16: {F16 | BF16} x {F16 | BF16} -> FP32, dense.  The two operand formats are separate
+// fields (A: bits 7-9, B: bits 10-12; 0 = F16, 1 = BF16) and may differ.
+//   a_mn / b_mn : 0 = K-major operand, 1 = MN-major operand;  a_f16 / b_f16 : 1 = the operand holds fp16, 0 = bf16
+__device__ __forceinline__ uint32_t make_idesc(uint32_t M, uint32_t N, uint32_t a_mn, uint32_t b_mn, uint32_t a_f16 = 0,
+                                               uint32_t b_f16 = 0) {
   uint32_t d = 0;
-  d |= 1u << 4;   // D format  : F32
-  d |= 1u << 7;   // A format  : BF16
-  d |= 1u << 10;  // B format  : BF16
+  d |= 1u << 4;                     // D format  : F32
+  d |= (a_f16 ? 0u : 1u) << 7;      // A format
+  d |= (b_f16 ? 0u : 1u) << 10;     // B format
   d |= (a_mn & 1u) << 15;
   d |= (b_mn & 1u) << 16;
   d |= ((N >> 3) & 0x3Fu) << 17;
@@ -195,9 +198,16 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// ---------------------------------------------------------------- bf16 hi/lo split (bf16x3 arithmetic)
-// x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits in two bf16 operands.
-// A*B is evaluated as Ahi*Bhi + Ahi*Blo + Alo*Bhi with fp32 accumulation in TMEM.
+// ---------------------------------------------------------------- hi/lo split operands ("x3" arithmetic)
+// x ~= hi + lo with hi = rn16(x), lo = rn16(x - hi); A*B is evaluated as Ahi*Bhi + Ahi*Blo + Alo*Bhi with fp32 accumulation
+// in TMEM.  Two 16-bit formats are used:
+//   bf16 pairs (8 + 8 mantissa bits, fp32's exponent range): the BACKWARD tensors (z_bar, p: gradients of any magnitude);
+//              ~2^-17 relative per operand
+//   fp16 pairs (11 + 11 bits): the weights and every FORWARD activation (values of O(1e-4 .. 1e2): softplus / ReLU outputs,
+//              positional encodings, normals, features); ~2^-22 relative per operand, i.e. fp32-class products.  Measured
+//              reason (round 2): with bf16 pairs the SDF carried ~3e-5 absolute error, which the Laplace density divides
+//              by beta -- at beta = 0.01 the composited end points missed the 1e-4 bound at 1024 rays, and the error of the
+//              compositing weights dominated the gradient error of the rendering head.  Conversions saturate (no inf).
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
@@ -212,19 +222,37 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float a, float b) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
 }
-// hi/lo split of a pair: hi = bf16(x), lo = bf16(x - hi)
+__device__ __forceinline__ uint32_t cvt_f16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// the two fp32 values of a packed pair
+template <bool F16>
+__device__ __forceinline__ void unpack2(uint32_t v, float& a, float& b) {
+  if (F16) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
+    a = f.x; b = f.y;
+  } else {
+    a = __uint_as_float(v << 16);
+    b = __uint_as_float(v & 0xFFFF0000u);
+  }
+}
+// hi/lo split of a pair: hi = rn16(x), lo = rn16(x - hi)
+template <bool F16>
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  hi = cvt_bf16x2(a, b);
-  const float ra = a - __uint_as_float(hi << 16);
-  const float rb = b - __uint_as_float(hi & 0xFFFF0000u);
-  lo = cvt_bf16x2(ra, rb);
+  float ha, hb;
+  if (F16) hi = cvt_f16x2(a, b); else hi = cvt_bf16x2(a, b);
+  unpack2<F16>(hi, ha, hb);
+  if (F16) lo = cvt_f16x2(a - ha, b - hb); else lo = cvt_bf16x2(a - ha, b - hb);
 }
 // splits 8 consecutive fp32 values into two 16-byte vectors (hi, lo)
+template <bool F16>
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
-  split2(v[0], v[1], hi.x, lo.x);
-  split2(v[2], v[3], hi.y, lo.y);
-  split2(v[4], v[5], hi.z, lo.z);
-  split2(v[6], v[7], hi.w, lo.w);
+  split2<F16>(v[0], v[1], hi.x, lo.x);
+  split2<F16>(v[2], v[3], hi.y, lo.y);
+  split2<F16>(v[4], v[5], hi.z, lo.z);
+  split2<F16>(v[6], v[7], hi.w, lo.w);
 }
 
 }  // namespace neat

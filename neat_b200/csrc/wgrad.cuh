@@ -26,6 +26,8 @@ struct WJob {
   float scale;
   int n_tiles;
   int split, n_split;
+  int x_f16, y_f16;  // operand formats (umma.cuh): tiles written by the forward kernels hold fp16 pairs, by the backward
+                     // kernels bf16 pairs; the instruction descriptor carries one format per operand
 };
 
 // 16-byte vector reduction into global memory (sm_90+): one L2 transaction instead of four
@@ -140,8 +142,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WJob* __rest
   } else if (warp == 5) {  // MMA warp (converged; one elected lane issues)
     // MN-major operands: core matrix = 8 points (K) x 8 columns (16 B); K-direction stride 128 B,
     // MN-direction stride = one chunk (2048 B)
-    const uint32_t idesc = make_idesc(128, job.n_cols, 1, 1);
-    const uint32_t idesc1 = make_idesc(128, 16, 1, 1);
+    const uint32_t idesc = make_idesc(128, job.n_cols, 1, 1, job.x_f16, job.y_f16);
+    const uint32_t idesc1 = make_idesc(128, 16, 1, 1, job.x_f16, 0);  // the in-kernel ones operand is bf16
     const uint32_t d = __shfl_sync(0xffffffffu, sm.tmem_base, 0), d1 = d + 256;
     const uint64_t dxh0 = make_desc_k(smem_u32(sm.x_hi), 128, A_CHUNK_BYTES), dxl0 = make_desc_k(smem_u32(sm.x_lo), 128, A_CHUNK_BYTES);
     const uint64_t dyh0 = make_desc_k(smem_u32(sm.y_hi), 128, A_CHUNK_BYTES), dyl0 = make_desc_k(smem_u32(sm.y_lo), 128, A_CHUNK_BYTES);

@@ -287,7 +287,7 @@ class Renderer:
     # ---- feature tiles <-> [M, F] (standalone ImplicitNetwork / head entry points only) ------------
     def unpack_features(self, tiles, M):
         F = self.ctx.cfg.feat
-        t = tiles.view(torch.bfloat16).view(-1, 2, 32, 128, 8).float()
+        t = tiles.view(torch.float16).view(-1, 2, 32, 128, 8).float()   # forward tiles hold fp16 hi / lo pairs
         full = (t[:, 0] + t[:, 1]).permute(0, 2, 1, 3).reshape(-1, 256)
         return full[:M, :F].contiguous()
 
@@ -296,8 +296,9 @@ class Renderer:
         nt = (M + 127) // 128
         full = torch.zeros(nt * 128, 256, device=feat.device)
         full[:M, :F] = feat
-        hi = full.to(torch.bfloat16)
-        lo = (full - hi.float()).to(torch.bfloat16)
+        full = full.clamp(-65504.0, 65504.0)
+        hi = full.to(torch.float16)
+        lo = (full - hi.float()).to(torch.float16)
         t = torch.stack([hi, lo], 0).view(2, nt, 128, 32, 8).permute(1, 0, 3, 2, 4).contiguous()
         return t.view(torch.uint8).reshape(-1)
 

@@ -65,17 +65,23 @@ def step_samples(st):
     return st.z.cpu(), z_eik
 
 
-def oracle_step(conf, sd_np, b, st, backward=True):
-    """The oracle's training forward (+ loss + autograd backward) at the sample positions of the GPU step `st`."""
-    P, leaves = G.oracle_params(conf, sd_np, track=backward)
+def oracle_step(conf, sd_np, b, st, backward=True, dtype=torch.float64):
+    """The oracle's training forward (+ loss + autograd backward) at the sample positions of the GPU step `st`.
+    dtype: float64 (default) = the reference ALGORITHM evaluated to working precision, i.e. the ground truth both the
+    fp32 reference and the kernels approximate (measured, round 2: for the gradients of this step the fp32 oracle itself is
+    5e-4 .. 1e-3 away from it -- scripts/measure_parity.py reports that distance beside the kernels'); float32 = what the
+    reference computes."""
+    P, leaves = G.oracle_params(conf, sd_np, dtype=dtype, track=backward)
     R = st.R
     sc = G.sampler_conf(conf)
     dummy = O.SamplerRandoms(torch.zeros(R, sc.N_samples_eval), torch.zeros(R, sc.N_samples),
                              torch.zeros(sc.N_samples_extra, dtype=torch.long), torch.zeros(R, dtype=torch.long))
-    rnd = O.TrainRandoms(dummy, st.eik_uniform.cpu())
-    oo = O.neat_forward(P, sc, T(b["intrinsics"][0]), T(b["pose"][0]), T(b["uv"][0]), T(b["uv_proj"][0]),
-                        gt_vertices=T(b["wf_vertices"]), training=True, rnd=rnd, samples=step_samples(st))
-    ol = O.neat_loss(oo, T(b["rgb"][0]), T(b["lines2d"][0]), oo["K"])
+    rnd = O.TrainRandoms(dummy, st.eik_uniform.cpu().to(dtype))
+    D = lambda a: T(a).to(dtype)
+    z, z_eik = step_samples(st)
+    oo = O.neat_forward(P, sc, D(b["intrinsics"][0]), D(b["pose"][0]), D(b["uv"][0]), D(b["uv_proj"][0]),
+                        gt_vertices=D(b["wf_vertices"]), training=True, rnd=rnd, samples=(z.to(dtype), z_eik.to(dtype)))
+    ol = O.neat_loss(oo, D(b["rgb"][0]), D(b["lines2d"][0]), oo["K"])
     if backward:
         ol["loss"].backward()
     return oo, ol, leaves
