@@ -158,7 +158,10 @@ def reference_config(r, kind, beta):
 
 # ------------------------------------------------------------------------------------------------ our arm
 def train_config(rays, beta, steps, warmup, rank, world, dev, lib, e2e=True, timers=True, clocks=None):
-    """Times `steps` training steps at `rays` rays per GPU.  Returns a dict of raw measurements (max over ranks)."""
+    """Times `steps` training steps at `rays` rays per GPU.  Returns a dict of raw measurements (max over ranks).
+    value / e2e: neat_b200.trainer.FusedTrainStep (the step as two CUDA-graph replays + the junction hand-over);
+    kernel timers and `plugin_ms`: the same step through the plugin classes (model -> loss -> backward -> Adam, eager
+    launches), where CUDA events can bracket the individual kernels."""
     import torch
     import torch.distributed as dist
     from neat_b200 import synth
@@ -169,65 +172,98 @@ def train_config(rays, beta, steps, warmup, rank, world, dev, lib, e2e=True, tim
             dist.barrier()
         torch.cuda.synchronize()
 
-    ts = TR.TrainStep(synth.dtu_conf(), device=dev, seed=42, beta=beta)
+    warmup = max(warmup, 4)   # 2 eager steps, the capture, one replay
     hb = TR.host_batch(rays, seed=1 + rank)
     inp, gt = TR.to_device(hb, dev)
-    rn = ts.model._get_renderer()
+    ts = TR.FusedTrainStep(synth.dtu_conf(), device=dev, seed=42, beta=beta)
     for _ in range(warmup):
         ts.step(inp, gt)
     barrier()
     if clocks is not None:
         clocks.start()
-    rn.timers = {} if timers else None
-    l0 = lib.neat_launch_count()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     k_acc = torch.zeros(1, dtype=torch.int32, device=dev)  # the sampler's k is data dependent and drifts as beta trains
+    wait_ms = 0.0
     for _ in range(steps):
         ts.step(inp, gt)
-        k_acc += ts.model.last_step.n_iters
+        k_acc += ts.st.n_iters
+        wait_ms += ts.last_host_ms["wait_for_gpu"]
     e1.record()
     barrier()
-    ms_total = e0.elapsed_time(e1)
-    launches = lib.neat_launch_count() - l0
-    tm = rn.timer_ms() if timers else {}
-    rn.timers = None
-    r = {"rays": rays, "beta": beta, "steps": steps, "warmup": warmup, "ms_total": ms_total, "launches": int(launches),
-         "timers": tm, "k_last": int(ts.model.last_step.n_iters.item()), "k_mean": float(k_acc.item()) / steps,
-         "host_junction_block": getattr(ts.model, "last_host_ms", None), "h2d": TR.h2d_bytes(hb)}
+    r = {"rays": rays, "beta": beta, "steps": steps, "warmup": warmup, "ms_total": e0.elapsed_time(e1),
+         "launches": int(ts.launches_per_step * steps), "launches_per_step": int(ts.launches_per_step),
+         "k_last": int(ts.st.n_iters.item()), "k_mean": float(k_acc.item()) / steps,
+         "host_junction_block": dict(ts.last_host_ms, mean_wait_for_gpu=wait_ms / steps), "h2d": TR.h2d_bytes(hb)}
     if e2e:
-        # end to end from host buffers (same initial state and trajectory as the loop above)
+        # end to end from HOST buffers (same initial state and trajectory as the loop above): the step copies the pinned
+        # host batch to the device and the loss is read back, every step
         del ts
-        ts = TR.TrainStep(synth.dtu_conf(), device=dev, seed=42, beta=beta)
+        _release()
+        ts = TR.FusedTrainStep(synth.dtu_conf(), device=dev, seed=42, beta=beta)
         for _ in range(warmup):
-            ts.step(inp, gt)
+            ts.step(hb, hb)
         barrier()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2.record()
         loss_host = 0.0
         for _ in range(steps):
-            i2, g2 = TR.to_device(hb, dev)
-            loss_host = float(ts.step(i2, g2).item())
+            loss_host = float(ts.step(hb, hb)["loss"].item())
         e3.record()
         barrier()
         r["ms_e2e"] = e2.elapsed_time(e3)
         r["last_loss"] = loss_host
     if clocks is not None:
         r["clocks"] = clocks.stop()
-    t = torch.tensor([r["ms_total"], r.get("ms_e2e", 0.0)], device=dev, dtype=torch.float64)
+    del ts
+    _release()
+    tm = {}
+    if timers:
+        # per-kernel CUDA-event timers: the plugin path, eager launches
+        ps = TR.TrainStep(synth.dtu_conf(), device=dev, seed=42, beta=beta)
+        rn = ps.model._get_renderer()
+        for _ in range(3):
+            ps.step(inp, gt)
+        barrier()
+        n_t = min(steps, 20)
+        rn.timers = {}
+        l0 = lib.neat_launch_count()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(n_t):
+            ps.step(inp, gt)
+        p1.record()
+        barrier()
+        tm = {k: (v[0] / n_t * steps, v[1] / n_t * steps) for k, v in rn.timer_ms().items()}  # scaled to `steps`
+        rn.timers = None
+        r["plugin_ms_per_step"] = p0.elapsed_time(p1) / n_t
+        r["plugin_launches_per_step"] = (lib.neat_launch_count() - l0) / n_t
+        del ps, rn
+        _release()
+    r["timers"] = tm
+    t = torch.tensor([r["ms_total"], r.get("ms_e2e", 0.0), r.get("plugin_ms_per_step", 0.0)], device=dev, dtype=torch.float64)
     if world > 1:
         mine = torch.tensor([r["ms_total"] / steps, float(r["k_last"]), sum(v[1] for v in tm.values()) / steps,
-                             r.get("last_loss", 0.0)], device=dev, dtype=torch.float64)
+                             r.get("last_loss", 0.0), r["host_junction_block"]["mean_wait_for_gpu"]], device=dev,
+                            dtype=torch.float64)
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
         r["per_rank"] = [{"ms_per_step": round(float(a[0]), 3), "sampler_k": int(a[1]), "mlp_kernel_ms": round(float(a[2]), 3),
-                          "last_loss": round(float(a[3]), 5)} for a in allr]
+                          "last_loss": round(float(a[3]), 5), "host_wait_for_handover_ms": round(float(a[4]), 3)}
+                         for a in allr]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    r["ms_total"], r["ms_e2e"] = float(t[0]), float(t[1])
-    del ts
-    torch.cuda.empty_cache()
+    r["ms_total"], r["ms_e2e"], r["plugin_ms_per_step"] = float(t[0]), float(t[1]), float(t[2])
     return r
+
+
+def _release():
+    """Drop the previous configuration's workspaces (GBs of save records; the renderer / sampler / graph objects form
+    reference cycles, so collect before asking the allocator to return the memory)."""
+    import gc
+    import torch
+    gc.collect()
+    torch.cuda.empty_cache()
 
 
 def kernel_fractions(r, pk):
@@ -315,7 +351,7 @@ def eval_config(rays, beta, steps, warmup, rank, world, dev, lib):
          "gpu_launches": int(launches),
          "full_image_1600x1200_seconds_at_this_rate": round(1600 * 1200 / (world * rays * steps / (ms * 1e-3)), 3)}
     del model
-    torch.cuda.empty_cache()
+    _release()
     return r
 
 
@@ -343,7 +379,7 @@ def dp_check(rank, world, dev):
     losses = [torch.zeros(1, device=dev) for _ in range(world)]
     dist.all_gather(losses, lo["loss"].detach().reshape(1).float())
     del ts
-    torch.cuda.empty_cache()
+    _release()
     return {"allreduce_vs_mean_of_rank_gradients_rel_err": float(t[0]), "ok": bool(float(t[0]) < 1e-5),
             "rank_losses": [round(float(x), 5) for x in losses], "rays_per_rank": 256}
 
@@ -409,7 +445,8 @@ def main():
     config = {"workload": "DTU-shaped synthetic batch: %d rays/GPU x 98 samples, 8x256 SDF + 4x256 rendering/attraction "
                           "MLPs, ErrorBoundSampler (<=5 x 128 SDF queries/ray), train step = fwd+loss+bwd+Adam "
                           "(BASELINE configs[1])" % args.rays,
-              "optimizer": "Adam(lr=5e-4), all parameter tensors in one launch (neat_b200.optim.Adam)",
+              "optimizer": "Adam(lr=5e-4), all parameter tensors in one launch, step count / lr on the device",
+              "execution": "neat_b200.trainer.FusedTrainStep: two CUDA-graph replays per step + the host junction hand-over",
               "rays_per_gpu": args.rays, "samples_per_ray": S, "beta": args.beta, "parallelism": "dp%d" % world,
               "rng": "training draws (stratified jitter, inverse-CDF u, extra columns, eikonal points) made on the device",
               "precision_mode": "bf16x3 (hi/lo split operands, fp32 accumulate) on tcgen05",
@@ -417,6 +454,7 @@ def main():
     check = dp_check(rank, world, dev) if world > 1 else None
     clocks = ClockSampler(local) if rank == 0 else None
     r = train_config(args.rays, args.beta, args.steps, warm, rank, world, dev, lib, clocks=clocks)
+    warm = r["warmup"]
 
     extras = []
     if not args.no_extra_configs:
@@ -430,9 +468,10 @@ def main():
             if rays == args.rays and beta == args.beta and steps == args.steps:
                 continue
             x = train_config(rays, beta, steps, 3, rank, world, dev, lib, e2e=False)
-            extras.append({"name": name, "rays_per_gpu": rays, "beta": beta, "steps": steps, "warmup": 3,
+            extras.append({"name": name, "rays_per_gpu": rays, "beta": beta, "steps": steps, "warmup": x["warmup"],
                            "value": world * rays * steps / (x["ms_total"] * 1e-3), "unit": "rays/s",
-                           "ms_per_step": x["ms_total"] / steps, "sampler_k_last": x["k_last"],
+                           "ms_per_step": x["ms_total"] / steps, "plugin_path_ms_per_step": round(x["plugin_ms_per_step"], 4),
+                           "sampler_k_last": x["k_last"],
                            "sampler_k_mean": round(x["k_mean"], 3), "gpu_launches_per_step": x["launches"] / steps,
                            "kernel_ms_per_step": {k: round(v[1] / steps, 4) for k, v in x["timers"].items()},
                            "kernels": kernel_fractions(x, pk0)})
@@ -476,6 +515,11 @@ def main():
                              "kernels": kf},
                 "kernel_ms_per_step": {k: round(v[1] / steps, 4) for k, v in timers.items()},
                 "step_minus_big_kernels_ms": round(ms_total / steps - big, 4),
+                "plugin_path": {"ms_per_step": round(r["plugin_ms_per_step"], 4), "value": world * args.rays / (r["plugin_ms_per_step"] * 1e-3),
+                                "gpu_launches_per_step": r["plugin_launches_per_step"],
+                                "what": "the same step through the drop-in plugin classes (VolSDFNetwork.forward -> VolSDFLoss -> "
+                                        "backward -> neat_b200.optim.Adam, eager launches): where the per-kernel CUDA-event "
+                                        "timers of `kernel_ms_per_step` / `roofline` are taken"},
                 "host_junction_block": r["host_junction_block"], "per_rank": r.get("per_rank"), "dp_check": check,
                 "configs": extras}
         if world == 1 and not args.no_eager_baseline:

@@ -154,15 +154,6 @@ class ErrorBoundSampler:
         self._ws = None
         self._ws_R = -1
 
-    def _perm_mask(self):
-        """[max_iters, n_eval * max_iters]: 0 where column < n_eval * (row + 1), +inf elsewhere."""
-        if getattr(self, "_mask", None) is None:
-            c = self.cfg
-            col = torch.arange(c.n_eval * c.max_iters, device=self.ctx.device)[None, :]
-            lim = (torch.arange(1, c.max_iters + 1, device=self.ctx.device) * c.n_eval)[:, None]
-            self._mask = torch.where(col < lim, 0.0, float("inf")).float()
-        return self._mask
-
     def workspace(self, R):
         if self._ws_R < R:  # persistent: re-allocated only when the ray count grows
             n = int(self.ctx.lib.neat_sampler_workspace_bytes(R))
@@ -172,9 +163,11 @@ class ErrorBoundSampler:
 
     rng = "reference"  # "reference": replay the reference's CPU-generator stream; "device": draw on the GPU (no sync)
 
-    def get_z_vals(self, rays_o, rays_d, beta_param, training=False, randoms=None):
+    def get_z_vals(self, rays_o, rays_d, beta_param, training=False, randoms=None, device_tables=False):
         """rays_o [3] or [R,3], rays_d [R,3], beta_param: 0-dim/1-elem device tensor (density.beta).
         randoms (training): dict(t_rand, u_final, extra_idx, eik_idx) or None to draw them like the reference.
+        device_tables: `randoms` comes from Renderer.draws() (neat_train_draws): everything is already on the device,
+        including the extra-column table for EVERY candidate iteration count -- no device->host read of k.
         Returns z_vals [R, n_out], z_eik [R,1], n_iters (device int32 tensor)."""
         ctx, c, lib = self.ctx, self.cfg, self.ctx.lib
         R = rays_d.shape[0]
@@ -183,17 +176,18 @@ class ErrorBoundSampler:
         if o_stride == 0:
             rays_o = rays_o.reshape(-1)[:3].contiguous()
         ws = self.workspace(R)
-        n_it = torch.zeros(1, dtype=torch.int32, device=dev)
+        rn = getattr(self, "renderer", None)
+        n_it = rn.pool.get("sampler.n_it", 1, torch.int32) if rn is not None else torch.zeros(1, dtype=torch.int32, device=dev)
         z_vals = torch.empty(R, self.n_out, device=dev)
         z_eik = torch.empty(R, device=dev)
         P = ctypes.c_void_p
         t_rand = u_final = eik = None
-        device_rng = training and randoms is None and self.rng == "device"
         if training:
-            if device_rng:
-                t_rand = torch.rand(R, c.n_eval, device=dev)
-                u_final = torch.rand(R, c.n_final, device=dev)
+            if device_tables:
+                t_rand, u_final = randoms["t_rand"], randoms["u_final"]
             elif randoms is None:
+                if self.rng == "device":
+                    raise _lib.NeatError("rng='device' draws come from Renderer.draws(); pass them as `randoms`")
                 t_rand = torch.rand(R, c.n_eval).to(dev)       # ray_sampler.py:87
                 torch.randint(0, c.n_eval, (R,))               # :91 (drawn and unused by the reference)
                 u_final = torch.rand(R, c.n_final).to(dev)     # :234
@@ -201,20 +195,13 @@ class ErrorBoundSampler:
                 t_rand = randoms["t_rand"].to(dev, torch.float32).contiguous()
                 u_final = randoms["u_final"].to(dev, torch.float32).contiguous()
         import contextlib
-        rn = getattr(self, "renderer", None)
         with (rn.timed("sampler") if rn is not None else contextlib.nullcontext()):
             _lib.check(lib.neat_sampler_run(
                 ctx._h, ctypes.byref(c), ctx._chk(rays_o), o_stride, ctx._chk(rays_d, (R, 3)), R,
                 P(beta_param.data_ptr()), P(t_rand.data_ptr()) if training else None,
                 P(u_final.data_ptr()) if training else None, P(ws.data_ptr()), P(n_it.data_ptr()), ctx._stream()))
-        if device_rng:
-            # same distribution as the reference's randperm(128 k)[:n_extra] for whichever k the sampler stops at;
-            # all rows are drawn up front so that no device->host read of k is needed
-            # (the first n_extra entries of a uniform random permutation of [0, L) = the positions of the n_extra
-            # smallest of L i.i.d. uniform keys: one rand + one top-k for all candidate L instead of 5 randperms)
-            keys = torch.rand(c.max_iters, c.n_eval * c.max_iters, device=dev) + self._perm_mask()
-            table = keys.topk(max(c.n_extra, 1), dim=1, largest=False, sorted=False).indices.contiguous()
-            eik = torch.randint(0, self.n_out, (R,), device=dev)
+        if training and device_tables:
+            table, eik = randoms["extra_table"], randoms["eik_idx"]
         elif training:
             k = int(n_it.item())
             table = torch.zeros(c.max_iters, max(c.n_extra, 1), dtype=torch.int64)

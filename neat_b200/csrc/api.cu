@@ -95,9 +95,10 @@ struct neat_ctx {
   WJob* jobs_dev = nullptr;
   std::vector<WJob> jobs_last;  // what jobs_dev holds
   int jobs_cap = 0;
-  WnTable* wn_dev = nullptr;
-  WnTable wn_host{};
-  bool wn_valid = false;
+  WnTable* wn_dev[2] = {nullptr, nullptr};
+  WnTable wn_host[2]{};
+  bool wn_valid[2] = {false, false};
+  int wn_rows = 0, wn_slot = 0;
 };
 
 // persistent grid of a tile-MLP launch: one CTA per SM (or the debug cap), never more CTAs than tiles
@@ -271,7 +272,8 @@ void neat_destroy(neat_ctx* c) {
   cudaFree(c->g_fdst);
   cudaFree(c->ones_tile);
   cudaFree(c->jobs_dev);
-  cudaFree(c->wn_dev);
+  cudaFree(c->wn_dev[0]);
+  cudaFree(c->wn_dev[1]);
   delete c;
 }
 
@@ -314,12 +316,24 @@ int upload_wn_table(neat_ctx* c, const neat_wn_layer* layers, int n, cudaStream_
       ++i;
     }
   t.row_start[n] = rows;
-  if (!c->wn_dev) CK(cudaMalloc(&c->wn_dev, sizeof(WnTable)));
-  if (!c->wn_valid || std::memcmp(&t, &c->wn_host, sizeof(WnTable)) != 0) {
-    c->wn_host = t;
-    c->wn_valid = true;
-    CK(cudaMemcpyAsync(c->wn_dev, &c->wn_host, sizeof(WnTable), cudaMemcpyHostToDevice, st));
+  // two cached device tables: [0] the forward's (no gradient pointers), [1] the backward's -- each is uploaded once, the
+  // first time it is seen (alternating one table between the two re-uploaded it twice per step, and an upload from a host
+  // struct cannot be captured into a CUDA graph)
+  const int slot = layers[0].gv != nullptr ? 1 : 0;
+  if (!c->wn_dev[slot]) CK(cudaMalloc(&c->wn_dev[slot], sizeof(WnTable)));
+  if (!c->wn_valid[slot] || std::memcmp(&t, &c->wn_host[slot], sizeof(WnTable)) != 0) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    if (cs != cudaStreamCaptureStatusNone)
+      return fail(NEAT_EINVAL, "weight_norm: a new parameter table cannot be uploaded during stream capture (run one eager step first)");
+    CK(cudaStreamSynchronize(st));  // a launch still reading the previous table must have finished
+    c->wn_host[slot] = t;
+    c->wn_valid[slot] = true;
+    CK(cudaMemcpyAsync(c->wn_dev[slot], &c->wn_host[slot], sizeof(WnTable), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
   }
+  c->wn_rows = rows;
+  c->wn_slot = slot;
   return NEAT_OK;
 }
 }  // namespace
@@ -328,8 +342,8 @@ int neat_weight_norm_forward(neat_ctx* c, const neat_wn_layer* layers, int n_lay
   if (!c || !flat) return fail(NEAT_EINVAL, "null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (int e = upload_wn_table(c, layers, n_layers, st)) return e;
-  const int rows = c->wn_host.row_start[c->wn_host.n];
-  weight_norm_fwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(c->wn_dev, flat);
+  const int rows = c->wn_rows;
+  weight_norm_fwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(c->wn_dev[c->wn_slot], flat);
   ++g_launches;
   CK(cudaGetLastError());
   return NEAT_OK;
@@ -342,8 +356,8 @@ int neat_weight_norm_backward(neat_ctx* c, const neat_wn_layer* layers, int n_la
   if (int e = upload_wn_table(c, layers, n_layers, st)) return e;
   for (int i = 0; i < n_layers; ++i)
     if (!layers[i].gv || !layers[i].gb || (layers[i].g && !layers[i].gg)) return fail(NEAT_EINVAL, "weight_norm: null gradient pointer");
-  const int rows = c->wn_host.row_start[c->wn_host.n];
-  weight_norm_bwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(c->wn_dev, flat_grad, accumulate);
+  const int rows = c->wn_rows;
+  weight_norm_bwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(c->wn_dev[c->wn_slot], flat_grad, accumulate);
   ++g_launches;
   CK(cudaGetLastError());
   return NEAT_OK;
@@ -1334,9 +1348,14 @@ int neat_weight_gradients(neat_ctx* c, const neat_grad_group* groups, int n_grou
   // upload it when it changed, not every step (a > 64 KB copy from pageable memory blocks the host on the stream)
   if (c->jobs_last.size() != jobs.size() ||
       std::memcmp(c->jobs_last.data(), jobs.data(), sizeof(WJob) * jobs.size()) != 0) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    if (cs != cudaStreamCaptureStatusNone)
+      return fail(NEAT_EINVAL, "weight_gradients: a new job table cannot be uploaded during stream capture (run one eager step first)");
     CK(cudaStreamSynchronize(st));  // a launch still reading the previous table must have finished
-    CK(cudaMemcpyAsync(c->jobs_dev, jobs.data(), sizeof(WJob) * jobs.size(), cudaMemcpyHostToDevice, st));
-    c->jobs_last = jobs;
+    c->jobs_last = jobs;  // (the copy below reads the context's own vector: it outlives the call)
+    CK(cudaMemcpyAsync(c->jobs_dev, c->jobs_last.data(), sizeof(WJob) * jobs.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
   }
   wgrad_kernel<<<static_cast<int>(jobs.size()), WG_THREADS, sizeof(WgradSmem) + 1024, st>>>(c->jobs_dev);
   ++g_launches;

@@ -14,6 +14,7 @@ import torch
 from torch import nn
 
 from . import _lib, junction
+from . import ffn as ffn_kernels
 from .autograd import NeatStepFunction, StepState
 from .context import Context
 from .render import Renderer
@@ -302,6 +303,10 @@ class VolSDFNetwork(nn.Module):
             self._packed_version = v
         return rn
 
+    def seed_draws(self, seed):
+        """rng='device': restart the device-side sequence of training draws (same seed => same samples)."""
+        self._get_renderer().seed_draws(seed)
+
     # ------------------------------------------------------------------ reference helpers kept for callers
     def project2D(self, K, R, T, points3d):
         """VolSDFNetwork.project2D (neat_wfr_rend_a.py:317-331) for the evaluation callers, on the projection kernel
@@ -369,11 +374,11 @@ class VolSDFNetwork(nn.Module):
         st.uv, st.pose, st.K, st.uv_proj = uv, pose, K4, uv_proj
         rn.sampler.rng = self.rng
         st.sampler_randoms = self.replay.get("sampler") if self.replay else None
-        st.eik_uniform = self.replay["eik_uniform"] if self.replay else None
+        st.eik_uniform = self.replay.get("eik_uniform") if self.replay else None
         st.samples_override = self.replay.get("samples") if self.replay else None
         # global junctions (independent of the render step): enqueue first so that their host copy rides in the step's
         # single device->host transfer
-        glob = self.ffn(self.latents)
+        glob = ffn_kernels.apply_module(self.ffn, self.latents)   # own fp32 GEMM kernels (ffn.py), no cuBLAS
         st.junction_inputs = (glob.detach(), pose, K4)
         st.dbscan_enabled = self.dbscan_enabled
         st.param_layers = self._wn_layers()

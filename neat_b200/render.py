@@ -67,6 +67,29 @@ class Renderer:
         self._pinned = {}
         self.timers = None  # bench.py: dict name -> [(start, end) CUDA events] on the launching stream
         self.generation = 0  # bumped by every forward that reuses the named workspaces (autograd.py checks it in backward)
+        # device-side random draws of the training forward (csrc/train_aux.cuh): Philox keyed by (seed, a draw counter that
+        # lives on the device and is bumped by the kernel: replayable inside a CUDA graph)
+        self.draw_seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+        self.draw_counter = torch.zeros(2, dtype=torch.int64, device=ctx.device)
+
+    def seed_draws(self, seed):
+        """Restart the device-side draw sequence (same seed => the same samples, eikonal points, extra columns)."""
+        self.draw_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.draw_counter.zero_()
+
+    def draws(self, R):
+        """All random draws of one training forward in one launch (neat_train_draws): dict of device tensors."""
+        ctx, c, pool = self.ctx, self.sampler.cfg, self.pool
+        d = dict(t_rand=pool.get("draw.t_rand", R * c.n_eval).view(R, c.n_eval),
+                 u_final=pool.get("draw.u_final", R * c.n_final).view(R, c.n_final),
+                 extra_table=pool.get("draw.extra", c.max_iters * max(c.n_extra, 1), torch.int64).view(c.max_iters, -1),
+                 eik_idx=pool.get("draw.eik_idx", R, torch.int64),
+                 eik_uniform=pool.get("draw.eik_uniform", R * 3).view(R, 3))
+        _lib.check(ctx.lib.neat_train_draws(ctypes.byref(c), R, ctypes.c_float(self.scene_bounding_sphere),
+                                            ctypes.c_ulonglong(self.draw_seed), _ptr(self.draw_counter), _ptr(d["t_rand"]),
+                                            _ptr(d["u_final"]), _ptr(d["extra_table"]), _ptr(d["eik_idx"]),
+                                            _ptr(d["eik_uniform"]), ctx._stream()))
+        return d
 
     def timed(self, name):
         return _Timed(self, name)
@@ -242,9 +265,11 @@ class Renderer:
             self._pinned[key] = h = torch.empty(max(int(numel), 1), dtype=dtype, pin_memory=True)
         return h
 
-    def to_host_async(self, tensors):
+    def to_host_async(self, tensors, counter=None):
         """Enqueue copies of several small device tensors into pinned host buffers; returns (event, numpy views).
-        The views are valid after event.synchronize() and until the next call."""
+        The views are valid after event.synchronize() and until the next call.  counter: a device int64 tensor copied
+        LAST into its own pinned slot (self.handover_flag): a host that cannot wait on an event (the copies were captured
+        into a CUDA graph) polls that slot for the value it expects instead."""
         outs = []
         for i, t in enumerate(tensors):
             key = ("host%d" % i, t.dtype)
@@ -254,6 +279,10 @@ class Renderer:
             hv = h[:t.numel()].view(t.shape)
             hv.copy_(t, non_blocking=True)
             outs.append(hv)
+        if counter is not None:
+            flag = self.pinned("handover.flag", counter.numel(), counter.dtype)
+            flag[:counter.numel()].copy_(counter, non_blocking=True)
+            self.handover_flag = flag
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.ctx.device))
         return ev, [o.numpy() for o in outs]

@@ -15,7 +15,7 @@ sd_np = synth.make_state_dict(conf, seed=5, perturb=0.15, beta=beta)
 model = PU.make_model(conf, sd_np)
 b = synth.make_batch(R, seed=4)
 inp, gt = PU.device_inputs(b)
-torch.manual_seed(7)
+model.seed_draws(7)
 out = model(inp)
 st = model.last_step
 rgb_gt = gt["rgb"].reshape(-1, 3)

@@ -36,7 +36,7 @@ def main():
 
     def run(s):
         inp, gt = shard_batch(s)
-        torch.manual_seed(100 + s)                      # the device-side draws of shard s, whoever computes it
+        ts.model.seed_draws(100 + s)                    # the device-side draws of shard s, whoever computes it
         lo = ts.loss_fn(ts.model(inp), gt)
         lo["loss"].backward()
         return float(lo["loss"])

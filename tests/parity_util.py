@@ -47,7 +47,7 @@ def gpu_step(model, b, seed=7, keep_bars=False):
     inp, gt = device_inputs(b)
     for p in model.parameters():
         p.grad = None
-    torch.manual_seed(seed)
+    model.seed_draws(seed)
     out = model(inp)
     if keep_bars:
         for k in ("rgb_values", "lines3d", "grad_theta"):

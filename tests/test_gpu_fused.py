@@ -1,0 +1,92 @@
+"""FusedTrainStep (the step as two CUDA-graph replays + one host hand-over, neat_b200/trainer.py) against the plugin path
+(VolSDFNetwork.forward -> VolSDFLoss -> backward -> neat_b200.optim.Adam, i.e. code/training/volsdf_train.py:366-374):
+same kernels, same draws, same update -- parameters after several steps must agree to summation-order noise."""
+import numpy as np
+import pytest
+import torch
+
+from neat_b200 import synth
+from neat_b200 import trainer as TR
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(kind, steps, R=256, conf=None):
+    conf = conf or synth.dtu_conf()
+    dev = torch.device("cuda:0")
+    if kind == "plugin":
+        ts = TR.TrainStep(conf, device=dev, seed=11, beta=0.1)
+    else:
+        ts = TR.FusedTrainStep(conf, device=dev, seed=11, beta=0.1, graphs=(kind == "graphs"))
+    ts.model.seed_draws(123)
+    hb = TR.host_batch(R, seed=3)
+    inp, gt = TR.to_device(hb, dev)
+    losses = []
+    for _ in range(steps):
+        lo = ts.step(inp, gt)
+        losses.append(float((lo["loss"] if isinstance(lo, dict) else lo).reshape(-1)[0]))
+    torch.cuda.synchronize()
+    return ts, losses, {n: p.detach().clone() for n, p in ts.model.named_parameters()}
+
+
+def _max_rel(a, b):
+    return max(float((a[n] - b[n]).abs().max() / b[n].abs().max().clamp_min(1e-12)) for n in a)
+
+
+def _rel_l2(a, b):
+    return max(float((a[n] - b[n]).norm() / b[n].norm().clamp_min(1e-12)) for n in a)
+
+
+def _max_abs(a, b):
+    return max(float((a[n] - b[n]).abs().max()) for n in a)
+
+
+def test_fused_eager_step_equals_plugin_step():
+    """One optimizer step: identical loss and parameters (the fused sequence without graphs vs autograd through the plugin)."""
+    _, l_p, p_p = _run("plugin", 1)
+    _, l_f, p_f = _run("eager", 1)
+    assert abs(l_p[0] - l_f[0]) < 1e-6 * max(1.0, abs(l_p[0]))
+    assert _max_rel(p_f, p_p) < 1e-5
+
+
+def test_graph_replay_equals_plugin_over_several_steps():
+    """6 steps (2 eager warm-up steps, capture, 4 replays): the loss trajectory and the parameters follow the plugin path; the
+    device-side Adam step count, the in-graph draw counter and the hand-over flag all advance per replay."""
+    ts_p, l_p, p_p = _run("plugin", 6)
+    ts_g, l_g, p_g = _run("graphs", 6)
+    assert ts_g.gA is not None and ts_g.launches_per_step > 20
+    for a, b in zip(l_p, l_g):
+        assert abs(a - b) < 1e-5 * max(1.0, abs(a)), (l_p, l_g)      # measured: identical to 6 digits
+    # Parameters: Adam normalises every entry's update to ~lr whatever the gradient's size, so an entry whose gradient is
+    # at the noise level of the fire-and-forget reductions (order of the REDs differs from run to run) moves by +-lr per
+    # step in either run -- two runs of the PLUGIN path differ by 9e-5 in single entries after 6 steps, plugin vs fused by
+    # 5e-4 = one lr.  Hence: per-tensor L2 agreement, and no entry further apart than two learning rates.
+    assert _rel_l2(p_g, p_p) < 2e-3
+    assert _max_abs(p_g, p_p) <= 2 * 5.0e-4 * 1.01
+    assert float(ts_g.adam_state[0]) == 6.0
+    assert int(ts_g.rn.draw_counter[0]) == 6
+    # optimizer state is torch.optim.Adam's
+    ts_g.sync_optimizer_state()
+    sd = ts_g.opt.state_dict()
+    assert int(sd["state"][0]["step"]) == 6
+
+
+def test_graph_step_handles_changing_junction_count_and_lr():
+    """The matched-junction count changes from step to step (device-side n) and the learning rate follows a scheduler
+    (device-side hyper-parameters): the replayed graphs see both."""
+    ts = TR.FusedTrainStep(synth.dtu_conf(), device="cuda:0", seed=5, beta=0.1)
+    sched = torch.optim.lr_scheduler.ExponentialLR(ts.opt, 0.5)
+    dev = torch.device("cuda:0")
+    matched = set()
+    before = None
+    for i in range(6):
+        inp, gt = TR.to_device(TR.host_batch(256, seed=10 + i), dev)
+        lo = ts.step(inp, gt)
+        sched.step()
+        matched.add(ts.last_host_ms["matched"])
+        assert np.isfinite(float(lo["loss"]))
+        if i == 4:
+            before = ts.model.implicit_network.lin3.bias.detach().clone()
+    torch.cuda.synchronize()
+    assert float(ts.hyper_dev[0]) == pytest.approx(5.0e-4 * 0.5 ** 5, rel=1e-6)
+    assert float((ts.model.implicit_network.lin3.bias - before).abs().max()) > 0

@@ -376,11 +376,11 @@ def test_parameter_gradients_accumulate_and_overwrite():
     params = dict(model.named_parameters())
     for p in model.parameters():
         p.grad = None
-    torch.manual_seed(0)
+    model.seed_draws(0)
     loss_fn(model(inp), gt)["loss"].backward()
     g1 = {k: params[k].grad.clone() for k in names}
     assert all(float(v.abs().sum()) > 0 for v in g1.values())
-    torch.manual_seed(0)  # same device-RNG draws -> same gradient, added on top
+    model.seed_draws(0)  # same device-RNG draws -> same gradient, added on top
     loss_fn(model(inp), gt)["loss"].backward()
     for k in names:
         assert G.rel_err(params[k].grad.cpu(), (2 * g1[k]).cpu()) < 1e-5, k
@@ -390,7 +390,7 @@ def test_parameter_gradients_accumulate_and_overwrite():
     for p in model.parameters():
         if p.requires_grad:
             p.grad = None
-    torch.manual_seed(0)
+    model.seed_draws(0)
     loss_fn(model(inp), gt)["loss"].backward()
     assert params[names[0]].grad is None
     assert G.rel_err(params[names[1]].grad.cpu(), g1[names[1]].cpu()) < 1e-5
@@ -549,7 +549,7 @@ def test_ragged_ray_counts_forward_backward_vs_oracle(conf_name, R):
     b = synth.make_batch(R, seed=4, img_res=res, focal=560.0 if conf_name == "toy" else 2900.0)
     inp = {"intrinsics": T(b["intrinsics"]).cuda(), "uv": T(b["uv"]).cuda(), "pose": T(b["pose"]).cuda(),
            "uv_proj": T(b["uv_proj"]).cuda(), "wireframe": [WF(b["wf_vertices"])]}
-    torch.manual_seed(7)
+    model.seed_draws(7)
     out = model(inp)
     lo = VolSDFLoss(**synth.loss_conf())(out, {"rgb": T(b["rgb"]), "lines2d": T(b["lines2d"])})
     lo["loss"].backward()
