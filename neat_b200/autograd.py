@@ -87,8 +87,8 @@ def step_forward(renderer, st, beta):
     # SMs idle, and the small launches (eikonal points: 16 tiles, surface points: 8 tiles) would each occupy a
     # handful of SMs for the latency of a whole tile.  They go to a side stream, where the block scheduler fits them
     # into the tails of the big launches:
-    #   main : render -> attraction head -> line compositing -> DBSCAN -> host hand-over -> rendering head -> colours
-    #   side : eikonal points (forked before the render launch) ...... surface points -> geometry (after the lines)
+    #   main : render -> attraction head -> line compositing -> rendering head -> colours
+    #   side : eikonal points (forked before the render launch) ... DBSCAN -> host hand-over -> surface points -> geometry
     # The big launches stay serialised (running the two heads concurrently was measured: no gain at 1024 rays, 3 %
     # slower at 8192).  The junction hand-over only needs the attraction head, so the host-side matching overlaps the
     # rendering head (plugin path) or the whole backward (FusedTrainStep) instead of an idle GPU.
@@ -105,20 +105,22 @@ def step_forward(renderer, st, beta):
     st.lines, st.att_save = renderer.head_forward(1, pts, M, st.grad, st.feat, training=True)
     w, lines3d, depth, points3d = renderer.composite_lines(z, st.sdf, st.lines, cam, dirs, beta)
     st.weights, st.depth, st.points3d = w, depth, points3d
-    if st.junction_inputs is not None:
-        if st.dbscan_enabled:
-            cent_d, n_d = renderer.dbscan_async(lines3d.view(-1, 3), 0.01)
-        else:  # abc-neat-a.conf: every attraction end point is a junction candidate (neat_wfr_rend_a.py:465-466)
-            cent_d = lines3d.view(-1, 3)
-            n_d = renderer.pool.get("step.n_all", 1, torch.int32)
-            n_d.fill_(2 * R)
-        st.junction_event, st.junction_host = renderer.to_host_async([n_d, cent_d] + list(st.junction_inputs),
-                                                                     counter=getattr(st, "handover_counter", None))
     lines_done = torch.cuda.Event()
     lines_done.record(main)
     st.rgb, st.rend_save = renderer.head_forward(0, pts, M, st.grad, st.feat, training=True)
     with torch.cuda.stream(side):
         side.wait_event(lines_done)
+        # junction candidates first (the host is waiting for them): DBSCAN is ~100 us of tiny launches (8-block grids),
+        # which used to sit on the main stream between the two heads (ncu launch list, profiles/r02_*)
+        if st.junction_inputs is not None:
+            if st.dbscan_enabled:
+                cent_d, n_d = renderer.dbscan_async(lines3d.view(-1, 3), 0.01)
+            else:  # abc-neat-a.conf: every attraction end point is a junction candidate (neat_wfr_rend_a.py:465-466)
+                cent_d = lines3d.view(-1, 3)
+                n_d = renderer.pool.get("step.n_all", 1, torch.int32)
+                n_d.fill_(2 * R)
+            st.junction_event, st.junction_host = renderer.to_host_async([n_d, cent_d] + list(st.junction_inputs),
+                                                                         counter=getattr(st, "handover_counter", None))
         p3 = renderer.explicit_points(points3d)
         st.sdf3, st.grad3, _, _, _ = renderer.sdf_outputs(p3, R, clamp=True, want_feat=False, tag="surface")
         st.lines2d, st.lines2d_calib, st.l3d, st.pose_inv = renderer.line_geometry(pose, K, st.uv_proj, points3d,

@@ -1012,8 +1012,21 @@ int neat_train_draws(const neat_sampler_config* s, int R, float radius, unsigned
 int neat_gemm_f32(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc, int ta, int tb,
                   const float* bias, int relu, const float* mask, int ldm, int accumulate, void* stream) {
   if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) return fail(NEAT_EINVAL, "bad argument");
-  GemmParams p{A, B, C, M, N, K, lda, ldb, ldc, ta, tb, bias, relu, mask, ldm, accumulate};
-  gemm_f32_kernel<<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  GemmParams p{A, B, C, M, N, K, lda, ldb, ldc, ta, tb, bias, relu, mask, ldm, accumulate, K};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int gx = (N + GEMM_TN - 1) / GEMM_TN, gy = (M + GEMM_TM - 1) / GEMM_TM;
+  int gz = 1;
+  // split-K for reductions much longer than the output is large (the weight gradients: K = 1024 latents): enough CTAs
+  // for every SM; only with a linear epilogue, and the partial sums are ADDED, so a non-accumulating call clears C first
+  if (!bias && !relu && !mask && K >= 512 && gx * gy < 148) {
+    p.k_chunk = 64;
+    gz = (K + p.k_chunk - 1) / p.k_chunk;
+    if (!accumulate) {
+      if (ldc != N) return fail(NEAT_EINVAL, "gemm: split-K needs a dense C when it overwrites");
+      CK(cudaMemsetAsync(C, 0, sizeof(float) * static_cast<size_t>(M) * N, st));
+    }
+  }
+  gemm_f32_kernel<<<dim3(gx, gy, gz), 128, 0, st>>>(p);
   ++g_launches;
   CK(cudaGetLastError());
   return NEAT_OK;

@@ -61,6 +61,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_fwd_kernel(const __grid_c
       float x[3] = {0.f, 0.f, 0.f};
       // ---- stage 0: feature tile by bulk copy into the main planes, [x, view, normal] into the aux columns
       epi_planes_free(sm, e);
+      // The previous tile's shared-memory writes are already ordered before this bulk load through the mbarrier chain
+      // (STS -> a_ready -> MMA -> tcgen05.commit -> d_ready -> here); the barrier below states the same ordering in a
+      // form compute-sanitizer's racecheck can see (it does not follow tcgen05.commit arrivals) -- one bar.sync per tile.
+      if (t > 0) epi_bar();
       if (e.lead) {
         const uint8_t* src = p.feat_tiles + static_cast<size_t>(tile) * TILE_MAIN_BYTES;
         mbar_arrive_expect_tx(&sm.in_ready, TILE_MAIN_BYTES);

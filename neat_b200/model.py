@@ -92,20 +92,21 @@ class _ProjectPoints(torch.autograd.Function):
 
 
 class _WeightNormMLP(nn.Module):
-    """lin0..lin{n-1} with nn.utils.weight_norm, parameters only: the math runs in the kernels."""
+    """lin0..lin{n-1} with nn.utils.weight_norm, parameters only: the math runs in the kernels.  Layers are created,
+    initialised (`init_fn(l, lin)`) and weight-normed one at a time, in the reference's order, so that the same
+    torch.manual_seed gives the same initial weights as the reference constructors (neat_wfr_rend_a.py:46-72)."""
 
-    def __init__(self, dims_in_out, weight_norm=True):
+    def __init__(self, dims_in_out, weight_norm=True, init_fn=None):
         super().__init__()
         self.num_layers = len(dims_in_out) + 1
+        self._weight_norm = weight_norm
         for l, (i, o) in enumerate(dims_in_out):
             lin = nn.Linear(i, o)
+            if init_fn is not None:
+                init_fn(l, lin)
+            if weight_norm:
+                lin = nn.utils.weight_norm(lin)
             setattr(self, "lin%d" % l, lin)
-        self._weight_norm = weight_norm
-
-    def _apply_weight_norm(self):
-        if self._weight_norm:
-            for l in range(self.num_layers - 1):
-                setattr(self, "lin%d" % l, nn.utils.weight_norm(getattr(self, "lin%d" % l)))
 
 
 class ImplicitNetwork(_WeightNormMLP):
@@ -120,25 +121,30 @@ class ImplicitNetwork(_WeightNormMLP):
         io = []
         for l in range(len(full) - 1):
             io.append((full[l], full[l + 1] - d0 if (l + 1) in skip_in else full[l + 1]))
-        super().__init__(io, weight_norm)
+        n = len(io)
+
+        def geometric(l, lin):                                  # neat_wfr_rend_a.py:55-69, same calls in the same order
+            if not geometric_init:
+                return
+            i, o = io[l]
+            if l == n - 1:
+                torch.nn.init.normal_(lin.weight, mean=math.sqrt(math.pi) / math.sqrt(i), std=0.0001)
+                torch.nn.init.constant_(lin.bias, -bias)
+            elif multires > 0 and l == 0:
+                torch.nn.init.constant_(lin.bias, 0.0)
+                torch.nn.init.constant_(lin.weight[:, 3:], 0.0)
+                torch.nn.init.normal_(lin.weight[:, :3], 0.0, math.sqrt(2) / math.sqrt(o))
+            elif multires > 0 and l in skip_in:
+                torch.nn.init.constant_(lin.bias, 0.0)
+                torch.nn.init.normal_(lin.weight, 0.0, math.sqrt(2) / math.sqrt(o))
+                torch.nn.init.constant_(lin.weight[:, -(d0 - 3):], 0.0)
+            else:
+                torch.nn.init.constant_(lin.bias, 0.0)
+                torch.nn.init.normal_(lin.weight, 0.0, math.sqrt(2) / math.sqrt(o))
+
+        super().__init__(io, weight_norm, init_fn=geometric)
         self.sdf_bounding_sphere, self.sphere_scale, self.skip_in = sdf_bounding_sphere, sphere_scale, tuple(skip_in)
         self.multires = multires
-        if geometric_init:
-            n = len(io)
-            for l, (i, o) in enumerate(io):
-                lin = getattr(self, "lin%d" % l)
-                with torch.no_grad():
-                    if l == n - 1:
-                        lin.weight.normal_(math.sqrt(math.pi) / math.sqrt(i), 1e-4)
-                        lin.bias.fill_(-bias)
-                    else:
-                        lin.bias.zero_()
-                        lin.weight.normal_(0.0, math.sqrt(2.0) / math.sqrt(o))
-                        if multires > 0 and l == 0:
-                            lin.weight[:, 3:].zero_()
-                        elif multires > 0 and l in skip_in:
-                            lin.weight[:, -(d0 - 3):].zero_()
-        self._apply_weight_norm()
         self._owner = None  # set by VolSDFNetwork (gives access to the kernel context)
 
     # --- standalone (inference) entry points used by evaluation / mesh extraction callers ---
@@ -179,7 +185,6 @@ class _Head(_WeightNormMLP):
         full = [d0] + list(dims) + [d_out]
         super().__init__([(full[l], full[l + 1]) for l in range(len(full) - 1)], weight_norm)
         self.mode, self.multires_view = mode, multires_view
-        self._apply_weight_norm()
         self._owner = None
         self._head = 0
 
@@ -353,7 +358,10 @@ class VolSDFNetwork(nn.Module):
     def forward(self, input):
         rn = self._get_renderer()
         dev = rn.ctx.device
-        K4 = input["intrinsics"][0].to(dev, torch.float32).contiguous()
+        K4 = input["intrinsics"][0].to(dev, torch.float32)
+        if tuple(K4.shape) == (3, 3):     # BlenderDataset hands out the 3x3 calibration (blender_hawp_dataset.py:40-41)
+            K4 = torch.block_diag(K4, torch.ones(1, 1, device=dev))
+        K4 = K4.contiguous()
         pose = input["pose"][0].to(dev, torch.float32).contiguous()
         uv = input["uv"].reshape(-1, 2).to(dev, torch.float32).contiguous()
         uv_proj = input["uv_proj"].reshape(-1, 2).to(dev, torch.float32).contiguous()

@@ -67,3 +67,25 @@ def test_loss_has_no_cpu_path():
     gt = {"rgb": torch.zeros(1, R, 3), "lines2d": torch.zeros(1, R, 5)}
     with pytest.raises(_lib.NeatError):
         VolSDFLoss(**synth.loss_conf())(out, gt)
+
+
+def test_same_seed_gives_the_reference_initial_weights():
+    """Constructing the plugin under torch.manual_seed(s) draws the same random numbers in the same order as the
+    reference constructors (neat_wfr_rend_a.py:46-72, 257-303): bit-identical initial state dicts, every shipped model
+    block.  Needs the reference (tree or the archive oracle/build_ref.py makes)."""
+    import pytest
+    import torch
+    from oracle import ref_shim
+    from neat_b200 import synth
+    from neat_b200.model import VolSDFNetwork
+    if not ref_shim.available():
+        pytest.skip("reference not available")
+    Net, _, _, _ = ref_shim.load_classes()
+    for conf in (synth.dtu_conf(), synth.abc_conf(), synth.toy_conf()):
+        torch.manual_seed(42)
+        ref = Net(conf=ref_shim.to_config(conf)).state_dict()
+        torch.manual_seed(42)
+        mine = VolSDFNetwork(conf).state_dict()
+        assert set(ref) == set(mine)
+        for k in ref:
+            assert torch.equal(ref[k], mine[k]), k
