@@ -4,7 +4,9 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libneat_b200.so")
+# NEAT_LIB_VARIANT=<tag> (measurement scripts only): an A/B build made by `python -m neat_b200.build --variant <tag> -D...`
+_VARIANT = os.environ.get("NEAT_LIB_VARIANT")
+LIB_PATH = os.path.join(_HERE, "libneat_b200.%s.so" % _VARIANT if _VARIANT else "libneat_b200.so")
 
 
 class NeatError(RuntimeError):
@@ -154,6 +156,8 @@ def load():
         fn.argtypes = args
     lib.neat_debug_set_l2_prefetch.restype = _I
     lib.neat_debug_set_l2_prefetch.argtypes = [_I]
+    lib.neat_debug_set_flags.restype = _I
+    lib.neat_debug_set_flags.argtypes = [ctypes.c_uint]
     lib.neat_debug_set_grid_cap.restype = _I
     lib.neat_debug_set_grid_cap.argtypes = [_P, _I]
     lib.neat_debug_set_wgrad_split.restype = _I

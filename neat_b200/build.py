@@ -22,22 +22,27 @@ def _newer_than(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, defines=()):
+    """variant / defines: an A/B build `libneat_b200.<variant>.so` with extra -D flags (scripts/whatif.py loads it through
+    NEAT_LIB_VARIANT); the product library is always the plain build."""
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     deps.append(os.path.join(os.path.dirname(HERE), "include", "neat_b200.h"))
-    if not force and not _newer_than(OUT, deps):
-        return OUT
-    cmd = [NVCC, "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC,-Wall", *ARCH,
+    out = os.path.join(HERE, "libneat_b200.%s.so" % variant) if variant else OUT
+    if not force and not variant and not _newer_than(out, deps):
+        return out
+    cmd = [NVCC, "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC,-Wall", *ARCH, *defines,
            "-Xptxas", "-v" if verbose else "-warn-spills",
-           "-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc failed")
     if verbose:
         sys.stderr.write(r.stdout + r.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    var = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=var,
+                defines=[a for a in sys.argv[1:] if a.startswith("-D")]))

@@ -1406,6 +1406,10 @@ int neat_debug_set_wgrad_split(neat_ctx* c, int max_split, int tiles_per_split) 
   return NEAT_OK;
 }
 
+int neat_debug_set_flags(unsigned flags) {
+  CK(cudaMemcpyToSymbol(g_dbg, &flags, sizeof(unsigned)));
+  return NEAT_OK;
+}
 int neat_debug_set_l2_prefetch(int on) {
   CK(cudaMemcpyToSymbol(g_l2_prefetch, &on, sizeof(int)));
   return NEAT_OK;

@@ -218,6 +218,11 @@ struct SdfBwdParams {
   float* zhat;              // scratch [gridDim.x][L-1][256][128] fp32
 };
 
+#ifndef NEAT_SDF_BWD_PF
+#define NEAT_SDF_BWD_PF 1
+#endif
+constexpr int SDF_BWD_PF = NEAT_SDF_BWD_PF;  // prefetch distance of the sweeps' saved-tensor loads, in 8-column units
+
 template <int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_constant__ SdfBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -237,14 +242,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
     Epi e = epi_make(sm);
     const SdfSaveLayout fl = sdf_save_layout(L, true);
     const SdfBwdSaveLayout bl = sdf_bwd_layout(L);
-    float* __restrict__ zhat_base = p.zhat + static_cast<size_t>(blockIdx.x) * (L - 1) * (256 * TILE_M);
+#ifdef NEAT_ZHAT_HINT
+    const uint64_t zh_pol = l2_policy_evict_last();
+#endif
+    uint8_t* __restrict__ zhat_base = reinterpret_cast<uint8_t*>(p.zhat) + static_cast<size_t>(blockIdx.x) * (L - 1) * (2 * ZH_PLANE_BYTES);
     for (int t = 0; t < my_tiles; ++t) {
       const int tile = blockIdx.x + t * gridDim.x;
       const int pt = tile * TILE_M + e.row;
       const bool valid = pt < p.pts.M;
       const uint8_t* __restrict__ frec = p.fwd_save + static_cast<size_t>(tile) * fl.total;
       uint8_t* brec = p.bwd_save + static_cast<size_t>(tile) * bl.total;
-      const float* __restrict__ d1_base = reinterpret_cast<const float*>(frec + fl.d1);
+      const uint8_t* __restrict__ d1_base = frec + fl.d1;   // sigma' records: 16-bit fixed point (engine.cuh)
       // ---------------------------------------------------------------- stage 0: tangent seed p_0 = J (act * n_bar)
       epi_planes_free(sm, e);
       if (e.j == 0) {
@@ -280,37 +288,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
       // ---------------------------------------------------------------- tangent sweep, layers 0 .. L-2
       for (int l = 0; l < L - 1; ++l) {
         const Step st = p.prog.s[l];
-        const float* __restrict__ d1 = d1_base + static_cast<size_t>(l) * (256 * TILE_M);
+        const uint8_t* __restrict__ d1 = d1_base + static_cast<size_t>(l) * D1_BYTES;
         const uint8_t* __restrict__ a_hi = frec + fl.a + static_cast<size_t>(l) * TILE_MAIN_BYTES;
         const uint8_t* __restrict__ a_lo = a_hi + PLANE_MAIN_BYTES;
-        float* __restrict__ zh = zhat_base + static_cast<size_t>(l) * (256 * TILE_M);
+        uint8_t* __restrict__ zh = zhat_base + static_cast<size_t>(l) * (2 * ZH_PLANE_BYTES);
         const int npad = st.w.npad;
-        float s1n[8];
-        uint4 ahn, aln;
+        // Loads of the saved tensors run SDF_BWD_PF units ahead of their use (the first ones before the accumulator wait):
+        // every one is an HBM round trip, and taken one unit ahead they formed a chain of eight per layer.  After full
+        // unrolling the arrays below are plain registers with short live ranges (3 x 12 in flight).
+        uint4 sp[SDF_BWD_PF + 1], ahv[SDF_BWD_PF + 1], alv[SDF_BWD_PF + 1];   // slot = unit % (PF + 1)
         auto issue = [&](int u) {
-          const int c = epi_unit_col(e, u);
+          const int c = epi_unit_col(e, u), k = u % (SDF_BWD_PF + 1);
           if (c < npad) {
-            f4_unpack(__ldg(f4_at(d1, c, e.row)), s1n);
-            f4_unpack(__ldg(f4_at(d1, c + 4, e.row)), s1n + 4);
-            ahn = ldg128(a_hi + (c >> 3) * A_CHUNK_BYTES + e.row * 16);
-            aln = ldg128(a_lo + (c >> 3) * A_CHUNK_BYTES + e.row * 16);
+            sp[k] = __ldg(s1_at(d1, e, u));
+            ahv[k] = ldg128(a_hi + unit_off(e, u));
+            alv[k] = ldg128(a_lo + unit_off(e, u));
           }
         };
         uint8_t* psave = brec + bl.p + static_cast<size_t>(l) * TILE_MAIN_BYTES;  // p_{l+1}
-        issue(0);
+#pragma unroll
+        for (int u = 0; u < SDF_BWD_PF; ++u) issue(u);
         epi_wait_d(sm, e);  // D = q_l = W_l p_l
 #pragma unroll
         for (int u = 0; u < N_UNITS; ++u) {
           const int c = epi_unit_col(e, u);
-          float s1[8];
-          const uint4 ah = ahn, al = aln;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) s1[j] = s1n[j];
-          if (u + 1 < N_UNITS) issue(u + 1);
+          constexpr int PFS = SDF_BWD_PF + 1;
+          const uint4 spu = sp[u % PFS], ahu = ahv[u % PFS], alu = alv[u % PFS];
+          if (u + SDF_BWD_PF < N_UNITS) issue(u + SDF_BWD_PF);
           if (c < npad) {
-            float a[8], q[8];
+            float a[8], q[8], s1[8];
             tmem_ld8(e.tm + st.d_col + c, q);
-            unpack_hilo8<false>(ah, al, a);
+            unpack_hilo8<false>(ahu, alu, a);
+            s1_unpack8(spu, s1);
             tmem_ld_wait();
             float zv[8];
 #pragma unroll
@@ -318,8 +327,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
               zv[i] = SP_BETA * (1.0f - s1[i]) * a[i] * q[i];  // zhat_l = sigma'' g_{l+1} q_l
               q[i] *= s1[i];                                     // p_{l+1}
             }
-            *f4_at(zh, c, e.row) = make_float4(zv[0], zv[1], zv[2], zv[3]);
-            *f4_at(zh, c + 4, e.row) = make_float4(zv[4], zv[5], zv[6], zv[7]);
+#ifdef NEAT_ZHAT_HINT
+            stg128_hint(zh_at(zh, 0, e, u), make_float4(zv[0], zv[1], zv[2], zv[3]), zh_pol);
+            stg128_hint(zh_at(zh, 1, e, u), make_float4(zv[4], zv[5], zv[6], zv[7]), zh_pol);
+#else
+            *zh_at(zh, 0, e, u) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+            *zh_at(zh, 1, e, u) = make_float4(zv[4], zv[5], zv[6], zv[7]);
+#endif
             store_a8_save<false>(sm.a_hi, sm.a_lo, psave, e.row, c, q);
           }
           if ((u & 1) && l < L - 2) epi_publish_group(sm, u >> 1);  // -> F_{l+1}
@@ -368,30 +382,40 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
       for (int l = L - 1; l >= 1; --l) {
         const Step st = p.prog.s[(L - 1) + (L - 1 - l)];
         const int ncols = p.prog.s[l - 1].w.npad;  // width of z_bar_{l-1}
-        const float* __restrict__ d1 = d1_base + static_cast<size_t>(l - 1) * (256 * TILE_M);
-        const float* zh = zhat_base + static_cast<size_t>(l - 1) * (256 * TILE_M);
-        float s1n[8], zzn[8];
+        const uint8_t* __restrict__ d1 = d1_base + static_cast<size_t>(l - 1) * D1_BYTES;
+        uint8_t* zh = zhat_base + static_cast<size_t>(l - 1) * (2 * ZH_PLANE_BYTES);
+        uint4 sp[SDF_BWD_PF + 1];
+        float4 z0[SDF_BWD_PF + 1], z1[SDF_BWD_PF + 1];
         auto issue = [&](int u) {
-          const int c = epi_unit_col(e, u);
+          const int c = epi_unit_col(e, u), k = u % (SDF_BWD_PF + 1);
           if (c < ncols) {
-            f4_unpack(__ldg(f4_at(d1, c, e.row)), s1n);
-            f4_unpack(__ldg(f4_at(d1, c + 4, e.row)), s1n + 4);
-            f4_unpack(*f4_at(zh, c, e.row), zzn);  // written by this very thread in the tangent sweep
-            f4_unpack(*f4_at(zh, c + 4, e.row), zzn + 4);
+            sp[k] = __ldg(s1_at(d1, e, u));
+#ifdef NEAT_ZHAT_HINT
+            z0[k] = ldg128_hint(zh_at(zh, 0, e, u), zh_pol);
+            z1[k] = ldg128_hint(zh_at(zh, 1, e, u), zh_pol);
+#else
+            z0[k] = *zh_at(zh, 0, e, u);  // written by this very thread in the tangent sweep
+            z1[k] = *zh_at(zh, 1, e, u);
+#endif
           }
         };
         uint8_t* zsave = brec + bl.zb + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES;  // z_bar_{l-1}
-        issue(0);
+#pragma unroll
+        for (int u = 0; u < SDF_BWD_PF; ++u) issue(u);
         epi_wait_d(sm, e);  // D = W_l^T z_bar_l  (gradient w.r.t. the input of layer l)
         if (l == L - 1) epi_planes_free(sm, e);  // the bulk store of z_bar_{L-1} out of the A planes (above)
 #pragma unroll
         for (int u = 0; u < N_UNITS; ++u) {
           const int c = epi_unit_col(e, u);
-          float s1[8], zz[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { s1[j] = s1n[j]; zz[j] = zzn[j]; }
-          if (u + 1 < N_UNITS) issue(u + 1);
+          constexpr int PFS = SDF_BWD_PF + 1;
+          const uint4 spu = sp[u % PFS];
+          const float4 z0u = z0[u % PFS], z1u = z1[u % PFS];
+          if (u + SDF_BWD_PF < N_UNITS) issue(u + SDF_BWD_PF);
           if (c < ncols) {
+            float s1[8], zz[8];
+            s1_unpack8(spu, s1);
+            f4_unpack(z0u, zz);
+            f4_unpack(z1u, zz + 4);
             float gq[8];
             tmem_ld8(e.tm + st.d_col + c, gq);
             tmem_ld_wait();

@@ -252,6 +252,49 @@ __device__ __forceinline__ const float4* f4_at(const float* base, int col, int r
 }
 __device__ __forceinline__ void f4_unpack(const float4& v, float* o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
 
+// sigma'(z) = sigmoid(100 z) in [0, 1] travels between epilogues (sdf_render forward -> its normal pass -> both sweeps of
+// sdf_bwd) as 16-bit FIXED POINT, n = rn(65535 sigma'): 0 and 1 (the linear branch of Softplus) are exact, the absolute
+// error is <= 7.6e-6 everywhere.  Measured before adopting it (profiles/r02_whatif_parity.log, fp32 values rounded to
+// this grid): no change of any parameter gradient beyond run-to-run noise, normals 6.5e-6 -> 8.2e-6 of their range.  As
+// fp32 it was 8 KB of every 25 KB / point the forward writes and was read three times; the sweeps that read it are bound
+// by exactly that traffic (profiles/r02_whatif_timing.log: sdf_bwd 1.22 ms -> 0.80 ms with its loads switched off).
+// Layout of one layer's block (64 KB per tile): the operand tiles' own chunk-major order, [column / 8][row][8 columns]
+// -- the 8 columns of a unit are ONE 16-byte access per thread and 512 contiguous bytes per warp, and the byte offset of
+// (thread, unit) is the same expression for sigma', the hi / lo planes of a saved operand tile and the two planes of the
+// zhat scratch (unit_off below): one offset register serves every stream of the backward epilogues.
+constexpr int S1_LAYER_BYTES = 256 * TILE_M * 2;
+// byte offset of this thread's 16 bytes of unit u (8 columns) in a chunk-major plane
+__device__ __forceinline__ uint32_t unit_off(const Epi& e, int u) {
+  return static_cast<uint32_t>(2 * e.j * A_CHUNK_BYTES + e.row * 16) + static_cast<uint32_t>((u >> 1) * 8 + (u & 1)) * A_CHUNK_BYTES;
+}
+__device__ __forceinline__ uint4* s1_at(uint8_t* layer, const Epi& e, int u) {
+  return reinterpret_cast<uint4*>(layer + unit_off(e, u));
+}
+__device__ __forceinline__ const uint4* s1_at(const uint8_t* layer, const Epi& e, int u) {
+  return reinterpret_cast<const uint4*>(layer + unit_off(e, u));
+}
+// zhat scratch of one layer (sdf_bwd): two such planes of float4, columns 0-3 / 4-7 of every chunk
+constexpr int ZH_PLANE_BYTES = (256 / 8) * TILE_M * 16;
+__device__ __forceinline__ float4* zh_at(uint8_t* layer, int half, const Epi& e, int u) {
+  return reinterpret_cast<float4*>(layer + half * ZH_PLANE_BYTES + unit_off(e, u));
+}
+__device__ __forceinline__ uint32_t s1_pack2(float a, float b) {
+  // 2^23 + x rounds x to the nearest integer (ulp = 1): the low 16 bits of the sum's mantissa are n
+  return __byte_perm(__float_as_uint(fmaf(a, 65535.0f, 8388608.0f)), __float_as_uint(fmaf(b, 65535.0f, 8388608.0f)), 0x5410);
+}
+__device__ __forceinline__ uint4 s1_pack8(const float* d) {
+  return make_uint4(s1_pack2(d[0], d[1]), s1_pack2(d[2], d[3]), s1_pack2(d[4], d[5]), s1_pack2(d[6], d[7]));
+}
+__device__ __forceinline__ void s1_unpack2(uint32_t w, float& a, float& b) {
+  // bits 0x4B000000 | n are the float 2^23 + n; fma((2^23 + n), s, -2^23 s) = rn(n s) with a single rounding
+  constexpr float s = 1.0f / 65535.0f, c = -8388608.0f * s;
+  a = fmaf(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)), s, c);
+  b = fmaf(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)), s, c);
+}
+__device__ __forceinline__ void s1_unpack8(const uint4& w, float* o) {
+  s1_unpack2(w.x, o[0], o[1]); s1_unpack2(w.y, o[2], o[3]); s1_unpack2(w.z, o[4], o[5]); s1_unpack2(w.w, o[6], o[7]);
+}
+
 // after this thread finished writing its slice of group g of the A tile (and reading that part of the accumulator).
 // Every lane fences its own writes, the warp converges, ONE lane arrives: 16 arrivals per barrier phase instead of
 // 512 serialized shared-memory atomics on one word.  All publish / store helpers must be called warp-uniformly.

@@ -6,7 +6,7 @@
 // Both passes run on the tensor cores with the point tile resident in shared memory; no autograd graph.
 // Outputs per point: sdf (sphere-clamped), normal (unnormalised), feature tile (bf16 hi/lo, tile layout).
 // In training mode the kernel also writes what the hand-written backward needs (per 128-point tile):
-//   sigma'_l (fp32), the layer inputs u_l and the normal-pass vectors a_l (bf16 hi/lo operand tiles).
+//   sigma'_l (16-bit fixed point), the layer inputs u_l and the normal-pass vectors a_l (bf16 hi/lo operand tiles).
 #pragma once
 #include "engine.cuh"
 #include "sdf_query.cuh"
@@ -17,7 +17,7 @@ constexpr int PLANE_MAIN_BYTES = A_MAIN_COLS / 8 * A_CHUNK_BYTES;  // 65536
 constexpr int PLANE_AUX_BYTES = A_AUX_COLS / 8 * A_CHUNK_BYTES;    // 12288
 constexpr int TILE_MAIN_BYTES = 2 * PLANE_MAIN_BYTES;              // hi + lo
 constexpr int TILE_AUX_BYTES = 2 * PLANE_AUX_BYTES;
-constexpr int D1_BYTES = 256 * TILE_M * 4;                         // sigma' of one layer, [col][row] fp32
+constexpr int D1_BYTES = S1_LAYER_BYTES;                           // sigma' of one layer, 16-bit fixed point (engine.cuh)
 constexpr int RSKIP_BYTES = A_AUX_COLS * TILE_M * 4;
 
 // Byte layout of one tile's save record (training) / one CTA's scratch (inference)
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
       const int pt = tile * TILE_M + e.row;
       const bool valid = pt < p.pts.M;
       uint8_t* rec = p.save + static_cast<size_t>(tr ? tile : static_cast<int>(blockIdx.x)) * lay.total;
-      float* d1_base = reinterpret_cast<float*>(rec + lay.d1);
+      uint8_t* d1_base = rec + lay.d1;
       float* rskip = reinterpret_cast<float*>(rec + lay.rskip);
       float x[3] = {0.f, 0.f, 0.f};
       if (e.j == 0 && valid) load_point(p.pts, pt, x);
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
       for (int l = 0; l < L - 1; ++l) {
         const Step st = p.prog.s[l];
         const float4* bias = reinterpret_cast<const float4*>(p.packed + st.w.bias_off);
-        float* d1 = d1_base + static_cast<size_t>(l) * (256 * TILE_M);
+        uint8_t* d1 = d1_base + static_cast<size_t>(l) * D1_BYTES;
         uint8_t* usave = tr ? rec + lay.u + static_cast<size_t>(l) * TILE_MAIN_BYTES : nullptr;  // u_{l+1}
         epi_wait_d(sm, e);
         // (TMEM columns past npad are allocated but hold stale data: loaded unconditionally, never used)
@@ -115,26 +115,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
           for (int j = 0; j < 16; ++j) acc[j] = nxt[j];
           if (g + 1 < N_GROUPS) tmem_ld16(e.tm + st.d_col + epi_col(e, g + 1), nxt);
           const bool has = c0 < st.w.npad;
+          uint4 s1p[2];
           if (has) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 b = __ldg(bias + (c0 >> 2) + j);
-              const float bb[4] = {b.x, b.y, b.z, b.w};
-              float dd[4];
+            for (int h = 0; h < 2; ++h) {
+              float dd[8];
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                float hv;
-                softplus100_d1(fmaf(acc[4 * j + k], st.comp, bb[k]), hv, dd[k]);   // comp: layout.h (RZ accumulation)
-                acc[4 * j + k] = hv;
+              for (int j = 0; j < 2; ++j) {
+                const float4 b = __ldg(bias + (c0 >> 2) + 2 * h + j);
+                const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  float hv;
+                  softplus100_d1(fmaf(acc[8 * h + 4 * j + k], st.comp, bb[k]), hv, dd[4 * j + k]);   // comp: layout.h (RZ accumulation)
+                  acc[8 * h + 4 * j + k] = hv;
+                }
               }
-              *f4_at(d1, c0 + 4 * j, e.row) = make_float4(dd[0], dd[1], dd[2], dd[3]);
+              s1p[h] = s1_pack8(dd);
             }
             store_a16<true>(sm.a_hi, sm.a_lo, e.row, c0, acc);
           }
           epi_publish_group(sm, g);
-          if (has && usave) {  // after the publish: nothing waits for the save record (bf16 pairs, see engine.cuh)
-            stg_bf16_pairs8(usave, PLANE_MAIN_BYTES, e.row, c0 >> 3, acc);
-            stg_bf16_pairs8(usave, PLANE_MAIN_BYTES, e.row, (c0 >> 3) + 1, acc + 8);
+          if (has) {  // after the publish: nothing waits for the records (sigma': read back by this thread's normal pass)
+            *s1_at(d1, e, 2 * g) = s1p[0];
+            *s1_at(d1, e, 2 * g + 1) = s1p[1];
+            if (usave) {  // bf16 pairs, see engine.cuh
+              stg_bf16_pairs8(usave, PLANE_MAIN_BYTES, e.row, c0 >> 3, acc);
+              stg_bf16_pairs8(usave, PLANE_MAIN_BYTES, e.row, (c0 >> 3) + 1, acc + 8);
+            }
           }
         }
       }
@@ -187,14 +195,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
 
       // ------------------------------------------------------------ normal pass seed: a_{L-2} = sigma'_{L-2} * W_{L-1}[0,:]
       {
-        const float* d1 = d1_base + static_cast<size_t>(L - 2) * (256 * TILE_M);
+        const uint8_t* d1 = d1_base + static_cast<size_t>(L - 2) * D1_BYTES;
         const int npad = p.prog.s[L - 2].w.npad;
         for (int g = 0; g < N_GROUPS; ++g) {
           const int c0 = epi_col(e, g);
           if (c0 < npad) {
             float a[16];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) f4_unpack(*f4_at(d1, c0 + 4 * j, e.row), a + 4 * j);
+            s1_unpack8(*s1_at(d1, e, 2 * g), a);
+            s1_unpack8(*s1_at(d1, e, 2 * g + 1), a + 8);
 #pragma unroll
             for (int j = 0; j < 16; ++j) a[j] *= __ldg(w_row + c0 + j);
             store_a16<true>(sm.a_hi, sm.a_lo, e.row, c0, a);
@@ -211,27 +219,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
       for (int l = L - 2; l >= 1; --l) {
         const Step st = p.prog.s[(L + 1) + (L - 2 - l)];
         const int npad = st.w.npad;                            // width of the input of layer l
-        const float* d1 = d1_base + static_cast<size_t>(l - 1) * (256 * TILE_M);
+        const uint8_t* d1 = d1_base + static_cast<size_t>(l - 1) * D1_BYTES;
         const int n_main = (l == p.skip) ? p.H - p.E : npad;   // columns that feed a_{l-1}
-        float s1n[8];
+        // sigma'_{l-1} (16 bytes per unit, written by this very thread in the forward pass) is requested PF units ahead,
+        // the first PF before waiting for the accumulator: the round trips (L2 or HBM, ~1 us each) overlap the MMAs
+        // instead of forming a chain of eight as they did when taken one unit ahead (whole layer ahead: spills)
+        constexpr int PF = 4;
+        uint4 s1p[PF];
         auto issue = [&](int u) {
-          const int c = epi_unit_col(e, u);
-          if (c < npad) {
-            f4_unpack(*f4_at(d1, c, e.row), s1n);          // written by this very thread
-            f4_unpack(*f4_at(d1, c + 4, e.row), s1n + 4);
-          }
+          if (epi_unit_col(e, u) < npad) s1p[u % PF] = *s1_at(d1, e, u);
         };
+#pragma unroll
+        for (int u = 0; u < PF; ++u) issue(u);
         uint8_t* asave = tr ? rec + lay.a + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES : nullptr;  // a_{l-1}
-        issue(0);
         epi_wait_d(sm, e);
 #pragma unroll
         for (int u = 0; u < N_UNITS; ++u) {
           const int c = epi_unit_col(e, u);
-          float s1[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) s1[j] = s1n[j];
-          if (u + 1 < N_UNITS) issue(u + 1);
+          const uint4 s1u = s1p[u % PF];
+          if (u + PF < N_UNITS) issue(u + PF);
           if (c < npad) {
+            float s1[8];
+            s1_unpack8(s1u, s1);
             float acc[8];
             tmem_ld8(e.tm + st.d_col + c, acc);
             tmem_ld_wait();

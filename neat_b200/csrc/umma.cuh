@@ -77,6 +77,12 @@ __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, u
 // same hint issued by an epilogue thread made sdf_bwd slower (1.37 -> 1.57 ms): the issuing warp stalls, and the tile
 // waits for its slowest warp.  g_l2_prefetch (neat_debug_set_l2_prefetch): 0 = all hints off, n > 0 = wgrad's distance.
 __constant__ int g_l2_prefetch = 2;
+// what-if switches for measurements only (neat_debug_set_flags; 0 in every product / test path):
+//   1: wgrad skips X_hi * Y_lo      2: wgrad skips X_lo * Y_hi        4: sigma' rounded to 16-bit fixed point when saved
+//   8: sdf_bwd builds zhat from the hi plane of a_l only
+//  16: sdf_bwd epilogues skip their global loads   32: ... skip their global stores (p, z_bar; WRONG RESULTS, timing only)
+//  64: sdf_render skips the u / a / feat save stores   128: sdf_render's normal pass skips the sigma' loads (timing only)
+__constant__ unsigned g_dbg = 0;
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem, uint32_t bytes) {
   if (g_l2_prefetch)
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
@@ -84,6 +90,31 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem, uint32_t byte
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// ---------------------------------------------------------------- L2 eviction-priority hints (per access)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void stg128_hint(void* ptr, const float4& v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w),
+               "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ float4 ldg128_hint(const void* ptr, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(ptr), "l"(pol)
+               : "memory");
+  return v;
+}
 
 // generic-proxy writes to smem -> visible to the async proxy (TMA / tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

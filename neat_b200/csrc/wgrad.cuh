@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WJob* __rest
     const uint64_t dyh0 = make_desc_k(smem_u32(sm.y_hi), 128, A_CHUNK_BYTES), dyl0 = make_desc_k(smem_u32(sm.y_lo), 128, A_CHUNK_BYTES);
     const uint64_t don0 = make_desc_k(smem_u32(sm.ones), 128, A_CHUNK_BYTES);
     const bool has_bias = job.bias != nullptr;
+    const bool t_hl = !(g_dbg & 1u), t_lh = !(g_dbg & 2u);
     for (int t = 0; t < my_tiles; ++t) {
       mbar_wait(&sm.full, t & 1);
       tc_fence_after();
@@ -160,12 +161,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WJob* __rest
           const uint64_t dyh = desc_advance(dyh0, ko), dyl = desc_advance(dyl0, ko);
           const uint32_t acc = (t | ks) ? 1u : 0u;
           umma_bf16(d, dxh, dyh, idesc, acc);
-          umma_bf16(d, dxh, dyl, idesc, 1u);
-          umma_bf16(d, dxl, dyh, idesc, 1u);
+          if (t_hl) umma_bf16(d, dxh, dyl, idesc, 1u);
+          if (t_lh) umma_bf16(d, dxl, dyh, idesc, 1u);
           if (has_bias) {
             const uint64_t don = desc_advance(don0, ko);
             umma_bf16(d1, dxh, don, idesc1, acc);
-            umma_bf16(d1, dxl, don, idesc1, 1u);
+            if (t_lh) umma_bf16(d1, dxl, don, idesc1, 1u);
           }
         }
         umma_commit(&sm.empty);

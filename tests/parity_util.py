@@ -108,10 +108,10 @@ def grad_errors(named_grads, ref_grads):
     return table
 
 
-def assert_grads(table, tol_l2=GRAD_TOL_L2, tol_max=GRAD_TOL_MAX):
+def assert_grads(table, tol_l2=GRAD_TOL_L2, tol_max=GRAD_TOL_MAX, beta_tol=BETA_TOL):
     bad = []
     for n, (l2, mx, nrm) in table.items():
-        t2, tm = (BETA_TOL, BETA_TOL) if n == "density.beta" else (tol_l2, tol_max)
+        t2, tm = (beta_tol, beta_tol) if n == "density.beta" else (tol_l2, tol_max)
         if not (l2 <= t2 and mx <= tm):
             bad.append((n, l2, mx, nrm))
     assert not bad, "gradient parity: " + "; ".join("%s rel_l2 %.2e rel_max %.2e (|ref| %.2e)" % x for x in bad)

@@ -99,22 +99,11 @@ def test_eval_forward_vs_reference(name):
     errs = {k: G.rel_err(out[k].cpu(), g["eval_" + k])
             for k in ("rgb_values", "depth", "points3d", "lines3d", "lines2d", "lines2d_calib", "normal_map", "l3d")}
     errs["sdf_abs"] = float(np.abs(out["sdf"].cpu().numpy() - g["eval_sdf"]).max())
-    if name == "abc_beta0.1":
-        # The ABC camera sees the synthetic surface at grazing angles (|sdf| at the composited point up to 0.15, against
-        # 0.01 in the DTU cases): a ray whose bisection / searchsorted decision flips under 1e-6-level SDF differences
-        # moves its samples (measured: 17 of 128 rays, 0.14 % of the samples) and with them its geometric outputs, as in
-        # training mode (test_train_step_vs_reference).  Measured on B200: rgb 7e-7, lines2d 9e-7, depth 2.6e-5,
-        # normal_map 2.0e-5, points3d 1.2e-4, lines3d 1.3e-4, l3d 1.2e-4, sdf 5e-5 abs.  The 1e-4 statement for this
-        # configuration is made at identical samples (test_backward_vs_oracle_same_samples).
-        for k in ("rgb_values", "lines2d", "lines2d_calib", "normal_map", "depth"):
-            assert errs[k] < 1e-4, (k, errs[k])
-        for k in ("points3d", "lines3d", "l3d"):
-            assert errs[k] < 1e-3, (k, errs[k])
-        assert errs["sdf_abs"] < 5e-4
-        return
-    for k in ("rgb_values", "depth", "points3d", "lines3d", "lines2d", "lines2d_calib", "normal_map"):
+    # north_star's bound, 1e-4 of each output's range, on EVERY configuration (abc_beta0.1 included: with the forward
+    # operands as fp16 hi/lo pairs its grazing-angle rays no longer flip sampler decisions against the reference; measured
+    # on B200, profiles/r02_parity_measured.json: lines3d 1.6e-5, points3d 1.5e-5, l3d 1.5e-5, everything else < 4e-6)
+    for k in ("rgb_values", "depth", "points3d", "lines3d", "lines2d", "lines2d_calib", "normal_map", "l3d"):
         assert errs[k] < 1e-4, (k, errs[k])
-    assert errs["l3d"] < 1e-3
     assert errs["sdf_abs"] < 1e-4
 
 
@@ -146,56 +135,58 @@ def run_train(name):
 @pytest.mark.parametrize("name", CASES)
 def test_train_step_vs_reference(name):
     """Training forward (replayed CPU-generator draws) + loss vs the reference goldens, end to end INCLUDING
-    the sampler.  In training mode the final 64 depths come from random u through the inverse CDF, so the few
-    rays whose bisection decision flips under 1e-5-level SDF differences move their samples and with them the
-    per-ray outputs: the bound here is 5e-3 (the 1e-4 bound is asserted at identical samples in
-    test_backward_vs_oracle_same_samples and, including the sampler, in eval mode above)."""
+    the sampler.  In training mode the final 64 depths come from random u through the inverse CDF, so a ray whose
+    bisection decision flips under 1e-6-level SDF differences moves its samples and with them its 3D end points (one
+    ray of the toy case: lines3d 3.8e-4; every other output of every case <= 3e-5, scripts/measure_train_golden.py): per-ray
+    outputs within 1e-3, every loss term within 1e-4 (measured <= 7e-6); the 1e-4 bound on the outputs is asserted at
+    identical samples in test_backward_vs_oracle_same_samples and, including the sampler, in eval mode above."""
     g, conf, sd_np, model, out, lo = run_train(name)
     for k in ("rgb_values", "lines3d", "lines2d", "lines2d_calib", "j3d_global"):
         assert out[k].shape == g["train_" + k].shape, k
-        assert G.rel_err(out[k].detach().cpu(), g["train_" + k]) < 5e-3, k
+        assert G.rel_err(out[k].detach().cpu(), g["train_" + k]) < (1e-3 if k == "lines3d" else 1e-4), k
     assert out["j3d_local"].shape == g["train_j3d_local"].shape
-    assert G.rel_err(out["j3d_local"].detach().cpu(), g["train_j3d_local"]) < 5e-3
-    for k, tol in (("rgb_loss", 1e-4), ("line_loss", 1e-3), ("l2d_loss", 1e-3), ("j3d_loss", 1e-3), ("j2d_loss", 1e-3),
-                   ("eikonal_loss", 5e-3), ("loss", 1e-3)):
+    assert G.rel_err(out["j3d_local"].detach().cpu(), g["train_j3d_local"]) < 1e-4
+    for k, tol in (("rgb_loss", 1e-4), ("line_loss", 1e-4), ("l2d_loss", 1e-4), ("j3d_loss", 1e-4), ("j2d_loss", 1e-4),
+                   ("eikonal_loss", 1e-4), ("loss", 1e-4)):
         ref = float(g["loss_" + k])
         assert abs(float(lo[k]) - ref) <= tol * max(1.0, abs(ref)), (k, float(lo[k]), ref)
     assert int(lo["count"]) == int(g["loss_count"])
     if "train_median" in g:                                # abc-neat-a.conf: the match filter is the median matched cost
-        assert abs(float(out["median"]) - float(g["train_median"])) <= 5e-3 * max(1.0, float(g["train_median"]))
+        assert abs(float(out["median"]) - float(g["train_median"])) <= 1e-3 * max(1.0, float(g["train_median"]))
 
 
 @pytest.mark.parametrize("name", CASES)
 def test_backward_vs_oracle_same_samples(name):
     """Every parameter gradient of the hand-written backward (compositing adjoint, head sweeps, SDF double
-    backward, tensor-core weight-gradient GEMMs) vs autograd through the oracle evaluated at the SAME sample
-    positions (the sampler's discrete decisions are tested separately).  bf16x3 arithmetic: 2e-3 of the norm."""
+    backward, tensor-core weight-gradient GEMMs) vs autograd through the float64 oracle evaluated at the SAME sample
+    positions (the sampler's discrete decisions are tested separately), with the metric of tests/parity_util.py:
+    per tensor rel-L2 <= 1e-3 and max|d| / max|ref| <= 2e-3 (density.beta 1e-2)."""
+    import parity_util as PU
     from oracle import neat_oracle as O
     g, conf, sd_np, model, out, lo = run_train(name)
     st = model.last_step
-    P, leaves = G.oracle_params(conf, sd_np, track=True)
+    dt = torch.float64
+    P, leaves = G.oracle_params(conf, sd_np, dtype=dt, track=True)
     R = st.R
     z_eik = ((st.eik_pts[R:].cpu() - st.cam.cpu()[None]) * st.dirs.cpu()).sum(1, keepdim=True)
-    oo = O.neat_forward(P, G.sampler_conf(conf), T(g["in_intrinsics"][0]), T(g["in_pose"][0]), T(g["in_uv"][0]),
-                        T(g["in_uv_proj"][0]), gt_vertices=T(g["wf_vertices"]), training=True, rnd=G.train_randoms(g),
-                        samples=(st.z.cpu(), z_eik))
+    rnd = G.train_randoms(g)
+    rnd = O.TrainRandoms(rnd.sampler, rnd.eik_uniform.to(dt))
+    D = lambda a: T(a).to(dt)
+    oo = O.neat_forward(P, G.sampler_conf(conf), D(g["in_intrinsics"][0]), D(g["in_pose"][0]), D(g["in_uv"][0]),
+                        D(g["in_uv_proj"][0]), gt_vertices=D(g["wf_vertices"]), training=True, rnd=rnd,
+                        samples=(st.z.cpu().to(dt), z_eik.to(dt)))
     for k in ("rgb_values", "lines3d", "lines2d_calib", "grad_theta", "points3d", "depth"):
         assert G.rel_err(out[k].detach().cpu(), oo[k].detach()) < 1e-4, k
-    ol = O.neat_loss(oo, T(g["in_rgb"][0]), T(g["in_lines2d"][0]), oo["K"])
+    ol = O.neat_loss(oo, D(g["in_rgb"][0]), D(g["in_lines2d"][0]), oo["K"])
     ol["loss"].backward()
     for k in ("loss", "rgb_loss", "eikonal_loss", "line_loss", "j3d_loss", "j2d_loss"):
         assert abs(float(ol[k]) - float(lo[k])) < 1e-4 * max(1.0, abs(float(ol[k]))), k
-    checked = 0
-    for n, p in model.named_parameters():
-        ref = leaves[n].grad
-        assert ref is not None and p.grad is not None, n
-        ref = ref.numpy().astype(np.float64)
-        got = p.grad.detach().cpu().numpy().astype(np.float64)
-        norm = max(np.sqrt((ref * ref).sum()), 1e-12)
-        tol = 5e-2 if n == "density.beta" else 2e-3
-        assert np.abs(got - ref).max() <= tol * norm + 1e-9, (n, np.abs(got - ref).max() / norm)
-        checked += 1
-    assert checked >= 50
+    table = PU.grad_errors({n: p.grad for n, p in model.named_parameters()}, {n: v.grad for n, v in leaves.items()})
+    assert len(table) >= 50
+    # d loss / d density.beta is ONE scalar summed over every sample with mixed signs; in the 128-ray dtu_beta0.01 case it
+    # cancels to 8.9e-6 and the reference's own fp32 arithmetic is 0.95e-2 away from the float64 value there (oracle in
+    # float32 vs float64 at identical samples; 1.5e-5 in dtu_beta0.1), the kernels 1.2e-2: 3e-2 for that case only
+    PU.assert_grads(table, beta_tol=3e-2 if name == "dtu_beta0.01" else PU.BETA_TOL)
 
 
 @pytest.mark.parametrize("N,seed", [(64, 0), (2048, 1), (16384, 2)])
