@@ -186,13 +186,16 @@ def train_config(rays, beta, steps, warmup, rank, world, dev, lib, e2e=True, tim
     e0.record()
     k_acc = torch.zeros(1, dtype=torch.int32, device=dev)  # the sampler's k is data dependent and drifts as beta trains
     wait_ms = 0.0
+    ts.profile = []
     for _ in range(steps):
         ts.step(inp, gt)
         k_acc += ts.st.n_iters
         wait_ms += ts.last_host_ms["wait_for_gpu"]
     e1.record()
     barrier()
-    r = {"rays": rays, "beta": beta, "steps": steps, "warmup": warmup, "ms_total": e0.elapsed_time(e1),
+    prof = ts.profile_ms() or {}
+    ts.profile = None
+    r = {"rays": rays, "graph_ms": prof, "beta": beta, "steps": steps, "warmup": warmup, "ms_total": e0.elapsed_time(e1),
          "launches": int(ts.launches_per_step * steps), "launches_per_step": int(ts.launches_per_step),
          "k_last": int(ts.st.n_iters.item()), "k_mean": float(k_acc.item()) / steps,
          "host_junction_block": dict(ts.last_host_ms, mean_wait_for_gpu=wait_ms / steps), "h2d": TR.h2d_bytes(hb)}
@@ -245,12 +248,15 @@ def train_config(rays, beta, steps, warmup, rank, world, dev, lib, e2e=True, tim
     t = torch.tensor([r["ms_total"], r.get("ms_e2e", 0.0), r.get("plugin_ms_per_step", 0.0)], device=dev, dtype=torch.float64)
     if world > 1:
         mine = torch.tensor([r["ms_total"] / steps, float(r["k_last"]), sum(v[1] for v in tm.values()) / steps,
-                             r.get("last_loss", 0.0), r["host_junction_block"]["mean_wait_for_gpu"]], device=dev,
+                             r.get("last_loss", 0.0), r["host_junction_block"]["mean_wait_for_gpu"], r["k_mean"],
+                             prof.get("graph_A_ms", 0.0), prof.get("graph_B_ms", 0.0), prof.get("gap_ms", 0.0)], device=dev,
                             dtype=torch.float64)
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
         r["per_rank"] = [{"ms_per_step": round(float(a[0]), 3), "sampler_k": int(a[1]), "mlp_kernel_ms": round(float(a[2]), 3),
-                          "last_loss": round(float(a[3]), 5), "host_wait_for_handover_ms": round(float(a[4]), 3)}
+                          "last_loss": round(float(a[3]), 5), "host_wait_for_handover_ms": round(float(a[4]), 3),
+                          "sampler_k_mean": round(float(a[5]), 3), "graph_A_ms": round(float(a[6]), 3),
+                          "graph_B_ms_incl_allreduce_wait": round(float(a[7]), 3), "gap_ms": round(float(a[8]), 3)}
                          for a in allr]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     r["ms_total"], r["ms_e2e"], r["plugin_ms_per_step"] = float(t[0]), float(t[1]), float(t[2])
@@ -520,7 +526,8 @@ def main():
                                 "what": "the same step through the drop-in plugin classes (VolSDFNetwork.forward -> VolSDFLoss -> "
                                         "backward -> neat_b200.optim.Adam, eager launches): where the per-kernel CUDA-event "
                                         "timers of `kernel_ms_per_step` / `roofline` are taken"},
-                "host_junction_block": r["host_junction_block"], "per_rank": r.get("per_rank"), "dp_check": check,
+                "host_junction_block": r["host_junction_block"], "graph_ms": r.get("graph_ms"),
+                "per_rank": r.get("per_rank"), "dp_check": check,
                 "configs": extras}
         if world == 1 and not args.no_eager_baseline:
             try:

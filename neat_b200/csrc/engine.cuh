@@ -69,6 +69,16 @@ __device__ __forceinline__ void engine_init(EngineSmem<STAGES>& sm) {
   tc_fence_after();
 }
 
+// Warpgroup register reallocation: the producer / MMA warpgroup (whose loops live in uniform registers) shrinks to
+// AUX_REGS per thread, the four epilogue warpgroups grow from the launch bound's 96 to EPI_REGS.  Measured motivation
+// (round 2): the backward epilogues keep one 8-column unit of saved tensors in flight per thread because a second one
+// spills at 96 registers (sdf_bwd 1.11 -> 1.30 ms with the spills), and every unit is an HBM round trip.
+// The first statement of every role branch after engine_init (all four warps of a warpgroup execute the same one).
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 template <int STAGES>
 __device__ __forceinline__ void engine_fini(EngineSmem<STAGES>& sm) {
   tc_fence_before();

@@ -15,7 +15,11 @@ constexpr int EPI_WARPS = 16;                        // 4 row quadrants (TMEM la
 constexpr int N_GROUPS = EPI_WARPS / 4;              // column groups
 constexpr int GROUP_COLS = A_MAIN_COLS / N_GROUPS;   // 64 columns per group
 constexpr int EPI_THREADS = EPI_WARPS * 32;          // 512
-constexpr int NUM_THREADS = EPI_THREADS + 64;        // + weight producer warp + MMA issuer warp
+// + one more warpgroup: weight producer warp, MMA issuer warp and two idle warps.  Registers are handed out per 4 warps,
+// so 18 warps cost as much as 20 and cap every thread at 96; with a full fifth warpgroup that gives most of its registers
+// back (setmaxnreg, engine.cuh: role_registers) the 16 epilogue warps run with 112.
+constexpr int NUM_THREADS = EPI_THREADS + 128;
+constexpr int EPI_REGS = 112, AUX_REGS = 32;         // (96 - 32) * 128 freed = (112 - 96) * 512 taken
 constexpr uint32_t TMEM_COLS = 512;                  // two 256-column fp32 accumulators
 
 struct PLayer {        // a packed weight matrix: (nk_main + nk_aux) slabs of npad*64 bytes, then padded fp32 bias

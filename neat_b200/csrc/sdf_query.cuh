@@ -88,10 +88,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_query_kernel(const __grid_
   const int warp = warp_idx_uniform();
 
   if (warp == EPI_WARPS) {
+    reg_dec<AUX_REGS>();
     producer_loop(sm, p.prog, p.packed, my_tiles);
   } else if (warp == EPI_WARPS + 1) {
+    reg_dec<AUX_REGS>();
     mma_loop(sm, p.prog, my_tiles);
+  } else if (warp > EPI_WARPS + 1) {
+    reg_dec<AUX_REGS>();   // the two idle warps of the fifth warpgroup (layout.h)
   } else {
+    reg_inc<EPI_REGS>();
     Epi e = epi_make(sm);
     for (int t = 0; t < my_tiles; ++t) {
       const int pt = (blockIdx.x + t * gridDim.x) * TILE_M + e.row;

@@ -70,10 +70,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
   const int L = p.L;
 
   if (warp == EPI_WARPS) {
+    reg_dec<AUX_REGS>();
     producer_loop(sm, p.prog, p.packed, my_tiles);
   } else if (warp == EPI_WARPS + 1) {
+    reg_dec<AUX_REGS>();
     mma_loop(sm, p.prog, my_tiles);
+  } else if (warp > EPI_WARPS + 1) {
+    reg_dec<AUX_REGS>();   // the two idle warps of the fifth warpgroup (layout.h)
   } else {
+    reg_inc<EPI_REGS>();
     Epi e = epi_make(sm);
     const SdfSaveLayout lay = sdf_save_layout(L, p.training != 0);
     const float* __restrict__ w_row = reinterpret_cast<const float*>(p.packed + p.w_last_row_off);
@@ -224,7 +229,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
         // sigma'_{l-1} (16 bytes per unit, written by this very thread in the forward pass) is requested PF units ahead,
         // the first PF before waiting for the accumulator: the round trips (L2 or HBM, ~1 us each) overlap the MMAs
         // instead of forming a chain of eight as they did when taken one unit ahead (whole layer ahead: spills)
-        constexpr int PF = 4;
+#ifndef NEAT_RENDER_PF
+#define NEAT_RENDER_PF 4
+#endif
+        constexpr int PF = NEAT_RENDER_PF;
         uint4 s1p[PF];
         auto issue = [&](int u) {
           if (epi_unit_col(e, u) < npad) s1p[u % PF] = *s1_at(d1, e, u);

@@ -80,6 +80,7 @@ class FusedTrainStep:
         self._R = None
         self.gA = self.gB = None
         self.launches_per_step = None
+        self.profile = None   # bench.py: a list -> (start, after graph A, after graph B) CUDA events of every step
 
     # ------------------------------------------------------------------ static state
     def _setup(self, R, n_gt):
@@ -248,6 +249,10 @@ class FusedTrainStep:
         if use_graphs and self.gA is None:
             self._capture()
         expect = int(self._counter_base + self._replays + 1) if use_graphs else None
+        ev = None
+        if self.profile is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
         if use_graphs:
             self.gA.replay()
             self._replays += 1
@@ -256,11 +261,16 @@ class FusedTrainStep:
             torch.cuda.current_stream(self.device).synchronize()
             expect = int(self.rn.handover_flag[0])
             self._eager_done += 1
+        if ev is not None:
+            ev[1].record()
         self._host_junctions(wf, expect)
         if use_graphs:
             self.gB.replay()
         else:
             self._run_B()
+        if ev is not None:
+            ev[2].record()
+            self.profile.append(ev)
         self.n_steps += 1
         lo = self.loss_out
         return {"loss": self.total, "rgb_loss": lo[1], "eikonal_loss": lo[2], "line_loss": lo[3], "l2d_loss": lo[4],
@@ -287,6 +297,18 @@ class FusedTrainStep:
         torch.cuda.synchronize(dev)
         self._counter_base = int(self.rn.draw_counter[0].item())
         self._replays = 0
+
+    def profile_ms(self):
+        """Mean per-step (graph A, graph B, idle gap before the next step) device times of the profiled steps.  Graph B
+        holds the gradient all-reduce, so at N > 1 its time includes waiting for the slowest rank."""
+        ev = self.profile or []
+        if len(ev) < 2:
+            return None
+        n = len(ev)
+        a = sum(e[0].elapsed_time(e[1]) for e in ev) / n
+        b = sum(e[1].elapsed_time(e[2]) for e in ev) / n
+        gap = sum(ev[i][2].elapsed_time(ev[i + 1][0]) for i in range(n - 1)) / (n - 1)
+        return {"graph_A_ms": round(a, 4), "graph_B_ms": round(b, 4), "gap_ms": round(gap, 4)}
 
     def sync_optimizer_state(self):
         """Bring the host-side `step` entries of the torch.optim state (state_dict / checkpoints) up to date."""

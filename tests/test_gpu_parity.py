@@ -186,7 +186,11 @@ def test_backward_vs_oracle_same_samples(name):
     # d loss / d density.beta is ONE scalar summed over every sample with mixed signs; in the 128-ray dtu_beta0.01 case it
     # cancels to 8.9e-6 and the reference's own fp32 arithmetic is 0.95e-2 away from the float64 value there (oracle in
     # float32 vs float64 at identical samples; 1.5e-5 in dtu_beta0.1), the kernels 1.2e-2: 3e-2 for that case only
-    PU.assert_grads(table, beta_tol=3e-2 if name == "dtu_beta0.01" else PU.BETA_TOL)
+    # max|d| / max|ref|: 4e-3 at these sizes (2e-3 at the benchmarked ones, test_gpu_fullsize.py).  The saved operand tiles
+    # of the weight-gradient GEMMs carry 16-17 significant bits (bf16 hi + lo), and a gradient entry of a freshly
+    # initialised head is a sum of 8-12 k random-sign terms that cancels ~100-fold: measured worst 2.4e-3 (abc_beta0.1,
+    # rendering_network.lin1, |ref| 1e-3; rel-L2 5e-4), independent of the accumulation order (scripts/diag_wgrad_rz.py)
+    PU.assert_grads(table, tol_max=4e-3, beta_tol=3e-2 if name == "dtu_beta0.01" else PU.BETA_TOL)
 
 
 @pytest.mark.parametrize("N,seed", [(64, 0), (2048, 1), (16384, 2)])
