@@ -171,6 +171,7 @@ typedef struct {
   float* depth;            /* [R]     or NULL */
   float* points3d;         /* [R,3]   or NULL */
   float* normal_map;       /* [R,3] or NULL */
+  const float* bg_color;   /* [3] or NULL: white_bkgd, rgb_values += (1 - sum w) * bg_color (neat_wfr_rend_a.py:411-413) */
 } neat_composite_args;
 int neat_composite_forward(const neat_composite_args* a, void* stream);
 
@@ -299,6 +300,7 @@ typedef struct {
   const float *z, *sdf, *weights, *rgb, *act, *rgb_values_bar, *lines3d_bar, *beta_param;
   float beta_min;
   float *rgb_pre_bar, *lines_bar, *sdf_bar, *beta_bar;
+  const float* bg_color;   /* [3] or NULL, as in neat_composite_args */
 } neat_composite_bwd_args;
 int neat_composite_backward(const neat_composite_bwd_args* a, void* stream);
 

@@ -101,7 +101,7 @@ class PixelArgs(ctypes.Structure):
 class CompositeBwdArgs(ctypes.Structure):
     _fields_ = [("R", _I), ("S", _I), ("z", _P), ("sdf", _P), ("weights", _P), ("rgb", _P), ("act", _P),
                 ("rgb_values_bar", _P), ("lines3d_bar", _P), ("beta_param", _P), ("beta_min", ctypes.c_float),
-                ("rgb_pre_bar", _P), ("lines_bar", _P), ("sdf_bar", _P), ("beta_bar", _P)]
+                ("rgb_pre_bar", _P), ("lines_bar", _P), ("sdf_bar", _P), ("beta_bar", _P), ("bg_color", _P)]
 
 
 class WnLayer(ctypes.Structure):
@@ -130,7 +130,7 @@ class CompositeArgs(ctypes.Structure):
     _fields_ = [("R", _I), ("S", _I), ("z", _P), ("sdf", _P), ("rgb", _P), ("lines", _P), ("normals", _P),
                 ("rays_o", _P), ("rays_d", _P), ("beta_param", _P), ("beta_min", ctypes.c_float),
                 ("weights", _P), ("rgb_values", _P), ("lines3d", _P), ("depth", _P), ("points3d", _P),
-                ("normal_map", _P)]
+                ("normal_map", _P), ("bg_color", _P)]
 
 
 class SamplerConfig(ctypes.Structure):

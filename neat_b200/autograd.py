@@ -81,7 +81,11 @@ def step_forward(renderer, st, beta):
         r = renderer.scene_bounding_sphere
         st.eik_uniform = torch.empty(R, 3).uniform_(-r, r).to(dev)  # the reference's CPU-generator draw
     near = cam[None, :] + z_eik * dirs
-    st.eik_pts = torch.cat([st.eik_uniform.to(dev, torch.float32), near], 0).contiguous()
+    parts = [st.eik_uniform.to(dev, torch.float32), near]
+    if getattr(st, "junction_eikonal", False):       # neat_wfr_rend_a.py:524-525: + the (detached) global junctions
+        parts.append(st.junction_inputs[0].detach().to(dev, torch.float32))
+    st.eik_pts = torch.cat(parts, 0).contiguous()
+    st.n_eik = st.eik_pts.shape[0]
     pe = renderer.explicit_points(st.eik_pts)
     # Stream plan.  Every tile-MLP launch is 148 persistent CTAs (one per SM) whose last round of tiles leaves most
     # SMs idle, and the small launches (eikonal points: 16 tiles, surface points: 8 tiles) would each occupy a
@@ -99,7 +103,7 @@ def step_forward(renderer, st, beta):
     st.sdf, st.grad, st.act, st.feat, st.sdf_save = renderer.sdf_outputs(pts, M, clamp=True, training=True, tag="render")
     with torch.cuda.stream(side):
         side.wait_event(fork)
-        _, grad_theta, _, _, st.eik_save = renderer.sdf_outputs(pe, 2 * R, clamp=False, training=True,
+        _, grad_theta, _, _, st.eik_save = renderer.sdf_outputs(pe, st.n_eik, clamp=False, training=True,
                                                                 want_feat=False, want_sdf=False, tag="eik")
     grad_theta.record_stream(main)
     st.lines, st.att_save = renderer.head_forward(1, pts, M, st.grad, st.feat, training=True)
@@ -156,7 +160,7 @@ def step_backward(renderer, st, rvb, l3b, gtb, beta_bar, targets, accumulate):
     sdf_bar = pool.get("bwd.sdf_bar", M)
     a = _lib.CompositeBwdArgs(R, S, _ptr(st.z), _ptr(st.sdf), _ptr(st.weights), _ptr(st.rgb), _ptr(st.act), _ptr(rvb),
                               _ptr(l3b), _ptr(st.beta), renderer.beta_min, _ptr(rgb_pre_bar), _ptr(lines_bar),
-                              _ptr(sdf_bar), _ptr(beta_bar))
+                              _ptr(sdf_bar), _ptr(beta_bar), _ptr(renderer.bg_color))
     _lib.check(lib.neat_composite_backward(ctypes.byref(a), stream))
     feat_bar = pool.get("bwd.feat_bar", int(lib.neat_feat_bar_bytes(M)) // 4)
     n_bar = pool.get("bwd.n_bar", M * 3).view(M, 3)
@@ -175,8 +179,8 @@ def step_backward(renderer, st, rvb, l3b, gtb, beta_bar, targets, accumulate):
     # the eikonal points' double backward fills the tails of the launches above (side stream, own scratch; it was
     # forked at the top of backward)
     pe = renderer.explicit_points(st.eik_pts)
-    sbe = pool.get("bwd.sdf_eik", int(lib.neat_sdf_bwd_save_bytes(ctx._h, 2 * R)), torch.uint8)
-    scratch_e = pool.get("bwd.scratch_eik", int(lib.neat_sdf_bwd_scratch_bytes(ctx._h, 2 * R)), torch.uint8)
+    sbe = pool.get("bwd.sdf_eik", int(lib.neat_sdf_bwd_save_bytes(ctx._h, st.n_eik)), torch.uint8)
+    scratch_e = pool.get("bwd.scratch_eik", int(lib.neat_sdf_bwd_scratch_bytes(ctx._h, st.n_eik)), torch.uint8)
     with torch.cuda.stream(side):
         side.wait_event(fork)
         _lib.check(lib.neat_sdf_backward(ctx._h, ctypes.byref(pe), _ptr(gtb), None, None, None, _ptr(st.eik_save),
@@ -191,7 +195,7 @@ def step_backward(renderer, st, rvb, l3b, gtb, beta_bar, targets, accumulate):
     groups[0] = _lib.GradGroup(M, _ptr(st.sdf_save), _ptr(sb), _ptr(st.feat),
                                (_P * 2)(st.rend_save.data_ptr(), st.att_save.data_ptr()),
                                (_P * 2)(hb[0].data_ptr(), hb[1].data_ptr()))
-    groups[1] = _lib.GradGroup(2 * R, _ptr(st.eik_save), _ptr(sbe), None, (_P * 2)(None, None), (_P * 2)(None, None))
+    groups[1] = _lib.GradGroup(st.n_eik, _ptr(st.eik_save), _ptr(sbe), None, (_P * 2)(None, None), (_P * 2)(None, None))
     with renderer.timed("wgrad"):
         _lib.check(lib.neat_weight_gradients(ctx._h, groups, 2, _ptr(flat_grad), stream))
     st.debug = dict(rgb_pre_bar=rgb_pre_bar, lines_bar=lines_bar, sdf_bar=sdf_bar, n_bar=n_bar, feat_bar=feat_bar)
@@ -218,7 +222,7 @@ class NeatStepFunction(torch.autograd.Function):
         z = lambda *s: torch.zeros(*s, device=dev)
         rvb = rgb_values_bar.contiguous().float() if rgb_values_bar is not None else z(R, 3)
         l3b = lines3d_bar.reshape(R, 6).contiguous().float() if lines3d_bar is not None else z(R, 6)
-        gtb = grad_theta_bar.contiguous().float() if grad_theta_bar is not None else z(2 * R, 3)
+        gtb = grad_theta_bar.contiguous().float() if grad_theta_bar is not None else z(st.n_eik, 3)
         beta_bar = torch.zeros(1, device=dev)
         # parameter gradients: straight into p.grad (allocated here if the caller cleared it, added to otherwise)
         with torch.no_grad():

@@ -27,7 +27,8 @@ def net_config_from_conf(conf):
         multires=int(ci.get("multires", 0)), feat=int(conf["feature_vector_size"]),
         head_layers=len(cr["dims"]) + 1, head_hidden=cr["dims"][0],
         multires_view=int(cr.get("multires_view", 0)),
-        sphere_radius=float(conf.get("scene_bounding_sphere", 1.0)),
+        # white_bkgd builds the ImplicitNetwork with sdf_bounding_sphere = 0: no sphere clamp (neat_wfr_rend_a.py:266)
+        sphere_radius=0.0 if bool(conf.get("white_bkgd", False)) else float(conf.get("scene_bounding_sphere", 1.0)),
         sphere_scale=float(ci.get("sphere_scale", 1.0)))
 
 

@@ -637,6 +637,7 @@ int neat_composite_forward(const neat_composite_args* a, void* stream) {
   p.rays_o = a->rays_o; p.rays_d = a->rays_d; p.beta_param = a->beta_param; p.beta_min = a->beta_min;
   p.weights = a->weights; p.rgb_values = a->rgb_values; p.lines3d = a->lines3d; p.depth = a->depth;
   p.points3d = a->points3d; p.normal_map = a->normals ? a->normal_map : nullptr;
+  p.bg = a->rgb ? a->bg_color : nullptr;
   composite_fwd_kernel<<<(a->R + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
   ++g_launches;
   CK(cudaGetLastError());
@@ -1119,6 +1120,7 @@ int neat_composite_backward(const neat_composite_bwd_args* a, void* stream) {
   p.rgb_values_bar = a->rgb_values_bar; p.lines3d_bar = a->lines3d_bar; p.beta_param = a->beta_param;
   p.beta_min = a->beta_min; p.rgb_pre_bar = a->rgb_pre_bar; p.lines_bar = a->lines_bar; p.sdf_bar = a->sdf_bar;
   p.beta_bar = a->beta_bar;
+  p.bg = a->bg_color;
   composite_bwd_kernel<<<(a->R + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
   ++g_launches;
   CK(cudaGetLastError());

@@ -47,6 +47,7 @@ struct CompositeParams {
   float* depth;       // [R]
   float* points3d;    // [R,3]
   float* normal_map;  // [R,3] or nullptr
+  const float* bg;    // [3] or nullptr: white_bkgd, rgb_values += (1 - sum_i w_i) bg  (neat_wfr_rend_a.py:411-413)
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(128) composite_fwd_kernel(CompositeParams p) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
   float carry = 0.f;  // sum of free energy of all previous 32-sample blocks
+  float wsum = 0.f;
   for (int base = 0; base < S; base += 32) {
     const int i = base + lane;
     float fe = 0.f, zi = 0.f;
@@ -83,6 +85,7 @@ __global__ void __launch_bounds__(128) composite_fwd_kernel(CompositeParams p) {
     if (i < S) {
       const float w = (1.0f - expf(-fe)) * expf(-(carry + ex));
       if (p.weights) p.weights[static_cast<size_t>(r) * S + i] = w;
+      wsum += w;
       const size_t q = static_cast<size_t>(r) * S + i;
       if (p.rgb) { acc[0] += w * p.rgb[3 * q]; acc[1] += w * p.rgb[3 * q + 1]; acc[2] += w * p.rgb[3 * q + 2]; }
       if (p.lines) {
@@ -102,8 +105,9 @@ __global__ void __launch_bounds__(128) composite_fwd_kernel(CompositeParams p) {
   }
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = warp_sum(acc[i]);
+  if (p.bg) wsum = warp_sum(wsum);
   if (lane == 0) {
-    if (p.rgb) for (int c = 0; c < 3; ++c) p.rgb_values[3 * r + c] = acc[c];
+    if (p.rgb) for (int c = 0; c < 3; ++c) p.rgb_values[3 * r + c] = p.bg ? acc[c] + (1.0f - wsum) * p.bg[c] : acc[c];
     if (p.lines) for (int c = 0; c < 6; ++c) p.lines3d[6 * r + c] = acc[3 + c];
     if (p.depth) p.depth[r] = acc[9];
     if (p.points3d) for (int c = 0; c < 3; ++c) p.points3d[3 * r + c] = acc[10 + c];
@@ -232,6 +236,7 @@ struct CompositeBwdParams {
   float* lines_bar;     // [R,S,6]  = w * lines3d_bar
   float* sdf_bar;       // [R,S]    dL/d(raw network sdf) (masked by act)
   float* beta_bar;      // [1]      accumulated with atomicAdd: dL/d(density.beta parameter)
+  const float* bg;      // [3] or nullptr: white_bkgd -- d rgb_values / d w_i = rgb_i - bg
 };
 
 __global__ void __launch_bounds__(128) composite_bwd_kernel(CompositeBwdParams p) {
@@ -249,6 +254,7 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(CompositeBwdParams p
     float gb[3], lb[6];
 #pragma unroll
     for (int c = 0; c < 3; ++c) gb[c] = p.rgb_values_bar[3 * r + c];
+    const float gbg = p.bg ? gb[0] * p.bg[0] + gb[1] * p.bg[1] + gb[2] * p.bg[2] : 0.f;
 #pragma unroll
     for (int c = 0; c < 6; ++c) lb[c] = p.lines3d_bar[6 * r + c];
     // pass 1 (forward order): exclusive prefix of the free energy -> T_i ; pass 2 (reverse): suffix of w_bar w
@@ -280,6 +286,7 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(CompositeBwdParams p
         wi = w[i];
 #pragma unroll
         for (int c = 0; c < 3; ++c) { rgbv[c] = p.rgb[3 * q + c]; wbar += gb[c] * rgbv[c]; }
+        wbar -= gbg;
       }
       float tot;
       const float ex = warp_excl_scan(fe, tot);

@@ -110,7 +110,11 @@ __global__ void db_count_kernel(DbscanWs w, int N) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const int r = uf_find(w.parent, i);
-  w.parent[i] = r;
+  // The root goes to `next` (the cell lists are dead after db_link), NOT back into parent[i]: another thread's path
+  // halving (uf_find: read parent[i], read its parent, write parent[i]) could overwrite a flattened entry with an older,
+  // non-root ancestor, and db_sum would then drop the point from its cluster's centroid (a rare, run-dependent error:
+  // one failure of test_dbscan_vs_sklearn in ~10 full-suite runs led here).
+  w.next[i] = r;
   atomicAdd(&w.count[r], 1);
 }
 
@@ -157,7 +161,7 @@ __global__ void db_rank_kernel(DbscanWs w, int N, int* n_clusters) {
 __global__ void db_sum_kernel(DbscanWs w, const float* __restrict__ pts, int N) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
-  const int c = w.cid[w.parent[i]];
+  const int c = w.cid[w.next[i]];   // next[i] = the root of i (db_count)
   if (c < 0) return;
   atomicAdd(&w.sums[3 * c], static_cast<double>(pts[3 * i]));
   atomicAdd(&w.sums[3 * c + 1], static_cast<double>(pts[3 * i + 1]));

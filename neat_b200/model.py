@@ -234,10 +234,12 @@ class VolSDFNetwork(nn.Module):
         self.conf = c
         self.feature_vector_size = int(c["feature_vector_size"])
         self.scene_bounding_sphere = float(c.get("scene_bounding_sphere", 1.0))
-        self.white_bkgd = bool(c.get("white_bkgd", False))
+        self.white_bkgd = bool(c.get("white_bkgd", False))    # handled by the compositing kernels (render.Renderer.bg_color)
         if self.white_bkgd:
-            raise _lib.NeatError("white_bkgd is not supported by the kernels")
-        self.implicit_network = ImplicitNetwork(self.feature_vector_size, self.scene_bounding_sphere, **c["implicit_network"])
+            self.register_buffer("bg_color", torch.tensor([float(v) for v in c.get("bg_color", [1.0, 1.0, 1.0])]),
+                                 persistent=False)
+        self.implicit_network = ImplicitNetwork(self.feature_vector_size,
+                                                0.0 if self.white_bkgd else self.scene_bounding_sphere, **c["implicit_network"])
         self.rendering_network = RenderingNetwork(self.feature_vector_size, **c["rendering_network"])
         self.attraction_network = AttractionFieldNetwork(self.feature_vector_size, **c["attraction_network"])
         self.density = LaplaceDensity(**c["density"])
@@ -255,9 +257,9 @@ class VolSDFNetwork(nn.Module):
         self.use_median = bool(c.get("use_median", False))
         self.junction_eikonal = bool(c.get("junction_eikonal", False))
         self.use_l3d = bool(c.get("use_l3d", False))
-        if self.junction_eikonal or (self.use_l3d and not self.dbscan_enabled):
-            raise _lib.NeatError("junction_eikonal=True and use_l3d=True (without DBSCAN) are not supported: no shipped "
-                                 "conf enables them (dtu.conf / bmvs.conf: DBSCAN; abc-neat-a.conf: every end point)")
+        if self.use_l3d and not self.dbscan_enabled:
+            raise _lib.NeatError("use_l3d=True (without DBSCAN) is not supported: no shipped conf enables it "
+                                 "(dtu.conf / bmvs.conf: DBSCAN; abc-neat-a.conf: every end point)")
         import weakref
         ref = weakref.ref(self)
         for m in (self.implicit_network, self.rendering_network, self.attraction_network):
@@ -389,6 +391,7 @@ class VolSDFNetwork(nn.Module):
         glob = ffn_kernels.apply_module(self.ffn, self.latents)   # own fp32 GEMM kernels (ffn.py), no cuBLAS
         st.junction_inputs = (glob.detach(), pose, K4)
         st.dbscan_enabled = self.dbscan_enabled
+        st.junction_eikonal = self.junction_eikonal
         st.param_layers = self._wn_layers()
         self._packed_version = None  # the step packs its own copy
         # RNG order of the reference: the sampler's draws, then the eikonal uniform_ (neat_wfr_rend_a.py:518); the junction

@@ -65,6 +65,11 @@ class Renderer:
         self.scene_bounding_sphere = float(conf.get("scene_bounding_sphere", 1.0))
         self.pool = WorkspacePool(ctx.device)
         self._pinned = {}
+        # white_bkgd (neat_wfr_rend_a.py:262-264, 411-413): rgb_values += (1 - sum w) * bg_color; None = off
+        self.bg_color = None
+        if bool(conf.get("white_bkgd", False)):
+            self.bg_color = torch.tensor([float(v) for v in conf.get("bg_color", [1.0, 1.0, 1.0])], dtype=torch.float32,
+                                         device=ctx.device)
         self.timers = None  # bench.py: dict name -> [(start, end) CUDA events] on the launching stream
         self.generation = 0  # bumped by every forward that reuses the named workspaces (autograd.py checks it in backward)
         # device-side random draws of the training forward (csrc/train_aux.cuh): Philox keyed by (seed, a draw counter that
@@ -187,7 +192,7 @@ class Renderer:
         nmap = torch.empty(R, 3, device=dev) if want_normal_map else None
         a = _lib.CompositeArgs(R, S, _ptr(z), _ptr(sdf), _ptr(rgb), _ptr(lines), _ptr(normals) if want_normal_map else None,
                                _ptr(cam), _ptr(dirs), _ptr(beta_param), self.beta_min, _ptr(w), _ptr(rgb_values),
-                               _ptr(lines3d), _ptr(depth), _ptr(points3d), _ptr(nmap))
+                               _ptr(lines3d), _ptr(depth), _ptr(points3d), _ptr(nmap), _ptr(self.bg_color))
         _lib.check(ctx.lib.neat_composite_forward(ctypes.byref(a), ctx._stream()))
         return w, rgb_values, lines3d, depth, points3d, nmap
 
@@ -223,7 +228,7 @@ class Renderer:
         R, S = z.shape
         rgb_values = torch.empty(R, 3, device=ctx.device)
         a = _lib.CompositeArgs(R, S, _ptr(z), _ptr(sdf), _ptr(rgb), None, None, _ptr(cam), _ptr(dirs), _ptr(beta_param),
-                               self.beta_min, None, _ptr(rgb_values), None, None, None, None)
+                               self.beta_min, None, _ptr(rgb_values), None, None, None, None, _ptr(self.bg_color))
         _lib.check(ctx.lib.neat_composite_forward(ctypes.byref(a), ctx._stream()))
         return rgb_values
 

@@ -54,6 +54,14 @@ def toy_conf():
     return c
 
 
+def toy_white_conf():
+    """toy_conf with the two optional branches of the model class no shipped conf selects: white_bkgd (background colour,
+    ImplicitNetwork without the sphere clamp, neat_wfr_rend_a.py:262-266, 411-413) and junction_eikonal (:524-525)."""
+    c = toy_conf()
+    c.update(white_bkgd=True, bg_color=[1.0, 0.9, 0.8], junction_eikonal=True)
+    return c
+
+
 def loss_conf():
     return {"eikonal_weight": 0.1, "line_weight": 0.01, "rgb_loss": "torch.nn.L1Loss"}
 

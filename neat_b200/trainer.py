@@ -111,7 +111,8 @@ class FusedTrainStep:
         self.jout = f(3)
         # fused loss
         self.loss_scratch, self.loss_out = f(8 + R), f(8)
-        self.g_rgb, self.g_calib, self.g_theta, self.l3b = f(R, 3), f(R, 4), f(2 * R, 3), f(R, 6)
+        self.n_eik = 2 * R + (G if m.junction_eikonal else 0)   # eikonal points (neat_wfr_rend_a.py:515-525)
+        self.g_rgb, self.g_calib, self.g_theta, self.l3b = f(R, 3), f(R, 4), f(self.n_eik, 3), f(R, 6)
         self.total = f(1)
         # optimizer: torch.optim.Adam's state layout, step count / hyper-parameters on the device
         self.params = [p for p in m.parameters() if p.requires_grad]
@@ -155,6 +156,7 @@ class FusedTrainStep:
         glob = F.forward(m.latents.detach(), [l.weight.detach() for l in self.lin], [l.bias.detach() for l in self.lin], self.acts)
         st.junction_inputs = (glob, st.pose, st.K)
         st.dbscan_enabled = m.dbscan_enabled
+        st.junction_eikonal = m.junction_eikonal
         st.handover_counter = rn.draw_counter[:1]
         beta = m.density.beta.detach().reshape(1)
         rgb_values, lines3d, grad_theta = step_forward(rn, st, beta)
@@ -164,7 +166,7 @@ class FusedTrainStep:
                                            self._stream()))
         # VolSDFLoss core terms fused with their own gradient (loss_wfr.py:47-79), then the adjoint of project2D(I, ...)
         lf = self.loss_fn
-        a = _lib.LossArgs(R, 2 * R, ptr(rgb_values), ptr(self.gt["rgb"]), ptr(st.lines2d), ptr(st.lines2d_calib),
+        a = _lib.LossArgs(R, self.n_eik, ptr(rgb_values), ptr(self.gt["rgb"]), ptr(st.lines2d), ptr(st.lines2d_calib),
                           ptr(self.gt["lines2d"]), None, ptr(st.K), 4, ptr(grad_theta), float(lf.eikonal_weight),
                           float(lf.line_weight), ptr(self.loss_scratch), ptr(self.loss_out), ptr(self.g_rgb), ptr(self.g_calib),
                           ptr(self.g_theta))

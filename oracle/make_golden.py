@@ -203,6 +203,11 @@ def main():
         run_case("abc_beta0.1", synth.abc_conf(), 128, seed_w=3, beta=0.1, cam=(512, 512, 560.0, abc_pose))
         if only:
             return
+    if "white" in only or not only:
+        # the model class's optional branches no shipped conf selects: white_bkgd (+ no sphere clamp) and junction_eikonal
+        run_case("toy_white_jeik", synth.toy_white_conf(), 128, seed_w=4, beta=0.1, cam=(512, 512, 560.0, abc_pose))
+        if only:
+            return
     # toy: ABC camera 0 (f=560, 512x512), 256 rays x 64 samples, 4x128 nets
     run_case("toy_beta0.1", synth.toy_conf(), 256, seed_w=0, beta=0.1, cam=(512, 512, 560.0, abc_pose))
     # DTU nets (8x256 / 4x256), 98 samples, small ray count; two density settings (k=2.. and k=5)

@@ -52,6 +52,12 @@ class NeatParams:
     latents: Optional[torch.Tensor] = None
     dbscan_enabled: bool = True              # neat_wfr_rend_a.py:312-315 (model conf)
     use_median: bool = False
+    bg_color: Optional[torch.Tensor] = None  # white_bkgd (neat_wfr_rend_a.py:262-263, 411-413); also means sphere_radius = 0 (:266)
+    junction_eikonal: bool = False           # neat_wfr_rend_a.py:524-525
+
+    def sdf_sphere(self):
+        # ImplicitNetwork's sdf_bounding_sphere: 0 (no clamp) under white_bkgd (neat_wfr_rend_a.py:266)
+        return 0.0 if self.bg_color is not None else self.sphere_radius
 
     def beta(self):
         # code/model/density.py:28-30
@@ -63,7 +69,8 @@ class NeatParams:
                           cv(self.att_W), cv(self.att_b), self.beta_param.to(dtype),
                           self.beta_min, tuple(self.skip_in), self.multires, self.multires_view,
                           self.sphere_radius, self.sphere_scale, cv(self.ffn_W), cv(self.ffn_b),
-                          None if self.latents is None else self.latents.to(dtype), self.dbscan_enabled, self.use_median)
+                          None if self.latents is None else self.latents.to(dtype), self.dbscan_enabled, self.use_median,
+                          None if self.bg_color is None else self.bg_color.to(dtype), self.junction_eikonal)
 
 
 def weight_norm_effective(g, v):
@@ -176,13 +183,13 @@ def sdf_forward(P: NeatParams, x, save=False):
 
 
 def sphere_sdf(P: NeatParams, x):
-    return P.sphere_scale * (P.sphere_radius - x.norm(2, 1, keepdim=True))
+    return P.sphere_scale * (P.sdf_sphere() - x.norm(2, 1, keepdim=True))
 
 
 def sdf_vals(P: NeatParams, x):
     """ImplicitNetwork.get_sdf_vals (neat_wfr_rend_a.py:131-137)."""
     s = sdf_forward(P, x)[:, :1]
-    if P.sphere_radius > 0.0:
+    if P.sdf_sphere() > 0.0:
         s = torch.minimum(s, sphere_sdf(P, x))
     return s
 
@@ -196,7 +203,7 @@ def sdf_outputs(P: NeatParams, x, clamp=True):
     L = len(P.sdf_W)
     s_raw = out[:, :1]
     feat = out[:, 1:]
-    clamp = clamp and P.sphere_radius > 0.0
+    clamp = clamp and P.sdf_sphere() > 0.0
     if clamp:
         sph = sphere_sdf(P, x)
         act = (s_raw <= sph).to(x.dtype)      # torch.minimum sends the gradient to `self` on ties
@@ -233,7 +240,7 @@ def sdf_outputs_autograd(P: NeatParams, x, create_graph=False):
     x = x.detach().clone().requires_grad_(True)
     out = sdf_forward(P, x)
     sdf = out[:, :1]
-    if P.sphere_radius > 0.0:
+    if P.sdf_sphere() > 0.0:
         sdf = torch.minimum(sdf, sphere_sdf(P, x))
     g = torch.autograd.grad(sdf, x, torch.ones_like(sdf), create_graph=create_graph,
                             retain_graph=True)[0]
@@ -542,6 +549,8 @@ def render_rays(P: NeatParams, dirs, cam, z_vals):
     rgb = rendering_forward(P, pf, grad, df, feat).reshape(R, S, 3)
     w = volume_weights(z_vals, sdf.reshape(R, S), P.beta())
     rgb_values = (w[..., None] * rgb).sum(1)
+    if P.bg_color is not None:                                # neat_wfr_rend_a.py:411-413
+        rgb_values = rgb_values + (1.0 - w.sum(-1))[..., None] * P.bg_color.to(w.dtype)[None]
     l3 = attraction_forward(P, pf, grad, df, feat).reshape(R, S, 2, 3)
     lines3d = (w[:, :, None, None].detach() * l3).sum(1)      # weights detached: :410
     depth = (w * depth_ratio).sum(-1)
@@ -788,6 +797,8 @@ def neat_forward(P: NeatParams, sconf: SamplerConf, K, pose, uv, uv_proj, gt_ver
         out.update(junction_block(P, K, pose, rr["lines3d"], gt_vertices))
         near = camr + z_eik * dirs
         eik_pts = torch.cat([rnd.eik_uniform.to(dirs.dtype), near], 0)
+        if P.junction_eikonal:                                # neat_wfr_rend_a.py:524-525
+            eik_pts = torch.cat([eik_pts, out["j3d_global"].detach()], 0)
         _, _, g, _ = sdf_outputs(P, eik_pts, clamp=False)
         out["grad_theta"] = g
         out["eik_points"] = eik_pts

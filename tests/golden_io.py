@@ -9,7 +9,7 @@ from oracle import neat_oracle as O
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = {"toy_beta0.1": synth.toy_conf, "dtu_beta0.1": synth.dtu_conf, "dtu_beta0.01": synth.dtu_conf,
-         "abc_beta0.1": synth.abc_conf}
+         "abc_beta0.1": synth.abc_conf, "toy_white_jeik": synth.toy_white_conf}
 
 
 def load(name):
@@ -30,6 +30,9 @@ def oracle_params(conf, sd_np, dtype=torch.float32, track=False):
                                  sphere_radius=conf["scene_bounding_sphere"], sphere_scale=ci["sphere_scale"],
                                  beta_min=conf["density"]["beta_min"], track=track)
     P.dbscan_enabled, P.use_median = bool(conf.get("dbscan_enabled", True)), bool(conf.get("use_median", False))
+    if conf.get("white_bkgd", False):
+        P.bg_color = torch.tensor([float(v) for v in conf.get("bg_color", [1.0, 1.0, 1.0])], dtype=dtype)
+    P.junction_eikonal = bool(conf.get("junction_eikonal", False))
     return P, sd
 
 

@@ -61,7 +61,7 @@ def gpu_step(model, b, seed=7, keep_bars=False):
 def step_samples(st):
     """(z_vals [R,S], z_eik [R,1]) the GPU step used, as CPU tensors (the eikonal depth is recovered from the points)."""
     R = st.R
-    z_eik = ((st.eik_pts[R:].cpu() - st.cam.cpu()[None]) * st.dirs.cpu()).sum(1, keepdim=True)
+    z_eik = ((st.eik_pts[R:2 * R].cpu() - st.cam.cpu()[None]) * st.dirs.cpu()).sum(1, keepdim=True)
     return st.z.cpu(), z_eik
 
 
@@ -108,10 +108,15 @@ def grad_errors(named_grads, ref_grads):
     return table
 
 
-def assert_grads(table, tol_l2=GRAD_TOL_L2, tol_max=GRAD_TOL_MAX, beta_tol=BETA_TOL):
+def assert_grads(table, tol_l2=GRAD_TOL_L2, tol_max=GRAD_TOL_MAX, beta_tol=BETA_TOL, ref32=None):
+    """ref32: the same table for the float32 oracle (the reference's own arithmetic) against the float64 one.  Where a
+    tensor's float32 gradient is itself further from the float64 value than half the tolerance (ill-conditioned sums, e.g.
+    the background term of white_bkgd, whose exact weight gradient cancels to zero), the bound is twice that distance."""
     bad = []
     for n, (l2, mx, nrm) in table.items():
         t2, tm = (beta_tol, beta_tol) if n == "density.beta" else (tol_l2, tol_max)
+        if ref32 is not None and n in ref32:
+            t2, tm = max(t2, 2.0 * ref32[n][0]), max(tm, 2.0 * ref32[n][1])
         if not (l2 <= t2 and mx <= tm):
             bad.append((n, l2, mx, nrm))
     assert not bad, "gradient parity: " + "; ".join("%s rel_l2 %.2e rel_max %.2e (|ref| %.2e)" % x for x in bad)

@@ -168,15 +168,25 @@ def test_backward_vs_oracle_same_samples(name):
     dt = torch.float64
     P, leaves = G.oracle_params(conf, sd_np, dtype=dt, track=True)
     R = st.R
-    z_eik = ((st.eik_pts[R:].cpu() - st.cam.cpu()[None]) * st.dirs.cpu()).sum(1, keepdim=True)
+    z_eik = ((st.eik_pts[R:2 * R].cpu() - st.cam.cpu()[None]) * st.dirs.cpu()).sum(1, keepdim=True)
     rnd = G.train_randoms(g)
     rnd = O.TrainRandoms(rnd.sampler, rnd.eik_uniform.to(dt))
     D = lambda a: T(a).to(dt)
     oo = O.neat_forward(P, G.sampler_conf(conf), D(g["in_intrinsics"][0]), D(g["in_pose"][0]), D(g["in_uv"][0]),
                         D(g["in_uv_proj"][0]), gt_vertices=D(g["wf_vertices"]), training=True, rnd=rnd,
                         samples=(st.z.cpu().to(dt), z_eik.to(dt)))
+    # 1e-4 of the float64 value -- or, where the reference's own float32 arithmetic is further than 0.5e-4 from it, twice
+    # that distance: without the sphere clamp (toy_white_jeik) the composited end points of the float32 oracle are 2.0e-4
+    # (lines3d), 2.2e-4 (points3d) and 1.2e-4 (depth) away from the float64 ones at identical samples; < 2e-6 elsewhere
+    r32 = G.train_randoms(g)
+    P32, leaves32 = G.oracle_params(conf, sd_np, track=True)
+    o32 = O.neat_forward(P32, G.sampler_conf(conf), T(g["in_intrinsics"][0]), T(g["in_pose"][0]), T(g["in_uv"][0]),
+                         T(g["in_uv_proj"][0]), gt_vertices=T(g["wf_vertices"]), training=True, rnd=r32,
+                         samples=(st.z.cpu(), z_eik))
+    O.neat_loss(o32, T(g["in_rgb"][0]), T(g["in_lines2d"][0]), o32["K"])["loss"].backward()
     for k in ("rgb_values", "lines3d", "lines2d_calib", "grad_theta", "points3d", "depth"):
-        assert G.rel_err(out[k].detach().cpu(), oo[k].detach()) < 1e-4, k
+        tol = max(1e-4, 2.0 * G.rel_err(o32[k].detach(), oo[k].detach()))
+        assert G.rel_err(out[k].detach().cpu(), oo[k].detach()) < tol, (k, tol)
     ol = O.neat_loss(oo, D(g["in_rgb"][0]), D(g["in_lines2d"][0]), oo["K"])
     ol["loss"].backward()
     for k in ("loss", "rgb_loss", "eikonal_loss", "line_loss", "j3d_loss", "j2d_loss"):
@@ -185,12 +195,16 @@ def test_backward_vs_oracle_same_samples(name):
     assert len(table) >= 50
     # d loss / d density.beta is ONE scalar summed over every sample with mixed signs; in the 128-ray dtu_beta0.01 case it
     # cancels to 8.9e-6 and the reference's own fp32 arithmetic is 0.95e-2 away from the float64 value there (oracle in
-    # float32 vs float64 at identical samples; 1.5e-5 in dtu_beta0.1), the kernels 1.2e-2: 3e-2 for that case only
+    # float32 vs float64 at identical samples; 1.5e-5 in dtu_beta0.1), the kernels 1.2e-2; under white_bkgd the exact
+    # gradient of the background term is zero and float32 noise dominates: float32 oracle 4.5, kernels 0.42 on beta,
+    # 1.5e-2 / 2.0e-2 on the last layer's bias.  ref32 (parity_util.assert_grads) turns that into the bound.
     # max|d| / max|ref|: 4e-3 at these sizes (2e-3 at the benchmarked ones, test_gpu_fullsize.py).  The saved operand tiles
     # of the weight-gradient GEMMs carry 16-17 significant bits (bf16 hi + lo), and a gradient entry of a freshly
     # initialised head is a sum of 8-12 k random-sign terms that cancels ~100-fold: measured worst 2.4e-3 (abc_beta0.1,
     # rendering_network.lin1, |ref| 1e-3; rel-L2 5e-4), independent of the accumulation order (scripts/diag_wgrad_rz.py)
-    PU.assert_grads(table, tol_max=4e-3, beta_tol=3e-2 if name == "dtu_beta0.01" else PU.BETA_TOL)
+    ref32 = PU.grad_errors({n: v.grad for n, v in leaves32.items()}, {n: v.grad for n, v in leaves.items()})
+    # (same cancellation in toy_white_jeik's last SDF layer: weight_g of the sdf row 1.4e-3 here, float32 oracle 1e-4)
+    PU.assert_grads(table, tol_l2=3e-3 if name == "toy_white_jeik" else PU.GRAD_TOL_L2, tol_max=4e-3, ref32=ref32)
 
 
 @pytest.mark.parametrize("N,seed", [(64, 0), (2048, 1), (16384, 2)])
@@ -552,7 +566,7 @@ def test_ragged_ray_counts_forward_backward_vs_oracle(conf_name, R):
     st = model.last_step
     assert st.z.shape[0] == R
     P, leaves = G.oracle_params(conf, sd_np, track=True)
-    z_eik = ((st.eik_pts[R:].cpu() - st.cam.cpu()[None]) * st.dirs.cpu()).sum(1, keepdim=True)
+    z_eik = ((st.eik_pts[R:2 * R].cpu() - st.cam.cpu()[None]) * st.dirs.cpu()).sum(1, keepdim=True)
     S = st.z.shape[1]
     sc = G.sampler_conf(conf)
     dummy = O.SamplerRandoms(torch.zeros(R, sc.N_samples_eval), torch.zeros(R, sc.N_samples),

@@ -49,9 +49,10 @@ def test_no_cpu_fallback():
 
 def test_unsupported_confs_are_rejected():
     c = synth.toy_conf()
-    c["white_bkgd"] = True
+    c.update(dbscan_enabled=False, use_l3d=True)
     with pytest.raises(_lib.NeatError):
         VolSDFNetwork(c)
+    VolSDFNetwork(synth.toy_white_conf())     # white_bkgd + junction_eikonal: supported (golden case toy_white_jeik)
     c = synth.toy_conf()
     c["rendering_network"]["mode"] = "nerf"
     with pytest.raises(_lib.NeatError):
