@@ -361,6 +361,51 @@ def eval_config(rays, beta, steps, warmup, rank, world, dev, lib):
     return r
 
 
+def fast_mode_config(rays, rank, world, dev, steps=10):
+    """BASELINE configs[2] says "bf16 tensor-core MLPs": the opt-in one-MMA-per-MAC mode (neat_set_precision(ctx, 1), hi
+    planes only) at 8192 rays/GPU, with its MEASURED distance from the x3 parity mode on the first step (same weights,
+    same draws).  Informational: it misses north_star's 1e-4 bound, so nothing else in this file uses it."""
+    import torch
+    import torch.distributed as dist
+    from neat_b200 import _lib, synth
+    from neat_b200 import trainer as TR
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    outs, ms = {}, {}
+    for fast in (0, 1):
+        ts = TR.FusedTrainStep(synth.dtu_conf(), device=dev, seed=42, beta=0.1)
+        inp, gt = TR.to_device(TR.host_batch(rays, seed=1 + rank), dev)
+        rn = ts.model._get_renderer()
+        _lib.check(rn.ctx.lib.neat_set_precision(rn.ctx._h, fast))
+        ts.model.seed_draws(7)
+        ts.step(inp, gt)
+        torch.cuda.synchronize()
+        outs[fast] = {k: ts.out[k].detach().float().cpu() for k in ("rgb_values", "lines3d", "grad_theta")}
+        if fast:
+            for _ in range(4):
+                ts.step(inp, gt)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                ts.step(inp, gt)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        del ts, rn
+        _release()
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+    return {"name": "configs[2] in the one-MMA mode (\"bf16 tensor-core MLPs\": hi planes only, neat_set_precision(ctx, 1)): "
+                    "8192 rays/GPU, beta=0.1; NOT the parity mode",
+            "rays_per_gpu": rays, "beta": 0.1, "steps": steps, "warmup": 5, "value": world * rays * steps / (ms * 1e-3),
+            "unit": "rays/s", "ms_per_step": ms / steps,
+            "measured_distance_from_x3_first_step": {k: float("%.3g" % rel(outs[1][k], outs[0][k])) for k in outs[0]}}
+
+
 def dp_check(rank, world, dev):
     """N > 1: one step through the real plugin; the all-reduced flat bucket times 1/world must equal the mean of the
     per-rank gradients (gathered before the reduction)."""
@@ -484,6 +529,10 @@ def main():
         e = eval_config(65536, 0.01, 5, 3, rank, world, dev, lib)
         e["name"] = "configs[4]: eval-mode forward in 65536-ray chunks per GPU (full 1600x1200 image = 30 chunks), beta=0.01"
         extras.append(e)
+        try:
+            extras.append(fast_mode_config(8192, rank, world, dev))
+        except Exception as ex:  # informational entry: never lose the line to it
+            extras.append({"name": "configs[2] in the one-MMA mode", "failed": "%s: %s" % (type(ex).__name__, ex)})
 
     if rank == 0:
         pk, pk_kind = peaks()

@@ -10,8 +10,11 @@ for tool in racecheck synccheck memcheck; do
   grep -E "ERROR SUMMARY|RACECHECK SUMMARY|train step|eval forward|exit" gpurun_out/sanitizer_$tool.log | tail -5
 done
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python scripts/profile_step.py 1024 4 > gpurun_out/ncu_list.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"sdf_query|sdf_render|sdf_bwd|head_fwd|head_bwd|wgrad" --launch-skip 30 --launch-count 14 -o gpurun_out/step_full -f python scripts/profile_step.py 1024 4 > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"sdf_query|sdf_render|sdf_bwd|head_fwd|head_bwd|wgrad" --launch-skip 30 --launch-count 15 -o gpurun_out/step_full -f python scripts/profile_step.py 1024 4 > gpurun_out/ncu_full.log 2>&1
 timeout 600 ncu --metrics $M --clock-control none -k regex:"sampler_|composite_|db_|loss_|camera_rays|line_geometry|pose_inverse|weight_norm|adam_|train_draws|junction_|gemm_f32|colsum|pack_|project_" --csv --log-file gpurun_out/perray_metrics.csv python scripts/profile_step.py 1024 3 0.01 > gpurun_out/ncu_perray.log 2>&1
 timeout 600 ncu --metrics $M --clock-control none -k regex:"encodels|point_line_attraction|mask_|sample_pixels|line_vote|line_visibility|line_junction" --csv --log-file gpurun_out/aux_metrics.csv python scripts/profile_aux.py > gpurun_out/ncu_aux.log 2>&1
 tail -2 gpurun_out/ncu_aux.log
 ls -la gpurun_out/*.ncu-rep gpurun_out/*.csv
+# the benchmarked path (FusedTrainStep: two CUDA-graph replays per step): launch list of the last step
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/fused_launches.csv python scripts/profile_fused.py 1024 5 > gpurun_out/fused_ncu.log 2>&1
+tail -1 gpurun_out/fused_ncu.log

@@ -28,7 +28,7 @@ if os.path.exists(rep):
                         "smsp__issue_active.avg.pct_of_peak_sustained_active",
                         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct",
                         "smsp__inst_executed.sum", "launch__registers_per_thread"] if k in col]
-    out = ["# ncu --set full --clock-control none --import-source on -k regex:sdf_query|sdf_render|sdf_bwd|head_fwd|head_bwd|wgrad --launch-skip 30 --launch-count 14",
+    out = ["# ncu --set full --clock-control none --import-source on -k regex:sdf_query|sdf_render|sdf_bwd|head_fwd|head_bwd|wgrad --launch-skip 30 --launch-count 15",
            "#   python scripts/profile_step.py 1024 4   (plugin path, eager launches; 1024 rays x 98 samples, beta 0.1 -> sampler k = 2), one B200",
            "# per-launch values, cold L2 under replay",
            "# units: " + ", ".join("%s [%s]" % (k, units[col[k]]) for k in keys),

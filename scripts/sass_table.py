@@ -1,6 +1,6 @@
 """Per-kernel SASS evidence table (no GPU needed): cuobjdump -sass of the built library, instruction counts that prove
 the Blackwell-native paths (B200_PROFILING.md: tcgen05.mma -> UTC*MMA, tcgen05.ld/st -> LDTM/STTM, TMA bulk copies ->
-UBLKCP / UTMALDG, tcgen05.commit -> UTCBAR, mbarrier -> SYNCS, vector reductions -> RED).
+UBLKCP / UTMALDG, tcgen05.commit -> UTCBAR, mbarrier -> SYNCS, vector reductions -> RED, setmaxnreg -> USETMAXREG).
     python scripts/sass_table.py [tag]      -> profiles/<tag>_sass_table.txt"""
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -8,7 +8,7 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 so = os.path.join(ROOT, "neat_b200", "libneat_b200.so")
 txt = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
 MN = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "UBLKPF", "UTMALDG", "SYNCS", "HMMA", "MUFU.EX2", "MUFU.LG2", "RED.E", "REDG",
-      "LDG.E", "STG.E", "LDS", "STS", "ELECT"]
+      "LDG.E", "STG.E", "LDS", "STS", "ELECT", "USETMAXREG"]
 cnt = collections.OrderedDict()
 cur = None
 for line in txt.splitlines():
