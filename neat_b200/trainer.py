@@ -153,7 +153,20 @@ class FusedTrainStep:
         st.pose, st.K = self.inp["pose"][0], self.inp["intrinsics"][0]
         st.param_layers = m._wn_layers()
         rn.sampler.rng = "device"
-        glob = F.forward(m.latents.detach(), [l.weight.detach() for l in self.lin], [l.bias.detach() for l in self.lin], self.acts)
+        # the junction ffn only feeds the hand-over (side stream, after the attraction head), the projections of the
+        # global junctions below and, with junction_eikonal, the eikonal points: it runs on the side stream, off the
+        # critical path of the sampler
+        main, side = torch.cuda.current_stream(self.device), rn.side_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(fork)
+            glob = F.forward(m.latents.detach(), [l.weight.detach() for l in self.lin], [l.bias.detach() for l in self.lin],
+                             self.acts)
+            glob_ready = torch.cuda.Event()
+            glob_ready.record(side)
+        if m.junction_eikonal:
+            main.wait_event(glob_ready)
         st.junction_inputs = (glob, st.pose, st.K)
         st.dbscan_enabled = m.dbscan_enabled
         st.junction_eikonal = m.junction_eikonal
@@ -162,6 +175,7 @@ class FusedTrainStep:
         rgb_values, lines3d, grad_theta = step_forward(rn, st, beta)
         self.st = m.last_step = st
         pose_inv = st.pose_inv.reshape(-1)
+        main.wait_event(glob_ready)
         _lib.check(lib.neat_project_points(self.G, ptr(pose_inv), ptr(st.K), 4, ptr(glob), ptr(self.j2g), ptr(self.j2gc),
                                            self._stream()))
         # VolSDFLoss core terms fused with their own gradient (loss_wfr.py:47-79), then the adjoint of project2D(I, ...)
@@ -221,7 +235,8 @@ class FusedTrainStep:
                                                     ptr(self.g_j2gc), ptr(self.g_glob), self._stream()))
         self.g_glob.add_(self.g_j3g)
         F.backward(m.latents.detach(), [l.weight.detach() for l in self.lin], self.acts, self.g_glob, m.latents.grad,
-                   [l.weight.grad for l in self.lin], [l.bias.grad for l in self.lin], self.ffn_scratch, True)
+                   [l.weight.grad for l in self.lin], [l.bias.grad for l in self.lin], self.ffn_scratch, True,
+                   side=self.rn.side_stream())
         if self.world > 1:
             dist.all_reduce(self.bucket.flat, op=dist.ReduceOp.SUM)
         _lib.check(lib.neat_adam_step_device(self.adam_table, len(self.params), ptr(self.hyper_dev), ptr(self.adam_state),
