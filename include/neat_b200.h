@@ -189,6 +189,13 @@ size_t neat_dbscan_workspace_bytes(int N);
 int neat_dbscan(const float* points, int N, float eps, void* workspace, float* centroids, int* n_clusters,
                 void* stream);
 
+/* use_l3d junction candidates (neat_wfr_rend_a.py:454-455, 461-465; only read when dbscan_enabled is false):
+ * score_i = |(l3d_i - a_i) x (l3d_i - b_i)| / |a_i - b_i| for the 3D line (a_i, b_i) = lines3d[i]; the rays with
+ * score < max(median(score), 0.01) contribute both end points (ray order) followed by their l3d points.
+ * lines3d [R,6], l3d [R,3] -> out [3R,3] (first *n_out rows valid; n_out: device int); score [R] or NULL.  R <= 4096. */
+int neat_l3d_candidates(int R, const float* lines3d, const float* l3d, float* out, int* n_out, float* score,
+                        void* stream);
+
 /* ---- junction matching, HOST functions (no device work, no stream) -------------------------------------
  * The reference moves the clustered junctions to the CPU and solves two assignment problems with
  * scipy.optimize.linear_sum_assignment (neat_wfr_rend_a.py:466-484, loss_wfr.py:104-108).  These two entry

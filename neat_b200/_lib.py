@@ -34,6 +34,7 @@ SIGNATURES = {
     "neat_weight_norm_forward": (_I, [_P, _P, _I, _P, _P]),
     "neat_weight_norm_backward": (_I, [_P, _P, _I, _P, _I, _P]),
     "neat_set_precision": (_I, [_P, _I]),
+    "neat_l3d_candidates": (_I, [_I, _P, _P, _P, _P, _P, _P]),
     "neat_pack_weights": (_I, [_P, _P, _P]),
     "neat_sdf_points": (_I, [_P, _P, _I, _P, _P]),
     "neat_sdf_rays": (_I, [_P, _P, _I, _P, _P, _I, _I, _P, _P]),

@@ -116,19 +116,26 @@ def step_forward(renderer, st, beta):
         side.wait_event(lines_done)
         # junction candidates first (the host is waiting for them): DBSCAN is ~100 us of tiny launches (8-block grids),
         # which used to sit on the main stream between the two heads (ncu launch list, profiles/r02_*)
-        if st.junction_inputs is not None:
+        use_l3d = st.junction_inputs is not None and not st.dbscan_enabled and getattr(st, "use_l3d", False)
+
+        def hand_over(cent_d, n_d):
+            st.junction_event, st.junction_host = renderer.to_host_async([n_d, cent_d] + list(st.junction_inputs),
+                                                                         counter=getattr(st, "handover_counter", None))
+
+        if st.junction_inputs is not None and not use_l3d:
             if st.dbscan_enabled:
                 cent_d, n_d = renderer.dbscan_async(lines3d.view(-1, 3), 0.01)
             else:  # abc-neat-a.conf: every attraction end point is a junction candidate (neat_wfr_rend_a.py:465-466)
                 cent_d = lines3d.view(-1, 3)
                 n_d = renderer.pool.get("step.n_all", 1, torch.int32)
                 n_d.fill_(2 * R)
-            st.junction_event, st.junction_host = renderer.to_host_async([n_d, cent_d] + list(st.junction_inputs),
-                                                                         counter=getattr(st, "handover_counter", None))
+            hand_over(cent_d, n_d)
         p3 = renderer.explicit_points(points3d)
         st.sdf3, st.grad3, _, _, _ = renderer.sdf_outputs(p3, R, clamp=True, want_feat=False, tag="surface")
         st.lines2d, st.lines2d_calib, st.l3d, st.pose_inv = renderer.line_geometry(pose, K, st.uv_proj, points3d,
                                                                                    st.grad3, lines3d)
+        if use_l3d:  # the candidates need the tangent-plane points l3d (neat_wfr_rend_a.py:461-465)
+            hand_over(*renderer.l3d_candidates_async(lines3d, st.l3d))
         side_done = torch.cuda.Event()
         side_done.record(side)
     for t in (st.sdf3, st.grad3, st.lines2d, st.lines2d_calib, st.l3d, st.pose_inv):

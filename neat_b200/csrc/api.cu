@@ -797,6 +797,15 @@ int neat_project_points_backward(int N, const float* pose_inv, const float* K, i
   return NEAT_OK;
 }
 
+int neat_l3d_candidates(int R, const float* lines3d, const float* l3d, float* out, int* n_out, float* score, void* stream) {
+  if (R <= 0 || !lines3d || !l3d || !out || !n_out) return fail(NEAT_EINVAL, "bad argument");
+  if (R > L3D_MAX_R) return fail(NEAT_EUNSUPPORTED, "use_l3d: at most 4096 rays per call");
+  l3d_candidates_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(R, lines3d, l3d, out, n_out, score);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return NEAT_OK;
+}
+
 int neat_junction_terms(int n, const float* j3d_local, const float* j3d_global, const float* j2d_local_calib,
                         const float* j2d_global_calib, const float* j2d_local, const float* j2d_global, const int* rows,
                         const int* cols, float* out, void* stream) {

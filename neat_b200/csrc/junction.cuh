@@ -136,4 +136,96 @@ __global__ void junction_terms_bwd_kernel(int n, const float* __restrict__ j3l, 
   }
 }
 
+// use_l3d junction candidates (neat_wfr_rend_a.py:454-455, 461-465): score_i = |(l3d_i - a_i) x (l3d_i - b_i)| / |a_i - b_i|
+// for the 3D line (a_i, b_i) of ray i; the rays with score < max(median(score), 0.01) hand over both end points (ray
+// order), followed by their l3d points.  The reference does this with median / boolean-mask / cat launches and a host
+// sync for the mask; here: ONE block -- scores and a bitonic sort of their copy in shared memory (torch.median = the
+// lower median, element (R-1)/2 of the sorted scores), then an ordered compaction.  out [3R,3]; *n_out = 3 n_selected.
+constexpr int L3D_MAX_R = 4096;
+__global__ void __launch_bounds__(1024) l3d_candidates_kernel(int R, const float* __restrict__ lines3d,
+                                                              const float* __restrict__ l3d, float* __restrict__ out,
+                                                              int* __restrict__ n_out, float* __restrict__ score_out) {
+  __shared__ float score[L3D_MAX_R];
+  __shared__ float key[L3D_MAX_R];
+  __shared__ int wsum[32];
+  __shared__ int base;
+  const int tid = threadIdx.x;
+  int P2 = 1;
+  while (P2 < R) P2 <<= 1;
+  for (int i = tid; i < P2; i += blockDim.x) {
+    float sc = INFINITY;
+    if (i < R) {
+      const float* a = lines3d + 6 * i;
+      const float* q = l3d + 3 * i;
+      const float u[3] = {q[0] - a[0], q[1] - a[1], q[2] - a[2]}, v[3] = {q[0] - a[3], q[1] - a[4], q[2] - a[5]};
+      const float cx = u[1] * v[2] - u[2] * v[1], cy = u[2] * v[0] - u[0] * v[2], cz = u[0] * v[1] - u[1] * v[0];
+      const float dx = a[0] - a[3], dy = a[1] - a[4], dz = a[2] - a[5];
+      sc = sqrtf(cx * cx + cy * cy + cz * cz) / sqrtf(dx * dx + dy * dy + dz * dz);
+      score[i] = sc;
+      if (score_out) score_out[i] = sc;
+    }
+    key[i] = sc == sc ? sc : INFINITY;   // a NaN score (degenerate line) sorts last and is never selected
+  }
+  __syncthreads();
+  for (int k = 2; k <= P2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < P2; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const float x = key[i], y = key[ixj];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) { key[i] = y; key[ixj] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const float thr = fmaxf(key[(R - 1) / 2], 0.01f);
+  // pass 1: number selected; pass 2: ordered positions
+  int cnt = 0;
+  for (int i = tid; i < R; i += blockDim.x) cnt += score[i] < thr ? 1 : 0;
+  if (tid == 0) base = 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((tid & 31) == 0) wsum[tid >> 5] = cnt;
+  __syncthreads();
+  int total = 0;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) total += wsum[w];
+  __syncthreads();
+  for (int start = 0; start < R; start += blockDim.x) {
+    const int i = start + tid;
+    const int flag = (i < R && score[i] < thr) ? 1 : 0;
+    int v = flag;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, o);
+      if ((tid & 31) >= o) v += t;
+    }
+    if ((tid & 31) == 31) wsum[tid >> 5] = v;
+    __syncthreads();
+    if (tid < 32) {
+      int sct = tid < (blockDim.x >> 5) ? wsum[tid] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, sct, o);
+        if (tid >= o) sct += t;
+      }
+      wsum[tid] = sct;
+    }
+    __syncthreads();
+    const int woff = (tid >> 5) ? wsum[(tid >> 5) - 1] : 0;
+    if (flag) {
+      const int pos = base + woff + v - 1;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) out[6 * pos + c] = lines3d[6 * i + c];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) out[3 * (2 * total + pos) + c] = l3d[3 * i + c];
+    }
+    __syncthreads();
+    if (tid == 0) base += wsum[(blockDim.x >> 5) - 1];
+    __syncthreads();
+  }
+  if (tid == 0) *n_out = 3 * total;
+}
+
 }  // namespace neat

@@ -257,9 +257,6 @@ class VolSDFNetwork(nn.Module):
         self.use_median = bool(c.get("use_median", False))
         self.junction_eikonal = bool(c.get("junction_eikonal", False))
         self.use_l3d = bool(c.get("use_l3d", False))
-        if self.use_l3d and not self.dbscan_enabled:
-            raise _lib.NeatError("use_l3d=True (without DBSCAN) is not supported: no shipped conf enables it "
-                                 "(dtu.conf / bmvs.conf: DBSCAN; abc-neat-a.conf: every end point)")
         import weakref
         ref = weakref.ref(self)
         for m in (self.implicit_network, self.rendering_network, self.attraction_network):
@@ -392,6 +389,7 @@ class VolSDFNetwork(nn.Module):
         st.junction_inputs = (glob.detach(), pose, K4)
         st.dbscan_enabled = self.dbscan_enabled
         st.junction_eikonal = self.junction_eikonal
+        st.use_l3d = self.use_l3d
         st.param_layers = self._wn_layers()
         self._packed_version = None  # the step packs its own copy
         # RNG order of the reference: the sampler's draws, then the eikonal uniform_ (neat_wfr_rend_a.py:518); the junction

@@ -256,6 +256,17 @@ class Renderer:
                                        ctx._stream()))
         return cent, n
 
+    def l3d_candidates_async(self, lines3d, l3d):
+        """use_l3d junction candidates (neat_wfr_rend_a.py:461-465) without a device->host read: (buffer [3R,3],
+        device count [1])."""
+        ctx = self.ctx
+        R = l3d.shape[0]
+        out = self.pool.get("l3d.cand", 3 * R * 3).view(-1, 3)
+        n = self.pool.get("l3d.n", 1, torch.int32)
+        _lib.check(ctx.lib.neat_l3d_candidates(R, ctx._chk(lines3d.reshape(R, 6), (R, 6)), ctx._chk(l3d, (R, 3)),
+                                               _ptr(out), _ptr(n), None, ctx._stream()))
+        return out, n
+
     def side_stream(self):
         """Second stream for the small launches that fit into the tail of a big persistent one."""
         if getattr(self, "_side", None) is None:

@@ -62,6 +62,14 @@ def toy_white_conf():
     return c
 
 
+def toy_l3d_conf():
+    """toy_conf with the third junction-candidate rule of the model class (neat_wfr_rend_a.py:461-465): no DBSCAN,
+    use_l3d -- the rays whose tangent-plane point agrees best with their 3D line propose the junctions."""
+    c = toy_conf()
+    c.update(dbscan_enabled=False, use_l3d=True)
+    return c
+
+
 def loss_conf():
     return {"eikonal_weight": 0.1, "line_weight": 0.01, "rgb_loss": "torch.nn.L1Loss"}
 

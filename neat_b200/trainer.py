@@ -104,7 +104,7 @@ class FusedTrainStep:
         self.j2g, self.j2gc = f(G, 2), f(G, 2)
         self.g_j3g, self.g_j2gc, self.g_glob = f(G, 3), f(G, 2), f(G, 3)
         # the host -> device packet of the junction block: [n | rows | cols | local [cap,7]]
-        self.cap = max(1, min(n_gt, 2 * R))   # local junctions <= min(ground-truth junctions, candidates)
+        self.cap = max(1, min(n_gt, 3 * R))   # local junctions <= min(ground-truth junctions, candidates)
         n_words = 1 + 2 * self.cap + 7 * self.cap
         self.packet_host = torch.zeros(n_words, dtype=torch.int32, pin_memory=True)
         self.packet_dev = torch.zeros(n_words, dtype=torch.int32, device=dev)
@@ -170,6 +170,7 @@ class FusedTrainStep:
         st.junction_inputs = (glob, st.pose, st.K)
         st.dbscan_enabled = m.dbscan_enabled
         st.junction_eikonal = m.junction_eikonal
+        st.use_l3d = m.use_l3d
         st.handover_counter = rn.draw_counter[:1]
         beta = m.density.beta.detach().reshape(1)
         rgb_values, lines3d, grad_theta = step_forward(rn, st, beta)
@@ -289,6 +290,7 @@ class FusedTrainStep:
             ev[2].record()
             self.profile.append(ev)
         self.n_steps += 1
+        self.model._packed_version = None   # the parameters changed under raw pointers: eval entry points must re-pack
         lo = self.loss_out
         return {"loss": self.total, "rgb_loss": lo[1], "eikonal_loss": lo[2], "line_loss": lo[3], "l2d_loss": lo[4],
                 "count": lo[5], "j3d_loss": self.jout[0], "j2d_loss": self.jout[1], "j2d_stat": self.jout[2],

@@ -203,6 +203,10 @@ def main():
         run_case("abc_beta0.1", synth.abc_conf(), 128, seed_w=3, beta=0.1, cam=(512, 512, 560.0, abc_pose))
         if only:
             return
+    if "l3d" in only or not only:
+        run_case("toy_l3d", synth.toy_l3d_conf(), 128, seed_w=5, beta=0.1, cam=(512, 512, 560.0, abc_pose))
+        if only:
+            return
     if "white" in only or not only:
         # the model class's optional branches no shipped conf selects: white_bkgd (+ no sphere clamp) and junction_eikonal
         run_case("toy_white_jeik", synth.toy_white_conf(), 128, seed_w=4, beta=0.1, cam=(512, 512, 560.0, abc_pose))

@@ -54,6 +54,7 @@ class NeatParams:
     use_median: bool = False
     bg_color: Optional[torch.Tensor] = None  # white_bkgd (neat_wfr_rend_a.py:262-263, 411-413); also means sphere_radius = 0 (:266)
     junction_eikonal: bool = False           # neat_wfr_rend_a.py:524-525
+    use_l3d: bool = False                    # neat_wfr_rend_a.py:461-465 (only read when dbscan_enabled is False)
 
     def sdf_sphere(self):
         # ImplicitNetwork's sdf_bounding_sphere: 0 (no clamp) under white_bkgd (neat_wfr_rend_a.py:266)
@@ -70,7 +71,7 @@ class NeatParams:
                           self.beta_min, tuple(self.skip_in), self.multires, self.multires_view,
                           self.sphere_radius, self.sphere_scale, cv(self.ffn_W), cv(self.ffn_b),
                           None if self.latents is None else self.latents.to(dtype), self.dbscan_enabled, self.use_median,
-                          None if self.bg_color is None else self.bg_color.to(dtype), self.junction_eikonal)
+                          None if self.bg_color is None else self.bg_color.to(dtype), self.junction_eikonal, self.use_l3d)
 
 
 def weight_norm_effective(g, v):
@@ -740,9 +741,22 @@ class TrainRandoms:
     eik_uniform: torch.Tensor      # neat_wfr_rend_a.py:518  uniform_(-r, r) [R,3]
 
 
-def junction_block(P: NeatParams, K, pose, lines3d, gt_vertices):
-    """neat_wfr_rend_a.py:457-496: candidates = DBSCAN centroids (dbscan_enabled, :459-460) or every attraction end
-    point (:465-466; use_l3d is not restated), match filter < 10 px or < median matched cost (use_median, :475-482)."""
+def l3d_candidates(lines3d, l3d):
+    """neat_wfr_rend_a.py:454-455, 461-465 (use_l3d): the rays whose tangent-plane point l3d lies closer to their 3D
+    line than the median ray (but at least 0.01) hand both end points, then their l3d, to the junction matching."""
+    l3 = lines3d.detach().reshape(-1, 2, 3)
+    l3d = l3d.detach()
+    score = torch.norm(torch.cross(l3d - l3[:, 0], l3d - l3[:, 1], dim=-1), dim=-1) / torch.norm(l3[:, 0] - l3[:, 1], dim=-1)
+    med = score.median()
+    thr = med if float(med) > 0.01 or bool(torch.isnan(med)) else torch.tensor(0.01, dtype=score.dtype)   # python max(median, 0.01)
+    sel = score < thr
+    return torch.cat((l3[sel].reshape(-1, 3), l3d[sel]), dim=0), score
+
+
+def junction_block(P: NeatParams, K, pose, lines3d, gt_vertices, l3d=None):
+    """neat_wfr_rend_a.py:457-496: candidates = DBSCAN centroids (dbscan_enabled, :459-460), the l3d selection (use_l3d,
+    :461-465) or every attraction end point (:466-467); match filter < 10 px or < median matched cost (use_median,
+    :475-482)."""
     from scipy.optimize import linear_sum_assignment
     dt = lines3d.dtype
     Rm, T = pose_inverse_rt(pose)
@@ -751,6 +765,8 @@ def junction_block(P: NeatParams, K, pose, lines3d, gt_vertices):
     if P.dbscan_enabled:
         cent = dbscan_centroids(lines3d.detach().cpu().numpy().reshape(-1, 3), eps=0.01, min_samples=2)
         j3d = torch.tensor(cent).float().to(dt).reshape(-1, 3)
+    elif P.use_l3d:
+        j3d, _ = l3d_candidates(lines3d, l3d)
     else:
         j3d = lines3d.detach().reshape(-1, 3)
     j2d = project2d(K3, Rm, T, j3d)
@@ -794,7 +810,7 @@ def neat_forward(P: NeatParams, sconf: SamplerConf, K, pose, uv, uv_proj, gt_ver
                lines2d=geo["lines2d"], lines2d_calib=geo["lines2d_calib"], sdf=geo["sdf"],
                K=K[:3, :3], z_vals=z_vals, weights=rr["weights"], n_sampler_iters=k)
     if training:
-        out.update(junction_block(P, K, pose, rr["lines3d"], gt_vertices))
+        out.update(junction_block(P, K, pose, rr["lines3d"], gt_vertices, l3d=geo["l3d"]))
         near = camr + z_eik * dirs
         eik_pts = torch.cat([rnd.eik_uniform.to(dirs.dtype), near], 0)
         if P.junction_eikonal:                                # neat_wfr_rend_a.py:524-525

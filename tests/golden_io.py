@@ -9,7 +9,8 @@ from oracle import neat_oracle as O
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = {"toy_beta0.1": synth.toy_conf, "dtu_beta0.1": synth.dtu_conf, "dtu_beta0.01": synth.dtu_conf,
-         "abc_beta0.1": synth.abc_conf, "toy_white_jeik": synth.toy_white_conf}
+         "abc_beta0.1": synth.abc_conf, "toy_white_jeik": synth.toy_white_conf,
+         "toy_l3d": synth.toy_l3d_conf}
 
 
 def load(name):
@@ -33,6 +34,7 @@ def oracle_params(conf, sd_np, dtype=torch.float32, track=False):
     if conf.get("white_bkgd", False):
         P.bg_color = torch.tensor([float(v) for v in conf.get("bg_color", [1.0, 1.0, 1.0])], dtype=dtype)
     P.junction_eikonal = bool(conf.get("junction_eikonal", False))
+    P.use_l3d = bool(conf.get("use_l3d", False))
     return P, sd
 
 

@@ -49,10 +49,12 @@ def test_no_cpu_fallback():
 
 def test_unsupported_confs_are_rejected():
     c = synth.toy_conf()
-    c.update(dbscan_enabled=False, use_l3d=True)
-    with pytest.raises(_lib.NeatError):
-        VolSDFNetwork(c)
+    c["ray_sampler"]["inverse_sphere_bg"] = True
+    from neat_b200.context import sampler_config_from_conf
+    with pytest.raises(_lib.NeatError):        # cannot run in the reference's own class either
+        sampler_config_from_conf(c)
     VolSDFNetwork(synth.toy_white_conf())     # white_bkgd + junction_eikonal: supported (golden case toy_white_jeik)
+    VolSDFNetwork(synth.toy_l3d_conf())       # use_l3d without DBSCAN: supported (golden case toy_l3d)
     c = synth.toy_conf()
     c["rendering_network"]["mode"] = "nerf"
     with pytest.raises(_lib.NeatError):
