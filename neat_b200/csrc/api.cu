@@ -1205,12 +1205,13 @@ struct Planes {  // an operand: per-tile base + stride, offsets of the hi / lo p
   uint32_t hi, lo;
   int cols;
   int f16;  // 1: fp16 pairs (written by a forward kernel), 0: bf16 pairs (written by a backward kernel)
+  int main; // 1: main operand tile (half-tile-contiguous global layout, engine.cuh), 0: aux tile (shared-memory order)
 };
 Planes main_planes(const void* base, uint64_t stride, uint32_t off, int cols, int f16) {
-  return Planes{static_cast<const uint8_t*>(base), stride, off, off + PLANE_MAIN_BYTES, cols, f16};
+  return Planes{static_cast<const uint8_t*>(base), stride, off, off + PLANE_MAIN_BYTES, cols, f16, 1};
 }
 Planes aux_planes(const void* base, uint64_t stride, uint32_t off, int cols, int f16) {
-  return Planes{static_cast<const uint8_t*>(base), stride, off, off + PLANE_AUX_BYTES, cols, f16};
+  return Planes{static_cast<const uint8_t*>(base), stride, off, off + PLANE_AUX_BYTES, cols, f16, 0};
 }
 inline int c16(int x) { return (x + 15) / 16 * 16; }
 inline int c8(int x) { return (x + 7) / 8 * 8; }
@@ -1234,6 +1235,7 @@ void add_gemm(std::vector<WJob>& jobs, const Planes& X, int x_valid, const Plane
       j.bias = bias;
       j.n_tiles = n_tiles; j.split = sp; j.n_split = n_split;
       j.x_f16 = X.f16; j.y_f16 = Y.f16;
+      j.x_main = X.main; j.y_main = Y.main;
       jobs.push_back(j);
     }
   }

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_bwd_kernel(const __grid_c
           const int c0 = epi_col(e, g);
           if (c0 < st.w.npad) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) mraw[g][j] = ldg128(u_hi + ((c0 >> 3) + j) * A_CHUNK_BYTES + e.row * 16);
+            for (int j = 0; j < 2; ++j) mraw[g][j] = ldg128(u_hi + gtile_off((c0 >> 3) + j, e.row));
           }
         }
         uint8_t* zsave = brec + bl.zb + static_cast<size_t>(l - 1) * TILE_MAIN_BYTES;  // z_bar_{l-1}
@@ -311,8 +311,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
           const int c = epi_unit_col(e, u), k = u % (SDF_BWD_PF + 1);
           if (c < npad) {
             sp[k] = __ldg(s1_at(d1, e, u));
-            ahv[k] = ldg128(a_hi + unit_off(e, u));
-            alv[k] = ldg128(a_lo + unit_off(e, u));
+            ahv[k] = ldg128(a_hi + gunit_off(e, u));
+            alv[k] = ldg128(a_lo + gunit_off(e, u));
           }
         };
         uint8_t* psave = brec + bl.p + static_cast<size_t>(l) * TILE_MAIN_BYTES;  // p_{l+1}
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
               v[4 * j] = valid ? t.x : 0.f; v[4 * j + 1] = valid ? t.y : 0.f;
               v[4 * j + 2] = valid ? t.z : 0.f; v[4 * j + 3] = valid ? t.w : 0.f;
             }
-            store_a16<false>(sm.a_hi, sm.a_lo, e.row, c0, v);
+            store_a16_save<false>(sm.a_hi, sm.a_lo, brec + bl.zb + static_cast<size_t>(L - 1) * TILE_MAIN_BYTES, e.row, c0, v);
           }
         }
         if (e.j == 0) {
@@ -377,12 +377,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
         }
       }
       epi_publish_all(sm);  // -> T_{L-1}
+      // the main columns of z_bar_{L-1} went out from registers above (global operand-tile layout); the aux columns
+      // (the sdf column) leave as one bulk store out of the aux planes
       epi_wrote(sm);
       if (e.lead) {
         mbar_wait(&sm.wr_done, e.wr_phase);
-        uint8_t* dst = brec + bl.zb + static_cast<size_t>(L - 1) * TILE_MAIN_BYTES;
-        bulk_s2g(dst, sm.a_hi, PLANE_MAIN_BYTES);
-        bulk_s2g(dst + PLANE_MAIN_BYTES, sm.a_lo, PLANE_MAIN_BYTES);
         bulk_s2g(brec + bl.zb_aux, sm.a_hi + PLANE_MAIN_BYTES, PLANE_AUX_BYTES);
         bulk_s2g(brec + bl.zb_aux + PLANE_AUX_BYTES, sm.a_lo + PLANE_MAIN_BYTES, PLANE_AUX_BYTES);
         bulk_commit();

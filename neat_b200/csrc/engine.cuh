@@ -283,6 +283,24 @@ __device__ __forceinline__ uint4* s1_at(uint8_t* layer, const Epi& e, int u) {
 __device__ __forceinline__ const uint4* s1_at(const uint8_t* layer, const Epi& e, int u) {
   return reinterpret_cast<const uint4*>(layer + unit_off(e, u));
 }
+// GLOBAL layout of a saved MAIN operand tile (the tiles wgrad reads; bf16 pairs, hi plane then lo plane, 64 KB each):
+//     plane + (row / 64) * 32 KB + (col / 8) * 1 KB + (row % 64) * 16 + (col % 8) * 2
+// i.e. the shared-memory chunk-major order within each HALF of the points.  A half tile of any column range is then one
+// contiguous piece per plane, so wgrad streams half tiles through a two-stage ring with single bulk copies and multiplies
+// one half while the next one lands (as [chunk][128 rows] planes a half tile was 1 KB pieces: the copy engine's per-copy
+// cost made that pipeline slower than none, round 1).  The records are written from registers, so their layout is free;
+// aux tiles (12 KB planes, some of them bulk-stored out of shared memory) keep the shared-memory order.
+constexpr int G_HALF_ROWS = TILE_M / 2;
+constexpr int G_CHUNK_BYTES = G_HALF_ROWS * 16;                      // 1024
+constexpr int G_HALF_PLANE_BYTES = (A_MAIN_COLS / 8) * G_CHUNK_BYTES;  // 32768
+__device__ __forceinline__ uint32_t gtile_off(int chunk, int row) {
+  return static_cast<uint32_t>((row >> 6) * G_HALF_PLANE_BYTES + chunk * G_CHUNK_BYTES + (row & 63) * 16);
+}
+// ... of this thread's unit u (see unit_off)
+__device__ __forceinline__ uint32_t gunit_off(const Epi& e, int u) {
+  return gtile_off(2 * e.j + (u >> 1) * 8 + (u & 1), e.row);
+}
+
 // zhat scratch of one layer (sdf_bwd): two such planes of float4, columns 0-3 / 4-7 of every chunk
 constexpr int ZH_PLANE_BYTES = (256 / 8) * TILE_M * 16;
 __device__ __forceinline__ float4* zh_at(uint8_t* layer, int half, const Epi& e, int u) {
@@ -400,8 +418,9 @@ __device__ __forceinline__ void store_a16_save(uint8_t* a_hi, uint8_t* a_lo, uin
     sts128(s_hi + j * A_CHUNK_BYTES, hi);
     sts128(s_lo + j * A_CHUNK_BYTES, lo);
     if (gtile) {
-      __stcs(reinterpret_cast<uint4*>(gtile + off + j * A_CHUNK_BYTES), hi);
-      __stcs(reinterpret_cast<uint4*>(gtile + (A_MAIN_COLS / 8) * A_CHUNK_BYTES + off + j * A_CHUNK_BYTES), lo);
+      const uint32_t goff = gtile_off((c0 >> 3) + j, row);
+      __stcs(reinterpret_cast<uint4*>(gtile + goff), hi);
+      __stcs(reinterpret_cast<uint4*>(gtile + (A_MAIN_COLS / 8) * A_CHUNK_BYTES + goff), lo);
     }
   }
 }
@@ -425,20 +444,22 @@ __device__ __forceinline__ void sts16(uint8_t* a_hi, uint8_t* a_lo, int row, int
 // The saved operand tiles (read by the backward kernels and by wgrad) hold bf16 pairs whatever the shared-memory tile
 // holds: tcgen05.mma kind::f16 faults ("illegal instruction", measured on B200) when A and B carry different 16-bit
 // formats, and the backward tensors need bf16's exponent range.  16 / 8 fp32 values -> bf16 hi / lo -> global tile.
-// lo_off: byte offset of the lo plane from the hi plane (main tile: PLANE_MAIN, aux tile: PLANE_AUX).
+// lo_off: byte offset of the lo plane from the hi plane.  MAIN tile (lo_off = PLANE_MAIN): the half-tile-contiguous global
+// layout (gtile_off); aux tile (lo_off = PLANE_AUX): the shared-memory order.
 __device__ __forceinline__ void stg_bf16_pairs8(uint8_t* gtile, uint32_t lo_off, int row, int chunk, const float* v) {
   uint4 hi, lo;
   split8<false>(v, hi, lo);
-  const uint32_t off = chunk * A_CHUNK_BYTES + row * 16;
+  const uint32_t off = lo_off == (A_MAIN_COLS / 8) * A_CHUNK_BYTES ? gtile_off(chunk, row)
+                                                                   : static_cast<uint32_t>(chunk * A_CHUNK_BYTES + row * 16);
   __stcs(reinterpret_cast<uint4*>(gtile + off), hi);
   __stcs(reinterpret_cast<uint4*>(gtile + lo_off + off), lo);
 }
 __device__ __forceinline__ void stg16(uint8_t* gtile, int row, int c0, const uint4 hi[2], const uint4 lo[2]) {
-  const uint32_t off = (c0 >> 3) * A_CHUNK_BYTES + row * 16;
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
-    __stcs(reinterpret_cast<uint4*>(gtile + off + j * A_CHUNK_BYTES), hi[j]);
-    __stcs(reinterpret_cast<uint4*>(gtile + (A_MAIN_COLS / 8) * A_CHUNK_BYTES + off + j * A_CHUNK_BYTES), lo[j]);
+    const uint32_t goff = gtile_off((c0 >> 3) + j, row);
+    __stcs(reinterpret_cast<uint4*>(gtile + goff), hi[j]);
+    __stcs(reinterpret_cast<uint4*>(gtile + (A_MAIN_COLS / 8) * A_CHUNK_BYTES + goff), lo[j]);
   }
 }
 template <bool F16>
@@ -449,8 +470,9 @@ __device__ __forceinline__ void store_a8_save(uint8_t* a_hi, uint8_t* a_lo, uint
   sts128(smem_u32(a_hi) + off, hi);
   sts128(smem_u32(a_lo) + off, lo);
   if (gtile) {
-    __stcs(reinterpret_cast<uint4*>(gtile + off), hi);
-    __stcs(reinterpret_cast<uint4*>(gtile + (A_MAIN_COLS / 8) * A_CHUNK_BYTES + off), lo);
+    const uint32_t goff = gtile_off(c0 >> 3, row);
+    __stcs(reinterpret_cast<uint4*>(gtile + goff), hi);
+    __stcs(reinterpret_cast<uint4*>(gtile + (A_MAIN_COLS / 8) * A_CHUNK_BYTES + goff), lo);
   }
 }
 template <bool F16>

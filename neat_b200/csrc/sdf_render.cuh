@@ -234,8 +234,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_render_kernel(const __grid
 #endif
         constexpr int PF = NEAT_RENDER_PF;
         uint4 s1p[PF];
+        // (at the skip layer the transposed GEMM is wider than the layer below: its extra columns are the skip part,
+        // which needs no sigma' and whose record was never written)
+        const int n_s1 = min(npad, static_cast<int>(p.prog.s[l - 1].w.npad));
         auto issue = [&](int u) {
-          if (epi_unit_col(e, u) < npad) s1p[u % PF] = *s1_at(d1, e, u);
+          s1p[u % PF] = epi_unit_col(e, u) < n_s1 ? *s1_at(d1, e, u) : make_uint4(0u, 0u, 0u, 0u);
         };
 #pragma unroll
         for (int u = 0; u < PF; ++u) issue(u);

@@ -72,10 +72,10 @@ __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, u
                : "memory");
 }
 // ask the L2 to fetch [gmem, gmem + bytes) (16-byte aligned, size % 16 == 0); no completion tracking.
-// Used (a) by wgrad for the tiles ahead of the one being multiplied (none: 1.60 ms, distance 1: 1.43 ms) and (b) by the
+// Used (a) by wgrad for the tile ahead of the one being multiplied and (b) by the
 // weight-producer warp of the backward kernels for the saved tensors the NEXT step's epilogue reads (engine.cuh).  The
 // same hint issued by an epilogue thread made sdf_bwd slower (1.37 -> 1.57 ms): the issuing warp stalls, and the tile
-// waits for its slowest warp.  g_l2_prefetch (neat_debug_set_l2_prefetch): 0 = all hints off, n > 0 = wgrad's distance.
+// waits for its slowest warp.  g_l2_prefetch (neat_debug_set_l2_prefetch): 0 = all hints off.
 __constant__ int g_l2_prefetch = 2;
 // what-if switches for measurements only (neat_debug_set_flags; 0 in every product / test path):
 //   1: wgrad skips X_hi * Y_lo      2: wgrad skips X_lo * Y_hi        4: sigma' rounded to 16-bit fixed point when saved

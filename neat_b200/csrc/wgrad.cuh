@@ -28,6 +28,9 @@ struct WJob {
   int split, n_split;
   int x_f16, y_f16;  // operand formats (umma.cuh): tiles written by the forward kernels hold fp16 pairs, by the backward
                      // kernels bf16 pairs; the instruction descriptor carries one format per operand
+  int x_main, y_main;  // 1: MAIN operand tile in the half-tile-contiguous global layout (engine.cuh: gtile_off), one bulk
+                       // copy per plane and half; 0: aux tile in shared-memory order ([chunk][128 rows]): one 1 KB copy
+                       // per chunk, plane and half (<= 6 chunks)
 };
 
 // 16-byte vector reduction into global memory (sm_90+): one L2 transaction instead of four
@@ -64,18 +67,46 @@ __device__ __forceinline__ void flush_row32(float* row, const float* v, int n_va
     if (j < n_valid) red_add_f32(row + j, scale * v[j]);
 }
 
-constexpr int WG_X_PLANE = 128 / 8 * A_CHUNK_BYTES;  // 32768
-constexpr int WG_Y_PLANE = 256 / 8 * A_CHUNK_BYTES;    // 65536
-constexpr int WG_ONES_BYTES = 2 * A_CHUNK_BYTES;  // 16 columns
-constexpr int WG_THREADS = 192;                   // warps 0-3 flush, warp 4 loads, warp 5 issues MMAs
+// Shared memory: a TWO-STAGE ring of HALF tiles (64 points): while the MMAs of one half run, the next half lands.
+// A stage holds the hi / lo planes of X (128 columns) and Y (256 columns) in chunk-major order over 64 rows:
+// element (pt, col) -> plane + (col / 8) * 1024 + pt * 16 + (col % 8) * 2 -- the bytes of the global layout, so a plane of
+// a main operand is ONE bulk copy.  (Round 1 measured this pipeline with [chunk][128 rows] global tiles: 96 copies of
+// 1 KB per stage, 1.66 -> 2.35 ms.  The single-stage kernel it replaces ran load and MMA back to back: 1.20 ms at 1024
+// rays with the MMAs exposed, profiles/r02_whatif_timing.log.)
+constexpr int WG_HALF = TILE_M / 2;                       // points per stage
+constexpr int WG_CHUNK = WG_HALF * 16;                    // 1024
+constexpr int WG_X_PLANE = 128 / 8 * WG_CHUNK;            // 16384
+constexpr int WG_Y_PLANE = 256 / 8 * WG_CHUNK;            // 32768
+constexpr int WG_ONES_BYTES = 2 * WG_CHUNK;               // 16 columns x 64 points
+constexpr int WG_STAGES = 2;
+constexpr int WG_THREADS = 192;                           // warps 0-3 flush, warp 4 loads, warp 5 issues MMAs
 
 struct alignas(1024) WgradSmem {
-  uint8_t x_hi[WG_X_PLANE], x_lo[WG_X_PLANE];
-  uint8_t y_hi[WG_Y_PLANE], y_lo[WG_Y_PLANE];
+  uint8_t x_hi[WG_STAGES][WG_X_PLANE], x_lo[WG_STAGES][WG_X_PLANE];
+  uint8_t y_hi[WG_STAGES][WG_Y_PLANE], y_lo[WG_STAGES][WG_Y_PLANE];
   uint8_t ones[WG_ONES_BYTES];
-  uint64_t full, empty, d_ready;
+  uint64_t full[WG_STAGES], empty[WG_STAGES], d_ready;
   uint32_t tmem_base;
 };
+
+// copies `n_chunks` chunks of one plane of one half tile into a stage plane; main layout: contiguous, aux: per chunk
+__device__ __forceinline__ void wg_load_plane(uint8_t* dst, const uint8_t* tile_plane, int first_chunk, int n_chunks, int half,
+                                              int is_main, uint64_t* bar) {
+  if (is_main) {
+    bulk_g2s(dst, tile_plane + half * G_HALF_PLANE_BYTES + first_chunk * G_CHUNK_BYTES, n_chunks * WG_CHUNK, bar);
+  } else {
+    for (int c = 0; c < n_chunks; ++c)
+      bulk_g2s(dst + c * WG_CHUNK, tile_plane + (first_chunk + c) * A_CHUNK_BYTES + half * WG_CHUNK, WG_CHUNK, bar);
+  }
+}
+__device__ __forceinline__ void wg_prefetch_plane(const uint8_t* tile_plane, int first_chunk, int n_chunks, int is_main) {
+  if (is_main) {
+    bulk_prefetch_l2(tile_plane + first_chunk * G_CHUNK_BYTES, n_chunks * WG_CHUNK);
+    bulk_prefetch_l2(tile_plane + G_HALF_PLANE_BYTES + first_chunk * G_CHUNK_BYTES, n_chunks * WG_CHUNK);
+  } else {
+    bulk_prefetch_l2(tile_plane + first_chunk * A_CHUNK_BYTES, n_chunks * A_CHUNK_BYTES);
+  }
+}
 
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WJob* __restrict__ jobs) {
   extern __shared__ uint8_t smem_raw[];
@@ -83,26 +114,30 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WJob* __rest
   const WJob job = jobs[blockIdx.x];
   const int warp = warp_idx_uniform();
   const int my_tiles = job.n_tiles > job.split ? (job.n_tiles - job.split + job.n_split - 1) / job.n_split : 0;
+  const int n_halves = 2 * my_tiles;
 
   if (threadIdx.x == 0) {
-    mbar_init(&sm.full, 1);
-    mbar_init(&sm.empty, 1);
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], 1);
+    }
     mbar_init(&sm.d_ready, 1);
     fence_mbar_init();
   }
-  // ones operand: element (pt, col) -> chunk(col/8) * 2048 + pt * 16 + (col % 8) * 2 ; column 0 = 1.0
+  // ones operand: element (pt, col) -> chunk(col/8) * 1024 + pt * 16 + (col % 8) * 2 ; column 0 = 1.0
   for (int i = threadIdx.x; i < WG_ONES_BYTES / 4; i += blockDim.x) {
     const int byte = i * 4;
-    const bool first = byte < A_CHUNK_BYTES && (byte % 16) == 0;
+    const bool first = byte < WG_CHUNK && (byte % 16) == 0;
     reinterpret_cast<uint32_t*>(sm.ones)[i] = first ? 0x00003F80u : 0u;
   }
   // zero the part of the X planes that is never loaded (x_cols < 128)
   if (job.x_cols < 128) {
-    const int from = job.x_cols / 8 * A_CHUNK_BYTES;
-    for (int i = from / 16 + threadIdx.x; i < WG_X_PLANE / 16; i += blockDim.x) {
-      reinterpret_cast<uint4*>(sm.x_hi)[i] = make_uint4(0, 0, 0, 0);
-      reinterpret_cast<uint4*>(sm.x_lo)[i] = make_uint4(0, 0, 0, 0);
-    }
+    const int from = job.x_cols / 8 * WG_CHUNK;
+    for (int s = 0; s < WG_STAGES; ++s)
+      for (int i = from / 16 + threadIdx.x; i < WG_X_PLANE / 16; i += blockDim.x) {
+        reinterpret_cast<uint4*>(sm.x_hi[s])[i] = make_uint4(0, 0, 0, 0);
+        reinterpret_cast<uint4*>(sm.x_lo[s])[i] = make_uint4(0, 0, 0, 0);
+      }
   }
   fence_proxy_async();
   if (warp == 4) tmem_alloc(&sm.tmem_base, TMEM_COLS);
@@ -110,56 +145,61 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WJob* __rest
   __syncthreads();
   tc_fence_after();
 
-  const uint32_t xb = static_cast<uint32_t>(job.x_cols / 8) * A_CHUNK_BYTES;
-  const uint32_t yb = static_cast<uint32_t>(job.n_cols / 8) * A_CHUNK_BYTES;
+  const int xc = job.x_cols / 8, yc = job.n_cols / 8;   // chunks per plane
+  const uint32_t stage_bytes = static_cast<uint32_t>(2 * (xc + yc)) * WG_CHUNK;
   if (warp == 4) {  // load warp (converged; one elected lane issues the bulk copies)
-    for (int t = 0; t < my_tiles; ++t) {
+    for (int h = 0; h < n_halves; ++h) {
+      const int t = h >> 1, half = h & 1, s = h & (WG_STAGES - 1);
       const uint64_t tile = static_cast<uint64_t>(job.split) + static_cast<uint64_t>(t) * job.n_split;
-      const uint8_t* xs = job.x_base + tile * job.x_stride + static_cast<uint64_t>(job.m0 / 8) * A_CHUNK_BYTES;
+      const uint8_t* xs = job.x_base + tile * job.x_stride;
       const uint8_t* ys = job.y_base + tile * job.y_stride;
-      mbar_wait(&sm.empty, (t & 1) ^ 1);
+      mbar_wait(&sm.empty[s], ((h / WG_STAGES) & 1) ^ 1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(&sm.full, 2 * xb + 2 * yb);
-        bulk_g2s(sm.x_hi, xs + job.x_hi, xb, &sm.full);
-        bulk_g2s(sm.x_lo, xs + job.x_lo, xb, &sm.full);
-        bulk_g2s(sm.y_hi, ys + job.y_hi, yb, &sm.full);
-        bulk_g2s(sm.y_lo, ys + job.y_lo, yb, &sm.full);
-        // the tile `dist` ahead streams from HBM into the L2 while this one is multiplied (g_l2_prefetch = dist; the
-        // first iteration also requests the tiles in between)
-        const int dist = g_l2_prefetch;
-        for (int a = (t == 0 ? 1 : dist); a <= dist; ++a) {
-          if (t + a >= my_tiles) break;
-          const uint8_t* xn = xs + static_cast<uint64_t>(a) * job.n_split * job.x_stride;
-          const uint8_t* yn = ys + static_cast<uint64_t>(a) * job.n_split * job.y_stride;
-          bulk_prefetch_l2(xn + job.x_hi, xb);
-          bulk_prefetch_l2(xn + job.x_lo, xb);
-          bulk_prefetch_l2(yn + job.y_hi, yb);
-          bulk_prefetch_l2(yn + job.y_lo, yb);
+        mbar_arrive_expect_tx(&sm.full[s], stage_bytes);
+        wg_load_plane(sm.x_hi[s], xs + job.x_hi, job.m0 / 8, xc, half, job.x_main, &sm.full[s]);
+        wg_load_plane(sm.x_lo[s], xs + job.x_lo, job.m0 / 8, xc, half, job.x_main, &sm.full[s]);
+        wg_load_plane(sm.y_hi[s], ys + job.y_hi, 0, yc, half, job.y_main, &sm.full[s]);
+        wg_load_plane(sm.y_lo[s], ys + job.y_lo, 0, yc, half, job.y_main, &sm.full[s]);
+        // the next tile is requested from HBM into the L2 while this one is multiplied.  With the two-stage ring the
+        // distance that paid for the single-stage kernel (2 tiles) only evicts what is about to be used: measured at
+        // 1024 rays 0 / 1 / 2 / 3 / 4 tiles ahead = 1.00 / 1.00 / 1.08 / 1.31 / 1.46 ms
+        if (half == 0) {
+          const int dist = g_l2_prefetch ? 1 : 0;
+          for (int a = (t == 0 ? 1 : dist); a <= dist; ++a) {
+            if (t + a >= my_tiles) break;
+            const uint8_t* xn = xs + static_cast<uint64_t>(a) * job.n_split * job.x_stride;
+            const uint8_t* yn = ys + static_cast<uint64_t>(a) * job.n_split * job.y_stride;
+            wg_prefetch_plane(xn + job.x_hi, job.m0 / 8, xc, job.x_main);
+            wg_prefetch_plane(xn + job.x_lo, job.m0 / 8, xc, job.x_main);
+            wg_prefetch_plane(yn + job.y_hi, 0, yc, job.y_main);
+            wg_prefetch_plane(yn + job.y_lo, 0, yc, job.y_main);
+          }
         }
       }
       __syncwarp();
     }
   } else if (warp == 5) {  // MMA warp (converged; one elected lane issues)
     // MN-major operands: core matrix = 8 points (K) x 8 columns (16 B); K-direction stride 128 B,
-    // MN-direction stride = one chunk (2048 B)
+    // MN-direction stride = one chunk (1024 B)
     const uint32_t idesc = make_idesc(128, job.n_cols, 1, 1, job.x_f16, job.y_f16);
     const uint32_t idesc1 = make_idesc(128, 16, 1, 1, job.x_f16, 0);  // the in-kernel ones operand is bf16
     const uint32_t d = __shfl_sync(0xffffffffu, sm.tmem_base, 0), d1 = d + 256;
-    const uint64_t dxh0 = make_desc_k(smem_u32(sm.x_hi), 128, A_CHUNK_BYTES), dxl0 = make_desc_k(smem_u32(sm.x_lo), 128, A_CHUNK_BYTES);
-    const uint64_t dyh0 = make_desc_k(smem_u32(sm.y_hi), 128, A_CHUNK_BYTES), dyl0 = make_desc_k(smem_u32(sm.y_lo), 128, A_CHUNK_BYTES);
-    const uint64_t don0 = make_desc_k(smem_u32(sm.ones), 128, A_CHUNK_BYTES);
+    const uint64_t don0 = make_desc_k(smem_u32(sm.ones), 128, WG_CHUNK);
     const bool has_bias = job.bias != nullptr;
     const bool t_hl = !(g_dbg & 1u), t_lh = !(g_dbg & 2u);
-    for (int t = 0; t < my_tiles; ++t) {
-      mbar_wait(&sm.full, t & 1);
+    for (int h = 0; h < n_halves; ++h) {
+      const int s = h & (WG_STAGES - 1);
+      mbar_wait(&sm.full[s], (h / WG_STAGES) & 1);
       tc_fence_after();
       if (elect_one()) {
+        const uint64_t dxh0 = make_desc_k(smem_u32(sm.x_hi[s]), 128, WG_CHUNK), dxl0 = make_desc_k(smem_u32(sm.x_lo[s]), 128, WG_CHUNK);
+        const uint64_t dyh0 = make_desc_k(smem_u32(sm.y_hi[s]), 128, WG_CHUNK), dyl0 = make_desc_k(smem_u32(sm.y_lo[s]), 128, WG_CHUNK);
 #pragma unroll
-        for (int ks = 0; ks < TILE_M / 16; ++ks) {
+        for (int ks = 0; ks < WG_HALF / 16; ++ks) {
           const uint32_t ko = ks * 256;  // 16 points = 2 core matrices of 128 B
           const uint64_t dxh = desc_advance(dxh0, ko), dxl = desc_advance(dxl0, ko);
           const uint64_t dyh = desc_advance(dyh0, ko), dyl = desc_advance(dyl0, ko);
-          const uint32_t acc = (t | ks) ? 1u : 0u;
+          const uint32_t acc = (h | ks) ? 1u : 0u;
           umma_bf16(d, dxh, dyh, idesc, acc);
           if (t_hl) umma_bf16(d, dxh, dyl, idesc, 1u);
           if (t_lh) umma_bf16(d, dxl, dyh, idesc, 1u);
@@ -169,7 +209,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WJob* __rest
             if (t_lh) umma_bf16(d1, dxl, don, idesc1, 1u);
           }
         }
-        umma_commit(&sm.empty);
+        umma_commit(&sm.empty[s]);
       }
       __syncwarp();
     }

@@ -130,7 +130,10 @@ class FusedTrainStep:
             stt = self.opt.state[p]
             self.adam_table[i] = _lib.AdamTensor(P(p.data_ptr()), P(p.grad.data_ptr()), P(stt["exp_avg"].data_ptr()),
                                                  P(stt["exp_avg_sq"].data_ptr()), p.numel())
-        self.hyper_host = torch.zeros(6, pin_memory=True)
+        # hyper-parameters of the step (lr, betas, eps, weight decay, 1/world): a ring of pinned slots, copied to the device
+        # BEFORE graph A of their step.  (One slot read by a copy inside graph B raced with the host, which is already
+        # writing the next step's values while graph B of the previous step is still queued behind graph A.)
+        self.hyper_host = torch.zeros(4, 6, pin_memory=True)
         self.hyper_dev, self.adam_state = f(6), f(3)
         self.adam_state[0] = float(self.n_steps)
 
@@ -228,7 +231,6 @@ class FusedTrainStep:
         ptr = lambda t: P(t.data_ptr())
         st, lf, glob = self.st, self.loss_fn, self.out["j3d_global"]
         self.packet_dev.copy_(self.packet_host, non_blocking=True)
-        self.hyper_dev.copy_(self.hyper_host, non_blocking=True)
         _lib.check(lib.neat_junction_step(ptr(self.packet_dev), self.cap, self.G, ptr(glob), ptr(self.j2gc), ptr(self.j2g),
                                           float(lf.junction_3d_weight), float(lf.junction_2d_weight), ptr(self.jout),
                                           ptr(self.g_j3g), ptr(self.g_j2gc), self._stream()))
@@ -261,8 +263,10 @@ class FusedTrainStep:
         for k in ("rgb", "lines2d"):
             self.gt[k].copy_(gt[k].reshape(self.gt[k].shape), non_blocking=True)
         g = self.opt.param_groups[0]
-        h = self.hyper_host.numpy()
+        slot = self.hyper_host[self.n_steps % self.hyper_host.shape[0]]
+        h = slot.numpy()
         h[0], h[1], h[2], h[3], h[4], h[5] = g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], 1.0 / self.world
+        self.hyper_dev.copy_(slot, non_blocking=True)   # stream-ordered: after graph B of the previous step, before this step
         use_graphs = self.graphs and self._eager_done >= 2
         if use_graphs and self.gA is None:
             self._capture()

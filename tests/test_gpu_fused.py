@@ -41,6 +41,13 @@ def _max_abs(a, b):
     return max(float((a[n] - b[n]).abs().max()) for n in a)
 
 
+def _worst(a, b):
+    l2 = {n: float((a[n] - b[n]).norm() / b[n].norm().clamp_min(1e-12)) for n in a}
+    mx = {n: float((a[n] - b[n]).abs().max()) for n in a}
+    n2, nm = max(l2, key=l2.get), max(mx, key=mx.get)
+    return "rel-L2 %.2e in %s (%d entries), max |d| %.2e in %s" % (l2[n2], n2, b[n2].numel(), mx[nm], nm)
+
+
 def test_fused_eager_step_equals_plugin_step():
     """One optimizer step: identical loss and parameters (the fused sequence without graphs vs autograd through the plugin)."""
     _, l_p, p_p = _run("plugin", 1)
@@ -58,11 +65,16 @@ def test_graph_replay_equals_plugin_over_several_steps():
     for a, b in zip(l_p, l_g):
         assert abs(a - b) < 1e-5 * max(1.0, abs(a)), (l_p, l_g)      # measured: identical to 6 digits
     # Parameters: Adam normalises every entry's update to ~lr whatever the gradient's size, so an entry whose gradient is
-    # at the noise level of the fire-and-forget reductions (order of the REDs differs from run to run) moves by +-lr per
-    # step in either run -- two runs of the PLUGIN path differ by 9e-5 in single entries after 6 steps, plugin vs fused by
-    # 5e-4 = one lr.  Hence: per-tensor L2 agreement, and no entry further apart than two learning rates.
-    assert _rel_l2(p_g, p_p) < 2e-3
-    assert _max_abs(p_g, p_p) <= 2 * 5.0e-4 * 1.01
+    # at the noise level of the fire-and-forget reductions (order of the REDs differs from run to run) moves by up to
+    # +-lr per step in either run: two runs of the SAME path differ by up to 7e-4 = 1.5 lr in single entries after 6 steps
+    # (scripts/diag_fused_flaky.py; plugin vs fused: up to 1.1e-3 = 2.2 lr, once in ~5 runs), and a small tensor
+    # (implicit_network.lin3.bias, |b| = 0.024) by 6e-5 in L2.  Hence: per tensor ||d||_2 <= 2e-3 ||p||_2 + lr, and no entry
+    # further apart than four learning rates (a random walk of +-lr steps over 6 updates).
+    lr = 5.0e-4
+    for n in p_p:
+        d, ref = float((p_g[n] - p_p[n]).norm()), float(p_p[n].norm())
+        assert d <= 2e-3 * ref + lr, (n, d, ref, _worst(p_g, p_p))
+    assert _max_abs(p_g, p_p) <= 4 * lr, _worst(p_g, p_p)
     assert float(ts_g.adam_state[0]) == 6.0
     assert int(ts_g.rn.draw_counter[0]) == 6
     # optimizer state is torch.optim.Adam's
