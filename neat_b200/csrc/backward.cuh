@@ -342,7 +342,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
             stg128_hint(zh_at(zh, 1, e, u), make_float4(zv[4], zv[5], zv[6], zv[7]), zh_pol);
 #else
             *zh_at(zh, 0, e, u) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+#ifndef NEAT_WHATIF_ZHAT_HALF
             *zh_at(zh, 1, e, u) = make_float4(zv[4], zv[5], zv[6], zv[7]);
+#endif
 #endif
             store_a8_save<false>(sm.a_hi, sm.a_lo, psave, e.row, c, q);
           }
@@ -404,7 +406,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_bwd_kernel(const __grid_co
             z1[k] = ldg128_hint(zh_at(zh, 1, e, u), zh_pol);
 #else
             z0[k] = *zh_at(zh, 0, e, u);  // written by this very thread in the tangent sweep
+#ifndef NEAT_WHATIF_ZHAT_HALF
             z1[k] = *zh_at(zh, 1, e, u);
+#else
+            z1[k] = z0[k];
+#endif
 #endif
           }
         };

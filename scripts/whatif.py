@@ -27,6 +27,8 @@ def set_flags(f):
 def timing(R, flag_sets, beta=0.1, n=10):
     ps = TR.TrainStep(synth.dtu_conf(), device=dev, seed=42, beta=beta)
     rn = ps.model._get_renderer()
+    if os.environ.get("NEAT_GRID_CAP"):
+        rn.ctx.debug_grid_cap(int(os.environ["NEAT_GRID_CAP"]))
     inp, gt = TR.to_device(TR.host_batch(R, seed=1), dev)
     for _ in range(3):
         ps.step(inp, gt)
