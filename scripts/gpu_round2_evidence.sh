@@ -18,3 +18,8 @@ ls -la gpurun_out/*.ncu-rep gpurun_out/*.csv
 # the benchmarked path (FusedTrainStep: two CUDA-graph replays per step): launch list of the last step
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/fused_launches.csv python scripts/profile_fused.py 1024 5 > gpurun_out/fused_ncu.log 2>&1
 tail -1 gpurun_out/fused_ncu.log
+timeout 600 compute-sanitizer --tool initcheck --print-limit 60 python scripts/sanitize_step.py 64 > gpurun_out/sanitizer_initcheck.log 2>&1
+grep -E "ERROR SUMMARY" gpurun_out/sanitizer_initcheck.log
+# the driver's two arms
+python bench.py --steps 20 --warmup 5 > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_final_reference.json 2> /dev/null
