@@ -37,3 +37,30 @@ print("max |d| over shared loss terms:", max(abs(ours[k] - ref[k]) for k in ours
 for k in ("rgb_values", "lines3d", "lines2d_calib", "grad_theta"):
     a, b = out[k].detach().float().cpu(), o2[k].detach().float().cpu()
     print(k, "rel err %.2e" % float((a - b).abs().max() / b.abs().max()))
+
+pa, pb = out["points"].detach().float().cpu(), o2["points"].detach().float().cpu()
+dz = (pa - pb).norm(dim=-1)                       # [R,S] distance between corresponding sample points
+print("rays whose samples differ by > 1e-4 somewhere: %d of %d; samples moved: %.3f %%" % (
+    int((dz.max(dim=1).values > 1e-4).sum()), dz.shape[0], 100.0 * float((dz > 1e-4).float().mean())))
+# ---- parameter gradients of that step, both implementations (sampler decisions of a few rays differ, see grad_theta)
+ps.bucket.zero()
+lo["loss"].backward()
+model.zero_grad()
+l2["loss"].backward()
+torch.cuda.synchronize()
+mine = dict(ps.model.named_parameters())
+worst = {}
+for n, p in model.named_parameters():
+    if p.grad is None or mine[n].grad is None:
+        continue
+    a, b = mine[n].grad.detach().double().cpu(), p.grad.detach().double().cpu()
+    if float(b.norm()) == 0.0:
+        continue
+    net = n.split(".")[0]
+    l2e, mxe = float((a - b).norm() / b.norm()), float((a - b).abs().max() / b.abs().max())
+    w = worst.setdefault(net, [0.0, 0.0, ""])
+    if l2e > w[0]:
+        w[0], w[2] = l2e, n
+    w[1] = max(w[1], mxe)
+for net, (l2e, mxe, n) in worst.items():
+    print("grad vs reference  %-20s worst rel-L2 %.2e (%s)  worst max-rel %.2e" % (net, l2e, n, mxe))
